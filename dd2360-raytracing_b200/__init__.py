@@ -1,0 +1,250 @@
+"""dd2360-raytracing_b200 — host-side mirror of the reference's render path over librt_b200.so (sm_100a CUDA).
+
+The compute lives in hand-written CUDA behind the C ABI of include/rt_abi.h; this module only binds it with
+ctypes and mirrors the call sequence of the reference's main() (main.cu:347-477):
+
+    rt = RayTracer(device=0)
+    rt.create_world(n=488, radius=0.1)          # rand_init + create_world          main.cu:388,399
+    rt.build_octree(spheres_per_leaf=30)        # D2H + buildOctree + H2D           main.cu:405-415
+    fb = rt.render(nx, ny, ns, use_octree=True) # render_init + render              main.cu:424-429
+    ppm = format_ppm(fb)                        # output_to_stream                  main.cu:321-333
+
+There is NO CPU fallback: importing works anywhere (so CPU-only CI can check the ABI surface), but every compute
+call needs the built library and a CUDA device and raises otherwise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "librt_b200.so")
+INCLUDE_DIR = os.path.normpath(os.path.join(HERE, "..", "include"))
+
+MAT_NONE, MAT_LAMBERTIAN, MAT_METAL, MAT_DIELECTRIC = -1, 0, 1, 2
+SEED_HEAD, SEED_UPSTREAM = 0, 1
+SHARD_NONE, SHARD_TILES, SHARD_SPP = 0, 1, 2
+
+SPHERE_DTYPE = np.dtype(
+    [("cx", "<f4"), ("cy", "<f4"), ("cz", "<f4"), ("radius", "<f4"), ("mat", "<i4"),
+     ("ax", "<f4"), ("ay", "<f4"), ("az", "<f4"), ("param", "<f4")]
+)
+
+# every symbol include/rt_abi.h declares (tests check the library exports exactly these)
+ABI_SYMBOLS = [
+    "rt_abi_version", "rt_create", "rt_destroy", "rt_last_error", "rt_set_stream", "rt_device_info",
+    "rt_scene_generate", "rt_scene_upload", "rt_scene_download", "rt_scene_size", "rt_camera_set", "rt_camera_get",
+    "rt_octree_build", "rt_octree_reference_bytes", "rt_octree_export_reference",
+    "rt_render_accumulate", "rt_finalize", "rt_render", "rt_render_to_host", "rt_format_ppm",
+    "rt_malloc", "rt_free", "rt_memcpy_to_host", "rt_synchronize",
+]
+
+
+class OctreeStats(C.Structure):
+    _fields_ = [("node_count", C.c_int32), ("leaf_count", C.c_int32), ("entries", C.c_int64),
+                ("dropped_full", C.c_int64), ("dropped_outside", C.c_int64), ("fine_voxels", C.c_int64),
+                ("fine_refs", C.c_int64), ("build_ms", C.c_float)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+class RenderArgs(C.Structure):
+    _fields_ = [("nx", C.c_int32), ("ny", C.c_int32), ("ns", C.c_int32), ("max_depth", C.c_int32),
+                ("use_octree", C.c_int32), ("seed_mode", C.c_int32), ("shard_mode", C.c_int32),
+                ("shard_rank", C.c_int32), ("shard_count", C.c_int32), ("reserved", C.c_int32 * 7)]
+
+
+class RenderStats(C.Structure):
+    _fields_ = [("rays", C.c_uint64), ("paths", C.c_uint64), ("sphere_tests", C.c_uint64), ("node_tests", C.c_uint64),
+                ("kernel_ms", C.c_float), ("launches", C.c_int32)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+class CameraDesc(C.Structure):
+    _fields_ = [("lookfrom", C.c_float * 3), ("lookat", C.c_float * 3), ("vup", C.c_float * 3),
+                ("vfov", C.c_float), ("aspect", C.c_float), ("aperture", C.c_float), ("focus_dist", C.c_float)]
+
+
+class RtError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load_library(path: str | None = None) -> C.CDLL:
+    """dlopen librt_b200.so and declare the ABI.  Fails loudly when the extension has not been built."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = path or LIB_PATH
+    if not os.path.exists(p):
+        raise RtError(f"{p} is missing: build it with `python dd2360-raytracing_b200/build.py` "
+                      f"(nvcc, sm_100a). There is no CPU fallback.")
+    L = C.CDLL(p)
+    vp, i32, f32, sz = C.c_void_p, C.c_int, C.c_float, C.c_size_t
+    sig = {
+        "rt_abi_version": (i32, []),
+        "rt_create": (i32, [i32, C.POINTER(vp)]),
+        "rt_destroy": (None, [vp]),
+        "rt_last_error": (C.c_char_p, [vp]),
+        "rt_set_stream": (i32, [vp, vp]),
+        "rt_device_info": (i32, [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(sz)]),
+        "rt_scene_generate": (i32, [vp, i32, f32]),
+        "rt_scene_upload": (i32, [vp, vp, i32]),
+        "rt_scene_download": (i32, [vp, vp, i32]),
+        "rt_scene_size": (i32, [vp]),
+        "rt_camera_set": (i32, [vp, C.POINTER(CameraDesc), i32, i32]),
+        "rt_camera_get": (i32, [vp, vp]),
+        "rt_octree_build": (i32, [vp, i32, C.POINTER(OctreeStats)]),
+        "rt_octree_reference_bytes": (sz, [i32]),
+        "rt_octree_export_reference": (i32, [vp, vp, sz]),
+        "rt_render_accumulate": (i32, [vp, C.POINTER(RenderArgs), vp, C.POINTER(RenderStats)]),
+        "rt_finalize": (i32, [vp, vp, vp, i32, i32, i32]),
+        "rt_render": (i32, [vp, C.POINTER(RenderArgs), vp, C.POINTER(RenderStats)]),
+        "rt_render_to_host": (i32, [vp, C.POINTER(RenderArgs), vp, C.POINTER(RenderStats)]),
+        "rt_format_ppm": (sz, [vp, i32, i32, vp, sz]),
+        "rt_malloc": (i32, [vp, sz, C.POINTER(vp)]),
+        "rt_free": (i32, [vp, vp]),
+        "rt_memcpy_to_host": (i32, [vp, vp, vp, sz]),
+        "rt_synchronize": (i32, [vp]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(L, name)
+        fn.restype = res
+        fn.argtypes = args
+    if path is None:
+        _lib = L
+    return L
+
+
+def format_ppm(fb: np.ndarray) -> bytes:
+    """output_to_stream (main.cu:321-333): P3 text, byte-identical to the reference writer."""
+    L = load_library()
+    fb = np.ascontiguousarray(fb, dtype=np.float32)
+    ny, nx, _ = fb.shape
+    need = L.rt_format_ppm(fb.ctypes.data, nx, ny, None, 0)
+    buf = C.create_string_buffer(need)
+    L.rt_format_ppm(fb.ctypes.data, nx, ny, buf, need)
+    return buf.raw[:need]
+
+
+def quantise(fb: np.ndarray) -> np.ndarray:
+    """int(255.99 * channel) in PPM row order (top row first), as uint8 [ny, nx, 3]."""
+    q = (255.99 * fb.astype(np.float64)).astype(np.int64)
+    return np.clip(q[::-1], 0, 255).astype(np.uint8)
+
+
+class RayTracer:
+    """One context per GPU: mirrors the reference's main() call sequence over the C ABI."""
+
+    def __init__(self, device: int = 0):
+        self.L = load_library()
+        self._ctx = C.c_void_p()
+        rc = self.L.rt_create(device, C.byref(self._ctx))
+        if rc != 0:
+            raise RtError(f"rt_create(device={device}) failed with code {rc}: no usable CUDA device "
+                          f"(this library has no CPU fallback)")
+        self.device = device
+        self.n = 0
+        self.spl = None
+
+    # -- plumbing --
+    def _ck(self, rc: int, what: str):
+        if rc != 0:
+            msg = self.L.rt_last_error(self._ctx)
+            raise RtError(f"{what} failed ({rc}): {msg.decode() if msg else ''}")
+
+    def close(self):
+        if self._ctx:
+            self.L.rt_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, cuda_stream_handle: int | None):
+        self._ck(self.L.rt_set_stream(self._ctx, C.c_void_p(cuda_stream_handle or 0)), "rt_set_stream")
+
+    def device_info(self):
+        sm, clk, mem = C.c_int(), C.c_int(), C.c_size_t()
+        self._ck(self.L.rt_device_info(self._ctx, C.byref(sm), C.byref(clk), C.byref(mem)), "rt_device_info")
+        return {"sm_count": sm.value, "clock_khz": clk.value, "mem_bytes": mem.value}
+
+    # -- scene (main.cu:388-401) --
+    def create_world(self, n: int, radius: float = 0.1):
+        self._ck(self.L.rt_scene_generate(self._ctx, n, radius), "rt_scene_generate")
+        self.n = n
+        return self
+
+    def upload_world(self, spheres: np.ndarray):
+        spheres = np.ascontiguousarray(spheres, dtype=SPHERE_DTYPE)
+        self._ck(self.L.rt_scene_upload(self._ctx, spheres.ctypes.data, len(spheres)), "rt_scene_upload")
+        self.n = len(spheres)
+        return self
+
+    def spheres(self) -> np.ndarray:
+        out = np.zeros(self.n, dtype=SPHERE_DTYPE)
+        self._ck(self.L.rt_scene_download(self._ctx, out.ctypes.data, self.n), "rt_scene_download")
+        return out
+
+    def set_camera(self, nx: int, ny: int, desc: CameraDesc | None = None):
+        self._ck(self.L.rt_camera_set(self._ctx, C.byref(desc) if desc else None, nx, ny), "rt_camera_set")
+
+    def camera(self) -> np.ndarray:
+        out = np.zeros(22, dtype=np.float32)
+        self._ck(self.L.rt_camera_get(self._ctx, out.ctypes.data), "rt_camera_get")
+        return out
+
+    # -- octree (main.cu:405-415) --
+    def build_octree(self, spheres_per_leaf: int = 30) -> dict:
+        st = OctreeStats()
+        self._ck(self.L.rt_octree_build(self._ctx, spheres_per_leaf, C.byref(st)), "rt_octree_build")
+        self.spl = spheres_per_leaf
+        return st.as_dict()
+
+    def export_octree(self) -> np.ndarray:
+        n = self.L.rt_octree_reference_bytes(self.spl)
+        blob = np.zeros(n, dtype=np.uint8)
+        self._ck(self.L.rt_octree_export_reference(self._ctx, blob.ctypes.data, n), "rt_octree_export_reference")
+        return blob
+
+    # -- render (main.cu:424-429) --
+    @staticmethod
+    def args(nx, ny, ns, use_octree, max_depth=50, shard_mode=SHARD_NONE, shard_rank=0, shard_count=1,
+             seed_mode=SEED_HEAD) -> RenderArgs:
+        return RenderArgs(nx, ny, ns, max_depth, int(bool(use_octree)), seed_mode, shard_mode, shard_rank, shard_count)
+
+    def render(self, nx, ny, ns, use_octree=True, **kw):
+        """Whole frame with a HOST destination (render + device->host copy).  Returns (fb[ny,nx,3], stats)."""
+        a = self.args(nx, ny, ns, use_octree, **kw)
+        fb = np.empty((ny, nx, 3), dtype=np.float32)
+        st = RenderStats()
+        self._ck(self.L.rt_render_to_host(self._ctx, C.byref(a), fb.ctypes.data, C.byref(st)), "rt_render_to_host")
+        return fb, st.as_dict()
+
+    def render_device(self, args: RenderArgs, fb_dev_ptr: int, want_stats=True):
+        st = RenderStats()
+        self._ck(self.L.rt_render(self._ctx, C.byref(args), C.c_void_p(fb_dev_ptr), C.byref(st) if want_stats else None),
+                 "rt_render")
+        return st.as_dict() if want_stats else None
+
+    def render_accumulate(self, args: RenderArgs, accum_dev_ptr: int, want_stats=True):
+        st = RenderStats()
+        self._ck(self.L.rt_render_accumulate(self._ctx, C.byref(args), C.c_void_p(accum_dev_ptr),
+                                             C.byref(st) if want_stats else None), "rt_render_accumulate")
+        return st.as_dict() if want_stats else None
+
+    def finalize(self, accum_dev_ptr: int, fb_dev_ptr: int, nx, ny, ns):
+        self._ck(self.L.rt_finalize(self._ctx, C.c_void_p(accum_dev_ptr), C.c_void_p(fb_dev_ptr), nx, ny, ns), "rt_finalize")
+
+    def synchronize(self):
+        self._ck(self.L.rt_synchronize(self._ctx), "rt_synchronize")

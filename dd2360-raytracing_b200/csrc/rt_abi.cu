@@ -1,0 +1,487 @@
+// rt_abi.cu — implementation of the C ABI in include/rt_abi.h (context, scene, camera, build, render, output).
+// There is no CPU fallback anywhere in this library: every compute entry point launches CUDA kernels.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/rt_abi.h"
+#include "rt_math.cuh"
+#include "rt_octree.h"
+#include "rt_render.h"
+
+using namespace rt;
+
+struct rt_context {
+    int device = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaDeviceProp prop{};
+    std::string err;
+    // scene
+    int n = 0;
+    std::vector<rt_sphere_desc> host_scene;
+    float4 *geom = nullptr, *matl = nullptr;
+    int *tag = nullptr;
+    size_t scene_cap = 0;
+    // camera
+    bool have_camera = false;
+    int cam_nx = 0, cam_ny = 0;
+    CameraData *cam_dev = nullptr;
+    CameraData cam_host{};
+    // octree
+    OctreeBuilder *octree = nullptr;
+    float grid_density = 4.0f;
+    // render scratch
+    uint32_t *work_counter = nullptr;
+    unsigned long long *counters = nullptr;
+    float *scratch_fb = nullptr;
+    size_t scratch_fb_bytes = 0;
+    float *pinned = nullptr;
+    size_t pinned_bytes = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+static int fail(rt_context *ctx, int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->err = buf;
+    return code;
+}
+static int cuda_fail(rt_context *ctx, cudaError_t e, const char *what) {
+    return fail(ctx, (int)e, "CUDA error = %u at %s '%s'", (unsigned)e, what, cudaGetErrorString(e));
+}
+#define CK(call)                                              \
+    do {                                                      \
+        cudaError_t e_ = (call);                              \
+        if (e_ != cudaSuccess) return cuda_fail(ctx, e_, #call); \
+    } while (0)
+
+extern "C" int rt_abi_version(void) { return RT_ABI_VERSION; }
+
+extern "C" int rt_create(int device, rt_context **out) {
+    if (!out) return RT_ERR_INVALID;
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count <= 0) return e != cudaSuccess ? (int)e : (int)cudaErrorNoDevice;   // no CPU fallback
+    if (device < 0 || device >= count) return RT_ERR_INVALID;
+    rt_context *ctx = new rt_context();
+    ctx->device = device;
+    if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaGetDeviceProperties(&ctx->prop, device)) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaEventCreate(&ctx->ev0)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev1)) != cudaSuccess ||
+        (e = cudaMalloc(&ctx->work_counter, 4)) != cudaSuccess || (e = cudaMalloc(&ctx->counters, 8 * 8)) != cudaSuccess ||
+        (e = cudaMalloc(&ctx->cam_dev, sizeof(CameraData))) != cudaSuccess) {
+        delete ctx;
+        return (int)e;
+    }
+    ctx->stream = ctx->own_stream;
+    ctx->octree = new OctreeBuilder();
+    const char *dens = getenv("RT_GRID_DENSITY");
+    if (dens && atof(dens) > 0) ctx->grid_density = (float)atof(dens);
+    *out = ctx;
+    return RT_OK;
+}
+
+extern "C" void rt_destroy(rt_context *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    delete ctx->octree;
+    cudaFree(ctx->geom); cudaFree(ctx->matl); cudaFree(ctx->tag); cudaFree(ctx->cam_dev);
+    cudaFree(ctx->work_counter); cudaFree(ctx->counters); cudaFree(ctx->scratch_fb);
+    if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+}
+
+extern "C" const char *rt_last_error(const rt_context *ctx) { return ctx ? ctx->err.c_str() : "no context"; }
+
+extern "C" int rt_set_stream(rt_context *ctx, void *s) {
+    if (!ctx) return RT_ERR_INVALID;
+    ctx->stream = s ? (cudaStream_t)s : ctx->own_stream;
+    return RT_OK;
+}
+
+extern "C" int rt_device_info(const rt_context *ctx, int *sm_count, int *clock_khz, size_t *mem_bytes) {
+    if (!ctx) return RT_ERR_INVALID;
+    if (sm_count) *sm_count = ctx->prop.multiProcessorCount;
+    if (clock_khz) *clock_khz = ctx->prop.clockRate;
+    if (mem_bytes) *mem_bytes = ctx->prop.totalGlobalMem;
+    return RT_OK;
+}
+
+// ---- scene ------------------------------------------------------------------------------------------------------
+// main.cu:146-181.  The generator is one sequential XORWOW stream (seed 1984, curand_init(1984,0,0), main.cu:80),
+// so it runs on the host and the result is uploaded as SoA; arguments are drawn left to right as the device
+// evaluates them.  No device heap, no per-sphere `new`.
+static void generate_world(int n, float radius, std::vector<rt_sphere_desc> &out) {
+    out.assign((size_t)n, rt_sphere_desc{0, 0, 0, 0, RT_MAT_NONE, 0, 0, 0, 0});
+    if (n < 4) return;
+    xorwow rng;
+    xorwow_seed(rng, 1984ull);
+    auto RND = [&]() { return xorwow_uniform(rng); };
+    out[0] = rt_sphere_desc{0.f, -1000.f, -1.f, 1000.f, RT_MAT_LAMBERTIAN, 0.5f, 0.5f, 0.5f, 0.f};
+    int i = 1;
+    out[i++] = rt_sphere_desc{0.f, 1.f, 0.f, 1.f, RT_MAT_DIELECTRIC, 0.f, 0.f, 0.f, 1.5f};
+    out[i++] = rt_sphere_desc{-4.f, 1.f, 0.f, 1.f, RT_MAT_LAMBERTIAN, 0.4f, 0.2f, 0.1f, 0.f};
+    out[i++] = rt_sphere_desc{4.f, 1.f, 0.f, 1.f, RT_MAT_METAL, 0.7f, 0.6f, 0.5f, 0.f};
+    const int spheres_per_dim = (int)sqrtf((float)n - 4);     // main.cu:160
+    const double spacing = 20. / spheres_per_dim;              // main.cu:161
+    for (double a = -10; a < 10; a += spacing) {
+        for (double b = -10; b < 10 && i < n; b += spacing) {
+            const float choose_mat = RND();
+            rt_sphere_desc s{};
+            s.cx = (float)(a + (double)RND());
+            s.cy = radius;
+            s.cz = (float)(b + (double)RND());
+            s.radius = radius;
+            if (choose_mat < 0.8f) {
+                s.mat = RT_MAT_LAMBERTIAN;
+                const float q0 = RND(), q1 = RND(), q2 = RND(), q3 = RND(), q4 = RND(), q5 = RND();
+                s.ax = q0 * q1; s.ay = q2 * q3; s.az = q4 * q5;
+            } else if (choose_mat < 0.95f) {
+                s.mat = RT_MAT_METAL;
+                const float q0 = RND(), q1 = RND(), q2 = RND(), q3 = RND();
+                s.ax = 0.5f * (1.0f + q0); s.ay = 0.5f * (1.0f + q1); s.az = 0.5f * (1.0f + q2);
+                const float f = 0.5f * q3;
+                s.param = f < 1.0f ? f : 1.0f;                  // material.h:67
+            } else {
+                s.mat = RT_MAT_DIELECTRIC;
+                s.param = 1.5f;
+            }
+            out[i++] = s;
+        }
+    }
+}
+
+static int upload_scene(rt_context *ctx) {
+    const int n = ctx->n;
+    if ((size_t)n > ctx->scene_cap) {
+        cudaFree(ctx->geom); cudaFree(ctx->matl); cudaFree(ctx->tag);
+        ctx->geom = ctx->matl = nullptr; ctx->tag = nullptr; ctx->scene_cap = 0;
+        CK(cudaMalloc(&ctx->geom, (size_t)n * sizeof(float4)));
+        CK(cudaMalloc(&ctx->matl, (size_t)n * sizeof(float4)));
+        CK(cudaMalloc(&ctx->tag, (size_t)n * sizeof(int)));
+        ctx->scene_cap = (size_t)n;
+    }
+    std::vector<float4> g((size_t)n), m((size_t)n);
+    std::vector<int> t((size_t)n);
+    for (int i = 0; i < n; i++) {
+        const rt_sphere_desc &s = ctx->host_scene[(size_t)i];
+        g[(size_t)i] = make_float4(s.cx, s.cy, s.cz, s.radius);
+        m[(size_t)i] = make_float4(s.ax, s.ay, s.az, s.param);
+        t[(size_t)i] = s.mat;
+    }
+    CK(cudaMemcpyAsync(ctx->geom, g.data(), (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->matl, m.data(), (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->tag, t.data(), (size_t)n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));   // the staging vectors die here
+    ctx->octree->built = false;
+    return RT_OK;
+}
+
+extern "C" int rt_scene_generate(rt_context *ctx, int n, float radius) {
+    if (!ctx || n < 4) return fail(ctx, RT_ERR_INVALID, "rt_scene_generate: n must be >= 4");
+    CK(cudaSetDevice(ctx->device));
+    ctx->n = n;
+    generate_world(n, radius, ctx->host_scene);
+    return upload_scene(ctx);
+}
+
+extern "C" int rt_scene_upload(rt_context *ctx, const rt_sphere_desc *spheres, int n) {
+    if (!ctx || !spheres || n < 1) return fail(ctx, RT_ERR_INVALID, "rt_scene_upload: bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    ctx->n = n;
+    ctx->host_scene.assign(spheres, spheres + n);
+    for (auto &s : ctx->host_scene)
+        if (s.mat == RT_MAT_METAL && !(s.param < 1.0f)) s.param = 1.0f;   // metal::metal clamps fuzz (material.h:67)
+    return upload_scene(ctx);
+}
+
+extern "C" int rt_scene_download(rt_context *ctx, rt_sphere_desc *out, int n) {
+    if (!ctx || !out || n != ctx->n) return fail(ctx, RT_ERR_INVALID, "rt_scene_download: n does not match the scene");
+    memcpy(out, ctx->host_scene.data(), (size_t)n * sizeof(rt_sphere_desc));
+    return RT_OK;
+}
+
+extern "C" int rt_scene_size(const rt_context *ctx) { return ctx ? ctx->n : 0; }
+
+// ---- camera -----------------------------------------------------------------------------------------------------
+// camera.h:22-44 evaluated on the device (same libdevice tanf as the reference).  In the reference every argument
+// but the aspect ratio is a compile-time constant, so nvcc folds w, u, v with one rounding per operation; the
+// aspect-dependent part keeps the fused form seen in the SASS.
+__global__ void k_camera_setup(rt_camera_desc c, CameraData *out) {
+    const float lens_radius = __fdiv_rn(c.aperture, 2.0f);
+    const float theta = __fdiv_rn(__fmul_rn(c.vfov, 3.14159265358979323846f), 180.0f);
+    const float arg = __fdiv_rn(theta, 2.0f);
+    const float half_height = tanf(arg);
+    const float half_width = __fmul_rn(c.aspect, half_height);
+    float w[3], u[3], v[3];
+    {
+        const float d[3] = {__fsub_rn(c.lookfrom[0], c.lookat[0]), __fsub_rn(c.lookfrom[1], c.lookat[1]),
+                            __fsub_rn(c.lookfrom[2], c.lookat[2])};
+        const float l = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(d[0], d[0]), __fmul_rn(d[1], d[1])), __fmul_rn(d[2], d[2])));
+        for (int k = 0; k < 3; k++) w[k] = __fdiv_rn(d[k], l);
+        // cross(vup, w): vec3.h:95-99
+        const float cx = __fsub_rn(__fmul_rn(c.vup[1], w[2]), __fmul_rn(c.vup[2], w[1]));
+        const float cy = -__fsub_rn(__fmul_rn(c.vup[0], w[2]), __fmul_rn(c.vup[2], w[0]));
+        const float cz = __fsub_rn(__fmul_rn(c.vup[0], w[1]), __fmul_rn(c.vup[1], w[0]));
+        const float lc = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(cx, cx), __fmul_rn(cy, cy)), __fmul_rn(cz, cz)));
+        u[0] = __fdiv_rn(cx, lc); u[1] = __fdiv_rn(cy, lc); u[2] = __fdiv_rn(cz, lc);
+        v[0] = __fsub_rn(__fmul_rn(w[1], u[2]), __fmul_rn(w[2], u[1]));
+        v[1] = -__fsub_rn(__fmul_rn(w[0], u[2]), __fmul_rn(w[2], u[0]));
+        v[2] = __fsub_rn(__fmul_rn(w[0], u[1]), __fmul_rn(w[1], u[0]));
+    }
+    const float hw = __fmul_rn(half_width, c.focus_dist), hh = __fmul_rn(half_height, c.focus_dist);
+    const float h2 = __fmul_rn(__fmul_rn(2.0f, half_width), c.focus_dist);
+    const float v2 = __fmul_rn(__fmul_rn(2.0f, half_height), c.focus_dist);
+    for (int k = 0; k < 3; k++) {
+        out->origin[k] = c.lookfrom[k];
+        out->u[k] = u[k]; out->v[k] = v[k]; out->w[k] = w[k];
+        float t = __fmaf_rn(-hw, u[k], c.lookfrom[k]);
+        t = __fmaf_rn(-hh, v[k], t);
+        out->lower_left_corner[k] = __fsub_rn(t, __fmul_rn(c.focus_dist, w[k]));
+        out->horizontal[k] = __fmul_rn(h2, u[k]);
+        out->vertical[k] = __fmul_rn(v2, v[k]);
+    }
+    out->lens_radius = lens_radius;
+}
+
+extern "C" int rt_camera_set(rt_context *ctx, const rt_camera_desc *desc, int nx, int ny) {
+    if (!ctx || nx < 1 || ny < 1) return fail(ctx, RT_ERR_INVALID, "rt_camera_set: bad image size");
+    CK(cudaSetDevice(ctx->device));
+    rt_camera_desc c;
+    if (desc) {
+        c = *desc;
+    } else {   // main.cu:192-202
+        const float lf[3] = {13, 2, 3}, la[3] = {0, 0, 0}, up[3] = {0, 1, 0};
+        memcpy(c.lookfrom, lf, sizeof lf); memcpy(c.lookat, la, sizeof la); memcpy(c.vup, up, sizeof up);
+        c.vfov = 30.0f;
+        c.aspect = (float)nx / (float)ny;
+        c.aperture = 0.1f;
+        c.focus_dist = 10.0f;
+    }
+    k_camera_setup<<<1, 1, 0, ctx->stream>>>(c, ctx->cam_dev);
+    CK(cudaGetLastError());
+    CK(upload_camera_from_device(ctx->cam_dev, ctx->stream));
+    CK(cudaMemcpyAsync(&ctx->cam_host, ctx->cam_dev, sizeof(CameraData), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->have_camera = true;
+    ctx->cam_nx = nx; ctx->cam_ny = ny;
+    return RT_OK;
+}
+
+extern "C" int rt_camera_get(rt_context *ctx, float out22[22]) {
+    if (!ctx || !out22 || !ctx->have_camera) return fail(ctx, RT_ERR_STATE, "rt_camera_get: no camera set");
+    memcpy(out22, &ctx->cam_host, 22 * sizeof(float));
+    return RT_OK;
+}
+
+// ---- octree -----------------------------------------------------------------------------------------------------
+extern "C" int rt_octree_build(rt_context *ctx, int spl, rt_octree_stats *stats) {
+    if (!ctx || spl < 1) return fail(ctx, RT_ERR_INVALID, "rt_octree_build: SPHERES_PER_LEAF must be >= 1");
+    if (ctx->n < 1) return fail(ctx, RT_ERR_STATE, "rt_octree_build: no scene");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    CK(ctx->octree->build(ctx->stream, ctx->geom, ctx->tag, ctx->n, spl, ctx->grid_density));
+    CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    CK(cudaEventSynchronize(ctx->ev1));
+    if (stats) {
+        memset(stats, 0, sizeof *stats);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+        stats->build_ms = ms;
+        stats->node_count = ctx->octree->counts.node_count;
+        stats->entries = (int64_t)ctx->octree->stats_h[0];
+        stats->dropped_full = (int64_t)ctx->octree->stats_h[1];
+        stats->dropped_outside = (int64_t)ctx->octree->stats_h[2];
+        stats->fine_voxels = ctx->octree->counts.total_voxels;
+        stats->fine_refs = ctx->octree->total_refs;
+        stats->leaf_count = 0;   // known once the reference layout is exported
+    }
+    return RT_OK;
+}
+
+extern "C" size_t rt_octree_reference_bytes(int spl) { return OctreeBuilder::reference_bytes(spl); }
+
+extern "C" int rt_octree_export_reference(rt_context *ctx, void *host_blob, size_t bytes) {
+    if (!ctx || !host_blob) return RT_ERR_INVALID;
+    if (!ctx->octree->built) return fail(ctx, RT_ERR_STATE, "rt_octree_export_reference: build the octree first");
+    CK(cudaSetDevice(ctx->device));
+    CK(ctx->octree->export_reference(ctx->stream, host_blob, bytes));
+    return RT_OK;
+}
+
+// ---- render -----------------------------------------------------------------------------------------------------
+static int do_render(rt_context *ctx, const rt_render_args *a, float *out_dev, bool finalize, rt_render_stats *stats) {
+    if (!ctx || !a || !out_dev) return fail(ctx, RT_ERR_INVALID, "render: null argument");
+    if (a->nx < 1 || a->ny < 1 || a->ns < 1) return fail(ctx, RT_ERR_INVALID, "render: bad nx/ny/ns");
+    if (ctx->n < 1) return fail(ctx, RT_ERR_STATE, "render: no scene (rt_scene_generate / rt_scene_upload first)");
+    if (a->use_octree && !ctx->octree->built) return fail(ctx, RT_ERR_STATE, "render: USE_OCTREE set but no octree built");
+    if (a->seed_mode != RT_SEED_HEAD)
+        return fail(ctx, RT_ERR_UNSUPPORTED, "render: only the HEAD seeding curand_init(1984+pixel_index,0,0) is implemented");
+    CK(cudaSetDevice(ctx->device));
+    if (!ctx->have_camera || ctx->cam_nx != a->nx || ctx->cam_ny != a->ny) {
+        const int rc = rt_camera_set(ctx, nullptr, a->nx, a->ny);
+        if (rc) return rc;
+    }
+    const int count = a->shard_mode == RT_SHARD_NONE ? 1 : (a->shard_count < 1 ? 1 : a->shard_count);
+    const int rank = a->shard_mode == RT_SHARD_NONE ? 0 : a->shard_rank;
+    if (rank < 0 || rank >= count) return fail(ctx, RT_ERR_INVALID, "render: shard_rank out of range");
+    if (finalize && count > 1) return fail(ctx, RT_ERR_INVALID, "render: a sharded frame must go through rt_render_accumulate");
+
+    RenderLaunch p;
+    memset(&p, 0, sizeof p);
+    p.scene.geom = ctx->geom; p.scene.matl = ctx->matl; p.scene.tag = ctx->tag; p.scene.n = ctx->n;
+    if (a->use_octree) p.tree = ctx->octree->view();
+    p.nx = a->nx; p.ny = a->ny;
+    p.ns_total = a->ns;
+    p.ns_local = a->ns;
+    p.max_depth = a->max_depth > 0 ? a->max_depth : 50;
+    p.tiles_x = (a->nx + 7) / 8;
+    const long long tiles_y = (a->ny + 3) / 4;
+    const long long ntiles = (long long)p.tiles_x * tiles_y;
+    p.tile_first = 0; p.tile_stride = 1;
+    long long owned = ntiles;
+    const size_t fb_bytes = (size_t)a->nx * a->ny * 3 * sizeof(float);
+    if (a->shard_mode == RT_SHARD_TILES && count > 1) {
+        p.tile_first = rank; p.tile_stride = count;
+        owned = (ntiles - rank + count - 1) / count;
+        CK(cudaMemsetAsync(out_dev, 0, fb_bytes, ctx->stream));       // pixels of other shards stay 0 so shards add up
+    } else if (a->shard_mode == RT_SHARD_SPP && count > 1) {
+        p.ns_local = a->ns / count + (rank < a->ns % count ? 1 : 0);
+        // shard g draws from streams seeded 1984 + pixel_index + g*num_pixels: distinct seeds, the reference's own
+        // convention for independent streams (main.cu:91-93); g = 0 is the reference stream
+        p.seed_offset = (unsigned long long)rank * (unsigned long long)a->nx * (unsigned long long)a->ny;
+        if (p.ns_local == 0) {
+            CK(cudaMemsetAsync(out_dev, 0, fb_bytes, ctx->stream));
+            if (stats) memset(stats, 0, sizeof *stats);
+            return RT_OK;
+        }
+    }
+    if (owned * 32 > 0xfffffff0ll) return fail(ctx, RT_ERR_INVALID, "render: image too large for the 32-bit work queue");
+    p.total_items = (uint32_t)(owned * 32);
+    p.finalize = finalize ? 1 : 0;
+    p.out = out_dev;
+    p.work_counter = ctx->work_counter;
+    p.counters = ctx->counters;
+    CK(cudaMemsetAsync(ctx->counters, 0, 8 * 8, ctx->stream));
+    int blocks = 0;
+    CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    CK(launch_render(p, a->use_octree != 0, ctx->prop.multiProcessorCount, ctx->prop.sharedMemPerBlockOptin, ctx->stream, &blocks));
+    CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    if (stats) {
+        unsigned long long c[2] = {0, 0};
+        CK(cudaMemcpyAsync(c, ctx->counters, sizeof c, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaEventSynchronize(ctx->ev1));
+        CK(cudaStreamSynchronize(ctx->stream));
+        memset(stats, 0, sizeof *stats);
+        stats->rays = c[0]; stats->paths = c[1];
+        float ms = 0;
+        cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+        stats->kernel_ms = ms;
+        stats->launches = 1;
+    }
+    return RT_OK;
+}
+
+extern "C" int rt_render_accumulate(rt_context *ctx, const rt_render_args *args, float *accum_dev, rt_render_stats *stats) {
+    return do_render(ctx, args, accum_dev, false, stats);
+}
+
+extern "C" int rt_render(rt_context *ctx, const rt_render_args *args, float *fb_dev, rt_render_stats *stats) {
+    return do_render(ctx, args, fb_dev, true, stats);
+}
+
+extern "C" int rt_finalize(rt_context *ctx, const float *accum_dev, float *fb_dev, int nx, int ny, int ns) {
+    if (!ctx || !accum_dev || !fb_dev || nx < 1 || ny < 1 || ns < 1) return fail(ctx, RT_ERR_INVALID, "rt_finalize: bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    CK(launch_finalize(accum_dev, fb_dev, nx, ny, ns, ctx->stream));
+    return RT_OK;
+}
+
+extern "C" int rt_render_to_host(rt_context *ctx, const rt_render_args *args, float *fb_host, rt_render_stats *stats) {
+    if (!ctx || !args || !fb_host) return fail(ctx, RT_ERR_INVALID, "rt_render_to_host: null argument");
+    CK(cudaSetDevice(ctx->device));
+    const size_t bytes = (size_t)args->nx * args->ny * 3 * sizeof(float);
+    if (bytes > ctx->scratch_fb_bytes) {
+        cudaFree(ctx->scratch_fb);
+        ctx->scratch_fb = nullptr; ctx->scratch_fb_bytes = 0;
+        CK(cudaMalloc(&ctx->scratch_fb, bytes));
+        ctx->scratch_fb_bytes = bytes;
+    }
+    const int rc = do_render(ctx, args, ctx->scratch_fb, true, stats);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(fb_host, ctx->scratch_fb, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return RT_OK;
+}
+
+// ---- output: main.cu:321-333 -------------------------------------------------------------------------------------
+static inline char *put_int(char *p, int v) {   // what `ostream << int` prints
+    char tmp[16];
+    int n = 0;
+    unsigned u = v < 0 ? 0u - (unsigned)v : (unsigned)v;
+    do { tmp[n++] = (char)('0' + u % 10); u /= 10; } while (u);
+    if (v < 0) *p++ = '-';
+    while (n) *p++ = tmp[--n];
+    return p;
+}
+extern "C" size_t rt_format_ppm(const float *fb, int nx, int ny, char *buf, size_t cap) {
+    char head[64];
+    const int hl = snprintf(head, sizeof head, "P3\n%d %d\n255\n", nx, ny);
+    size_t off = (size_t)hl;
+    if (buf && off <= cap) memcpy(buf, head, (size_t)hl);
+    char line[48];
+    for (int j = ny - 1; j >= 0; j--) {
+        for (int i = 0; i < nx; i++) {
+            const size_t pi = ((size_t)j * nx + i) * 3;
+            char *p = line;
+            p = put_int(p, (int)(255.99 * fb[pi + 0])); *p++ = ' ';
+            p = put_int(p, (int)(255.99 * fb[pi + 1])); *p++ = ' ';
+            p = put_int(p, (int)(255.99 * fb[pi + 2])); *p++ = '\n';
+            const size_t len = (size_t)(p - line);
+            if (buf && off + len <= cap) memcpy(buf + off, line, len);
+            off += len;
+        }
+    }
+    return off;
+}
+
+// ---- device memory helpers -----------------------------------------------------------------------------------------
+extern "C" int rt_malloc(rt_context *ctx, size_t bytes, void **dev_ptr) {
+    if (!ctx || !dev_ptr) return RT_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMalloc(dev_ptr, bytes));
+    return RT_OK;
+}
+extern "C" int rt_free(rt_context *ctx, void *dev_ptr) {
+    if (!ctx) return RT_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaFree(dev_ptr));
+    return RT_OK;
+}
+extern "C" int rt_memcpy_to_host(rt_context *ctx, void *host, const void *dev, size_t bytes) {
+    if (!ctx || !host || !dev) return RT_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return RT_OK;
+}
+extern "C" int rt_synchronize(rt_context *ctx) {
+    if (!ctx) return RT_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return RT_OK;
+}

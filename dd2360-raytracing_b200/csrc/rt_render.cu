@@ -1,0 +1,286 @@
+// rt_render.cu — the render hot path: render_init + render + color (main.cu:43-117) as ONE persistent kernel.
+//
+// Reference shape: thread = pixel, 8x8 blocks, each thread runs its ns samples x <=50 bounces serially, so a warp
+// lives as long as its slowest pixel and every bounce pays two virtual calls and an AoS pointer chase.
+// This kernel:
+//   * persistent threads: the grid is sized to what is resident on the SMs; every lane owns one pixel at a time
+//     and runs its sample chain bounce by bounce (the chain is inherently serial: all samples of a pixel draw from
+//     one XORWOW stream).  When a lane's pixel is finished it claims the next one from a global queue;
+//     claims are compacted per warp with __ballot_sync/__popc so one atomic serves the whole warp.  Lanes therefore
+//     always have a ray to trace, whatever the path lengths of their neighbours;
+//   * pixels are queued in 8x4 tiles so that the 32 lanes of a warp start on neighbouring pixels (coherent rays);
+//   * XORWOW state lives in registers and is seeded in place (render_init fused; no 48-byte state array);
+//   * spheres are SoA float4, materials are tag-dispatched (no device heap, no vtables);
+//   * the octree's packed nodes, content boxes and cell descriptors are staged once per block in shared memory
+//     with a TMA bulk copy (cp.async.bulk + mbarrier); in flat-list mode the whole float4 sphere array is staged
+//     the same way and swept with warp-uniform (broadcast) shared-memory reads.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "rt_render.h"
+#include "rt_trace.cuh"
+
+namespace rt {
+
+__constant__ CameraData c_camera;
+
+cudaError_t upload_camera(const CameraData &cam, cudaStream_t st) {
+    return cudaMemcpyToSymbolAsync(c_camera, &cam, sizeof cam, 0, cudaMemcpyHostToDevice, st);
+}
+cudaError_t upload_camera_from_device(const CameraData *cam_dev, cudaStream_t st) {
+    return cudaMemcpyToSymbolAsync(c_camera, cam_dev, sizeof(CameraData), 0, cudaMemcpyDeviceToDevice, st);
+}
+
+// ---- TMA 1-D bulk copy global -> shared, completion on an mbarrier -------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t done = 0;
+    // bounded: a copy of a few KB completes in microseconds; never spin forever on a broken descriptor
+    for (int spin = 0; spin < (1 << 22) && !done; spin++) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    }
+    if (!done) __trap();
+}
+
+// Stage `bytes` (multiple of 16, 16-byte aligned on both sides) in chunks the bulk-copy engine accepts.
+__device__ __forceinline__ void stage_bulk(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    const uint32_t kChunk = 32768;
+    for (uint32_t off = 0; off < bytes; off += kChunk) {
+        const uint32_t n = bytes - off < kChunk ? bytes - off : kChunk;
+        bulk_g2s(static_cast<char *>(dst) + off, static_cast<const char *>(src) + off, n, bar);
+    }
+}
+
+// item -> pixel.  Items enumerate 8x4 tiles row-major, 32 pixels per tile; `tile_stride/tile_first` select the
+// interleaved tiles a shard owns (RT_SHARD_TILES).
+__device__ __forceinline__ bool item_to_pixel(const RenderLaunch &p, uint32_t item, int &i, int &j) {
+    const uint32_t local_tile = item >> 5, in = item & 31u;
+    const uint32_t tile = local_tile * (uint32_t)p.tile_stride + (uint32_t)p.tile_first;
+    const uint32_t ty = tile / (uint32_t)p.tiles_x, tx = tile - ty * (uint32_t)p.tiles_x;
+    i = (int)(tx * 8u + (in & 7u));
+    j = (int)(ty * 4u + (in >> 3));
+    return i < p.nx && j < p.ny;
+}
+
+template <bool OCTREE, bool GEOM_SMEM>
+__global__ void __launch_bounds__(kRenderThreads, 4) k_render(const __grid_constant__ RenderLaunch p) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t bar;
+
+    // ---- stage the read-mostly structures in shared memory (TMA bulk copy) ----
+    SceneView sc = p.scene;
+    TreeView tv = p.tree;
+    const float4 *geom_s = nullptr;
+    {
+        unsigned char *cur = smem_raw;
+        uint32_t total = 0;
+        if (threadIdx.x == 0) mbar_init(&bar, 1);
+        __syncthreads();
+        if (OCTREE) {
+            const uint32_t nb = (uint32_t)tv.node_count * sizeof(TreeNode), eb = (uint32_t)tv.node_count * sizeof(TreeExtent);
+            const uint32_t cb = (uint32_t)tv.cell_count * sizeof(CellGrid), xb = (uint32_t)tv.cell_count * sizeof(TreeExtent);
+            unsigned char *s_nodes = cur; cur += nb;
+            unsigned char *s_next = cur; cur += eb;
+            unsigned char *s_cells = cur; cur += cb;
+            unsigned char *s_cext = cur; cur += xb;
+            total = nb + eb + cb + xb;
+            if (threadIdx.x == 0) {
+                mbar_expect_tx(&bar, total);
+                stage_bulk(s_nodes, p.tree.nodes, nb, &bar);
+                stage_bulk(s_next, p.tree.node_ext, eb, &bar);
+                if (cb) stage_bulk(s_cells, p.tree.cells, cb, &bar);
+                if (xb) stage_bulk(s_cext, p.tree.cell_ext, xb, &bar);
+            }
+            tv.nodes = reinterpret_cast<const TreeNode *>(s_nodes);
+            tv.node_ext = reinterpret_cast<const TreeExtent *>(s_next);
+            tv.cells = reinterpret_cast<const CellGrid *>(s_cells);
+            tv.cell_ext = reinterpret_cast<const TreeExtent *>(s_cext);
+        } else if (GEOM_SMEM) {
+            total = (uint32_t)sc.n * sizeof(float4);
+            if (threadIdx.x == 0) {
+                mbar_expect_tx(&bar, total);
+                stage_bulk(cur, p.scene.geom, total, &bar);
+            }
+            geom_s = reinterpret_cast<const float4 *>(cur);
+        }
+        if (total) mbar_wait(&bar, 0);
+    }
+
+    const unsigned lane = threadIdx.x & 31u;
+    const uint32_t gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+
+    // per-lane path state
+    int pix = -1, pi = 0, pj = 0;
+    int s = 0, depth = 0;
+    xorwow rng;
+    rng.d = rng.v0 = rng.v1 = rng.v2 = rng.v3 = rng.v4 = 0;
+    vec3f o = mk(0, 0, 0), d = mk(0, 0, 1), att = mk(1, 1, 1), col = mk(0, 0, 0);
+    uint32_t nrays = 0, npaths = 0;
+    bool exhausted = false;
+    uint32_t first_item = gwarp * 32u + lane;   // the first claim needs no atomic: the queue head starts past the grid
+    bool first = true;
+    const float inv_ns = __fdiv_rn(1.0f, (float)p.ns_total);   // vec3.h:137-144: k = 1.0/t
+
+    while (true) {
+        // ---- claim pixels for idle lanes (ballot/popc-compacted queue pop) ----
+        while (true) {
+            const bool need = pix < 0 && !exhausted;
+            const unsigned m = __ballot_sync(0xffffffffu, need);
+            if (!m) break;
+            uint32_t item;
+            if (first) {
+                item = first_item;
+            } else {
+                uint32_t base = 0;
+                const int leader = __ffs(m) - 1;
+                if ((int)lane == leader) base = atomicAdd(p.work_counter, (uint32_t)__popc(m));
+                base = __shfl_sync(0xffffffffu, base, leader);
+                item = base + (uint32_t)__popc(m & ((1u << lane) - 1u));
+            }
+            if (need) {
+                if (item >= p.total_items) {
+                    exhausted = true;
+                } else if (item_to_pixel(p, item, pi, pj)) {
+                    pix = pj * p.nx + pi;
+                    s = 0; depth = 0;
+                    col = mk(0, 0, 0);
+                    xorwow_seed(rng, (unsigned long long)(long long)(1984 + pix) + p.seed_offset);   // main.cu:93
+                }
+            }
+            first = false;
+        }
+        if (!__ballot_sync(0xffffffffu, pix >= 0)) break;
+
+        if (pix >= 0) {
+            if (depth == 0) {   // new sample: main.cu:104-106
+                const float u = div_(add_((float)pi, xorwow_uniform(rng)), (float)p.nx);
+                const float v = div_(add_((float)pj, xorwow_uniform(rng)), (float)p.ny);
+                camera_ray(c_camera, u, v, rng, o, d);
+                att = mk(1.0f, 1.0f, 1.0f);
+                npaths++;
+            }
+            // ---- one iteration of color()'s loop (main.cu:47-73) ----
+            nrays++;
+            Hit h;
+            if (OCTREE) h = trace_tree(sc, tv, &p.tree.planes[0][0], o, d);
+            else if (GEOM_SMEM) h = trace_list(geom_s, sc.tag, sc.n, o, d);
+            else h = trace_list(sc.geom, sc.tag, sc.n, o, d);
+            bool sample_done = false;
+            vec3f contrib = mk(0, 0, 0);
+            if (h.idx >= 0) {
+                const float4 g = __ldg(sc.geom + h.idx);
+                const float4 m = __ldg(sc.matl + h.idx);
+                const int tag = __ldg(sc.tag + h.idx);
+                vec3f hp, hn, a, dn;
+                hit_point(g, o, d, h.t, hp, hn);
+                if (scatter(tag, m, d, hp, hn, a, dn, rng)) {
+                    att = mk(mul_(att.x, a.x), mul_(att.y, a.y), mul_(att.z, a.z));
+                    o = hp; d = dn;
+                    depth++;
+                    if (depth >= p.max_depth) sample_done = true;        // main.cu:74: return black
+                } else {
+                    sample_done = true;                                   // absorbed: main.cu:64
+                }
+            } else {
+                const vec3f c = sky(d);
+                contrib = mk(mul_(att.x, c.x), mul_(att.y, c.y), mul_(att.z, c.z));
+                sample_done = true;
+            }
+            if (sample_done) {
+                col = mk(add_(col.x, contrib.x), add_(col.y, contrib.y), add_(col.z, contrib.z));   // main.cu:107
+                depth = 0;
+                s++;
+                if (s >= p.ns_local) {
+                    float *out = p.out + (size_t)pix * 3;
+                    if (p.finalize) {   // main.cu:111-115
+                        out[0] = sqrt_(mul_(col.x, inv_ns));
+                        out[1] = sqrt_(mul_(col.y, inv_ns));
+                        out[2] = sqrt_(mul_(col.z, inv_ns));
+                    } else {
+                        out[0] = col.x; out[1] = col.y; out[2] = col.z;
+                    }
+                    pix = -1;
+                }
+            }
+        }
+        __syncwarp();
+    }
+
+    // ---- ray / path counters: one atomic per warp ----
+    unsigned long long r64 = nrays, p64 = npaths;
+    for (int off = 16; off > 0; off >>= 1) {
+        r64 += __shfl_xor_sync(0xffffffffu, r64, off);
+        p64 += __shfl_xor_sync(0xffffffffu, p64, off);
+    }
+    if (lane == 0) {
+        atomicAdd(p.counters + 0, r64);
+        atomicAdd(p.counters + 1, p64);
+    }
+}
+
+// fb = sqrt(accum * (1/ns)) (main.cu:111-114), for frames assembled from shards
+__global__ void k_finalize(const float *__restrict__ accum, float *__restrict__ fb, size_t n3, float inv_ns) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n3) fb[i] = __fsqrt_rn(__fmul_rn(accum[i], inv_ns));
+}
+
+cudaError_t launch_finalize(const float *accum, float *fb, int nx, int ny, int ns, cudaStream_t st) {
+    const size_t n3 = (size_t)nx * ny * 3;
+    const float inv_ns = (float)(1.0 / (double)(float)ns);
+    k_finalize<<<(unsigned)((n3 + 255) / 256), 256, 0, st>>>(accum, fb, n3, inv_ns);
+    return cudaGetLastError();
+}
+
+template <bool OCTREE, bool GEOM_SMEM>
+static cudaError_t launch_variant(const RenderLaunch &p, size_t smem, int sm_count, cudaStream_t st, int *blocks_out) {
+    auto kern = k_render<OCTREE, GEOM_SMEM>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kRenderThreads, smem);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+    // persistent grid: exactly what is resident, never more blocks than there is work
+    long long blocks = (long long)per_sm * sm_count;
+    const long long need = ((long long)p.total_items + kRenderThreads - 1) / kRenderThreads;
+    if (blocks > need) blocks = need < 1 ? 1 : need;
+    RenderLaunch q = p;
+    const uint32_t head = (uint32_t)(blocks * kRenderThreads);
+    e = cudaMemcpyAsync(q.work_counter, &head, 4, cudaMemcpyHostToDevice, st);   // queue head starts past the grid
+    if (e != cudaSuccess) return e;
+    kern<<<(unsigned)blocks, kRenderThreads, smem, st>>>(q);
+    if (blocks_out) *blocks_out = (int)blocks;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_render(const RenderLaunch &p, bool octree, int sm_count, size_t smem_limit, cudaStream_t st,
+                          int *blocks_out) {
+    if (octree) {
+        const size_t smem = (size_t)p.tree.node_count * (sizeof(TreeNode) + sizeof(TreeExtent)) +
+                            (size_t)p.tree.cell_count * (sizeof(CellGrid) + sizeof(TreeExtent));
+        return launch_variant<true, false>(p, smem, sm_count, st, blocks_out);
+    }
+    const size_t geom_bytes = (size_t)p.scene.n * sizeof(float4);
+    if (geom_bytes + 1024 <= smem_limit) return launch_variant<false, true>(p, geom_bytes, sm_count, st, blocks_out);
+    return launch_variant<false, false>(p, 0, sm_count, st, blocks_out);
+}
+
+}  // namespace rt

@@ -1,0 +1,35 @@
+// rt_render.h — launch interface of the persistent render kernel (rt_render.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "rt_types.h"
+
+namespace rt {
+
+constexpr int kRenderThreads = 128;
+
+struct RenderLaunch {
+    SceneView scene;
+    TreeView tree;
+    int nx, ny;
+    int ns_total;            // samples per pixel of the whole frame (divisor of the final average)
+    int ns_local;            // samples this launch traces per pixel
+    int max_depth;
+    int tiles_x;             // 8x4 pixel tiles per row
+    int tile_first, tile_stride;   // this shard owns tiles tile_first + k*tile_stride
+    uint32_t total_items;    // owned tiles * 32
+    unsigned long long seed_offset;   // added to the per-pixel seed 1984 + pixel_index (spp shards)
+    int finalize;            // 1: write sqrt(sum/ns) (main.cu:111-115); 0: write the linear sum
+    float *out;              // nx*ny*3 floats
+    uint32_t *work_counter;  // queue head
+    unsigned long long *counters;   // [0] rays, [1] paths
+};
+
+cudaError_t upload_camera(const CameraData &cam, cudaStream_t st);
+cudaError_t upload_camera_from_device(const CameraData *cam_dev, cudaStream_t st);
+cudaError_t launch_render(const RenderLaunch &p, bool octree, int sm_count, size_t smem_limit, cudaStream_t st,
+                          int *blocks_out);
+cudaError_t launch_finalize(const float *accum, float *fb, int nx, int ny, int ns, cudaStream_t st);
+
+}  // namespace rt

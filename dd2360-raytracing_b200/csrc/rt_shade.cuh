@@ -1,0 +1,145 @@
+// rt_shade.cuh — per-lane ray generation, ray-sphere test and material scatter.
+//
+// Each function states the reference lines it reproduces.  The arithmetic is bit-compatible with the reference's
+// sm_100 build: same operations, same operand order, and the same multiply-add fusion ptxas applies there
+// (rt_math.cuh).  RNG draws happen in the device's order of evaluation (left to right).
+#pragma once
+#include "rt_math.cuh"
+#include "rt_types.h"
+
+namespace rt {
+
+constexpr float kTMin = 0.001f;      // main.cu:54, acceleration_structure.h:260,325
+constexpr float kTMax = 3.402823466e+38f;  // FLT_MAX
+
+// sphere.h:17-46.  `a` = dot(direction, direction) is hoisted by the caller (the reference recomputes the same
+// value for every sphere).  Returns true and the accepted root when t_min < t < t_max.
+RT_HD bool sphere_test(const float4 s, const vec3f o, const vec3f d, const float a, const float t_max, float &t_out) {
+    const vec3f oc = mk(sub_(o.x, s.x), sub_(o.y, s.y), sub_(o.z, s.z));     // sphere.h:18
+    const float b = dot3(oc, d);                                                // :20
+    const float c = fma_(-s.w, s.w, dot3(oc, oc));                             // :21  dot(oc,oc) - r*r
+    const float disc = fma_(b, b, -mul_(a, c));                                // :22  b*b - a*c
+    if (disc > 0.0f) {
+        const float sq = sqrt_(disc);
+        float temp = div_(sub_(-b, sq), a);                                    // :27
+        if (temp < t_max && temp > kTMin) { t_out = temp; return true; }
+        temp = div_(add_(-b, sq), a);                                          // :36
+        if (temp < t_max && temp > kTMin) { t_out = temp; return true; }
+    }
+    return false;
+}
+
+// sphere.h:30-33: p = A + t*B (ray.h:13); normal = (p - center) / radius
+RT_HD void hit_point(const float4 s, const vec3f o, const vec3f d, const float t, vec3f &p, vec3f &n) {
+    p = mk(fma_(d.x, t, o.x), fma_(d.y, t, o.y), fma_(d.z, t, o.z));
+    n = mk(div_(sub_(p.x, s.x), s.w), div_(sub_(p.y, s.y), s.w), div_(sub_(p.z, s.z), s.w));
+}
+
+// material.h:33-41 random_in_unit_sphere
+RT_HD vec3f random_in_unit_sphere(xorwow &rng) {
+    vec3f p;
+    do {
+        const float u0 = xorwow_uniform(rng), u1 = xorwow_uniform(rng), u2 = xorwow_uniform(rng);
+        p = mk(fma_(u0, 2.0f, -1.0f), fma_(u1, 2.0f, -1.0f), fma_(u2, 2.0f, -1.0f));
+    } while (dot3(p, p) >= 1.0f);
+    return p;
+}
+
+// material.h:43-45 reflect: v - 2*dot(v,n)*n
+RT_HD vec3f reflect(const vec3f v, const vec3f n) {
+    const float d2 = mul_(2.0f, dot3(v, n));
+    return mk(fma_(-n.x, d2, v.x), fma_(-n.y, d2, v.y), fma_(-n.z, d2, v.z));
+}
+
+// material.h:17-31 refract
+RT_HD bool refract(const vec3f v, const vec3f n, const float ni_over_nt, vec3f &refracted) {
+    const vec3f uv = unit_vector(v);
+    const float dt = dot3(uv, n);
+    const float disc = fma_(-mul_(ni_over_nt, ni_over_nt), fma_(-dt, dt, 1.0f), 1.0f);
+    if (disc > 0.0f) {
+        const float sq = sqrt_(disc);
+        refracted = mk(fma_(sq, -n.x, mul_(ni_over_nt, fma_(dt, -n.x, uv.x))),
+                       fma_(sq, -n.y, mul_(ni_over_nt, fma_(dt, -n.y, uv.y))),
+                       fma_(sq, -n.z, mul_(ni_over_nt, fma_(dt, -n.z, uv.z))));
+        return true;
+    }
+    return false;
+}
+
+// material.h:11-15 schlick (pow in 32 bit: the same libdevice powf the reference build calls)
+RT_HD float schlick(const float cosine, const float ref_idx) {
+    float r0 = div_(sub_(1.0f, ref_idx), add_(1.0f, ref_idx));
+    r0 = mul_(r0, r0);
+    return fma_(sub_(1.0f, r0), powf(sub_(1.0f, cosine), 5.0f), r0);
+}
+
+// material.h:55-60 (lambertian), :68-73 (metal), :81-113 (dielectric); tag dispatch instead of a vtable.
+// Returns false when the ray is absorbed (metal only).
+RT_HD bool scatter(const int tag, const float4 m, const vec3f d_in, const vec3f p, const vec3f n, vec3f &atten,
+                   vec3f &d_out, xorwow &rng) {
+    if (tag == 0) {  // lambertian: target = p + normal + r; direction = target - p (not simplified)
+        const vec3f r = random_in_unit_sphere(rng);
+        const vec3f target = mk(add_(add_(p.x, n.x), r.x), add_(add_(p.y, n.y), r.y), add_(add_(p.z, n.z), r.z));
+        d_out = mk(sub_(target.x, p.x), sub_(target.y, p.y), sub_(target.z, p.z));
+        atten = mk(m.x, m.y, m.z);
+        return true;
+    }
+    if (tag == 1) {  // metal: draws even when fuzz == 0
+        const vec3f refl = reflect(unit_vector(d_in), n);
+        const vec3f r = random_in_unit_sphere(rng);
+        d_out = mk(fma_(m.w, r.x, refl.x), fma_(m.w, r.y, refl.y), fma_(m.w, r.z, refl.z));
+        atten = mk(m.x, m.y, m.z);
+        return dot3(d_out, n) > 0.0f;
+    }
+    // dielectric
+    const float ref_idx = m.w;
+    const vec3f reflected = reflect(d_in, n);
+    vec3f outward, refracted = mk(0.f, 0.f, 0.f);
+    float ni_over_nt, cosine, reflect_prob;
+    atten = mk(1.0f, 1.0f, 1.0f);
+    const float ddn = dot3(d_in, n);
+    if (ddn > 0.0f) {
+        outward = mk(-n.x, -n.y, -n.z);
+        ni_over_nt = ref_idx;
+        cosine = div_(ddn, sqrt_(dot3(d_in, d_in)));
+        cosine = sqrt_(fma_(-mul_(ref_idx, ref_idx), fma_(-cosine, cosine, 1.0f), 1.0f));
+    } else {
+        outward = n;
+        ni_over_nt = div_(1.0f, ref_idx);
+        cosine = div_(-ddn, sqrt_(dot3(d_in, d_in)));
+    }
+    if (refract(d_in, outward, ni_over_nt, refracted)) reflect_prob = schlick(cosine, ref_idx);
+    else reflect_prob = 1.0f;
+    d_out = (xorwow_uniform(rng) < reflect_prob) ? reflected : refracted;
+    return true;
+}
+
+// camera.h:12-18 random_in_unit_disk + :45-49 get_ray
+RT_HD void camera_ray(const CameraData &c, const float s, const float t, xorwow &rng, vec3f &o, vec3f &d) {
+    float px, py;
+    do {
+        const float u0 = xorwow_uniform(rng), u1 = xorwow_uniform(rng);
+        px = fma_(u0, 2.0f, -1.0f);
+        py = fma_(u1, 2.0f, -1.0f);
+    } while (fma_(px, px, mul_(py, py)) >= 1.0f);
+    const float rdx = mul_(c.lens_radius, px), rdy = mul_(c.lens_radius, py);
+    float off[3], org[3], dir[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        off[k] = fma_(c.u[k], rdx, mul_(c.v[k], rdy));
+        org[k] = add_(c.origin[k], off[k]);
+        dir[k] = sub_(sub_(fma_(c.vertical[k], t, fma_(c.horizontal[k], s, c.lower_left_corner[k])), c.origin[k]), off[k]);
+    }
+    o = mk(org[0], org[1], org[2]);
+    d = mk(dir[0], dir[1], dir[2]);
+}
+
+// main.cu:68-71: sky gradient for a ray that hit nothing
+RT_HD vec3f sky(const vec3f d) {
+    const vec3f ud = unit_vector(d);
+    const float t = mul_(0.5f, add_(ud.y, 1.0f));
+    const float omt = sub_(1.0f, t);
+    return mk(fma_(t, 0.5f, omt), fma_(t, 0.7f, omt), add_(t, omt));
+}
+
+}  // namespace rt

@@ -1,0 +1,136 @@
+/*
+ * rt_abi.h — C ABI of librt_b200.so: the B200-native (sm_100a) render hot path of DD2360-RayTracing.
+ *
+ * The reference has no plugin / FFI layer: its "interface" for this path is the set of call sites in
+ * main() (main.cu:347-477) plus the header class surface.  Every entry point below names the reference call
+ * site it replaces.  Plain C: opaque handle, pointers and sizes only; no C++ types, no exceptions, no torch.
+ * Every function returns 0 on success or a non-zero code (a cudaError_t value, or RT_ERR_* below) and leaves a
+ * message retrievable with rt_last_error().  A context is bound to one GPU and one stream and is not
+ * thread-safe (the reference is single-threaded on the default stream, main.cu:388-429).
+ *
+ * There is NO CPU fallback: if no CUDA device is usable rt_create fails.
+ */
+#ifndef RT_ABI_H
+#define RT_ABI_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RT_ABI_VERSION 1
+
+enum {
+    RT_OK = 0,
+    RT_ERR_INVALID = 10001,      /* bad argument */
+    RT_ERR_STATE = 10002,        /* call order: e.g. render before a scene exists */
+    RT_ERR_UNSUPPORTED = 10003
+};
+
+/* material tags (material.h:52,62,76) */
+enum { RT_MAT_NONE = -1, RT_MAT_LAMBERTIAN = 0, RT_MAT_METAL = 1, RT_MAT_DIELECTRIC = 2 };
+/* per-pixel stream seeding: RT_SEED_HEAD = curand_init(1984 + pixel_index, 0, 0) (main.cu:93);
+ * RT_SEED_UPSTREAM = curand_init(1984, pixel_index, 0) (main.cu:90, commented out in the reference) */
+enum { RT_SEED_HEAD = 0, RT_SEED_UPSTREAM = 1 };
+/* how a frame is split over ranks: whole frame, interleaved pixel tiles (bit-identical to the
+ * 1-GPU image after the sum), or samples-per-pixel shards (statistically equivalent, not bit-identical) */
+enum { RT_SHARD_NONE = 0, RT_SHARD_TILES = 1, RT_SHARD_SPP = 2 };
+
+/* One sphere and its material, flattened: what `sphere(center, radius, new <material>(...))` carries
+ * (sphere.h:10, material.h:54,64,78).  36 bytes, same layout the oracle uses. */
+typedef struct rt_sphere_desc {
+    float cx, cy, cz, radius;
+    int32_t mat;            /* RT_MAT_*; RT_MAT_NONE marks a slot create_world never wrote (never hit) */
+    float ax, ay, az;       /* albedo: lambertian, metal */
+    float param;            /* metal: fuzz (clamped to <= 1 as metal::metal does); dielectric: ref_idx */
+} rt_sphere_desc;
+
+/* camera(lookfrom, lookat, vup, vfov, aspect, aperture, focus_dist) — camera.h:22 */
+typedef struct rt_camera_desc {
+    float lookfrom[3], lookat[3], vup[3];
+    float vfov, aspect, aperture, focus_dist;
+} rt_camera_desc;
+
+typedef struct rt_octree_stats {
+    int32_t node_count, leaf_count;     /* Octree::nodeCount / leafCount */
+    int64_t entries;                    /* (cell, sphere) entries stored in leaf buckets */
+    int64_t dropped_full;               /* entries the reference drops with "Leaf nodes full" */
+    int64_t dropped_outside;            /* spheres outside the root box */
+    int64_t fine_voxels, fine_refs;     /* internal sub-grid size (not part of the reference layout) */
+    float build_ms;                     /* device time of the whole build */
+} rt_octree_stats;
+
+typedef struct rt_render_args {
+    int32_t nx, ny;          /* image size (main.cu:348-349) */
+    int32_t ns;              /* samples per pixel of the WHOLE frame (main.cu:350) */
+    int32_t max_depth;       /* 50 (main.cu:47); 0 selects 50 */
+    int32_t use_octree;      /* USE_OCTREE (main.cu:24): 1 = hitTree, 0 = hitable_list::hit */
+    int32_t seed_mode;       /* RT_SEED_* */
+    int32_t shard_mode;      /* RT_SHARD_* */
+    int32_t shard_rank, shard_count;
+    int32_t reserved[7];
+} rt_render_args;
+
+typedef struct rt_render_stats {
+    uint64_t rays;           /* closest-hit queries = iterations of color()'s loop (main.cu:47) */
+    uint64_t paths;          /* camera samples */
+    uint64_t sphere_tests;   /* ray-sphere tests executed (only counted when built with RT_COUNTERS) */
+    uint64_t node_tests;     /* octree node tests executed (same) */
+    float kernel_ms;         /* device time of the render kernel(s), CUDA events on the context's stream */
+    int32_t launches;        /* kernels launched by this call */
+} rt_render_stats;
+
+typedef struct rt_context rt_context;
+
+/* ---- context ---------------------------------------------------------------------------------------- */
+int rt_abi_version(void);
+int rt_create(int device, rt_context **out);                 /* replaces nothing; cudaSetDevice + stream */
+void rt_destroy(rt_context *ctx);                            /* replaces free_world + cudaFree x7 (main.cu:459-474) */
+const char *rt_last_error(const rt_context *ctx);
+int rt_set_stream(rt_context *ctx, void *cuda_stream);       /* cudaStream_t; NULL = the context's own stream */
+int rt_device_info(const rt_context *ctx, int *sm_count, int *clock_khz, size_t *mem_bytes);
+
+/* ---- scene: replaces rand_init + create_world (main.cu:388,399) ------------------------------------------ */
+/* The reference's generator: world seed 1984, NUM_SPHERES = n, SPHERE_RADIUS = radius (main.cu:22-23,146-181). */
+int rt_scene_generate(rt_context *ctx, int n, float sphere_radius);
+/* A caller-built world (the drop-in headers flatten hitable_list into this). */
+int rt_scene_upload(rt_context *ctx, const rt_sphere_desc *spheres, int n);
+int rt_scene_download(rt_context *ctx, rt_sphere_desc *out, int n);
+int rt_scene_size(const rt_context *ctx);
+/* camera: main.cu:192-202 constants with aspect = nx/ny when desc == NULL */
+int rt_camera_set(rt_context *ctx, const rt_camera_desc *desc, int nx, int ny);
+int rt_camera_get(rt_context *ctx, float out22[22]);         /* origin,llc,horizontal,vertical,u,v,w,lens_radius */
+
+/* ---- octree: replaces D2H(spheres) + buildOctree + H2D(Octree) (main.cu:405-415) -------------------------- */
+int rt_octree_build(rt_context *ctx, int spheres_per_leaf, rt_octree_stats *stats);
+size_t rt_octree_reference_bytes(int spheres_per_leaf);      /* sizeof(Octree) for that SPHERES_PER_LEAF */
+/* the tree in the reference's own memory layout (acceleration_structure.h:23-61), for the bit-exact check */
+int rt_octree_export_reference(rt_context *ctx, void *host_blob, size_t bytes);
+
+/* ---- render: replaces render_init + render (main.cu:424-429) ---------------------------------------------- */
+/* Renders this rank's shard into `accum_dev` (device pointer, nx*ny*3 floats): LINEAR radiance sums (before
+ * /ns and sqrt), zero where the shard owns nothing, so that shards add up (main.cu:119-142 semantics). */
+int rt_render_accumulate(rt_context *ctx, const rt_render_args *args, float *accum_dev, rt_render_stats *stats);
+/* fb = sqrt(accum * (1/ns)) per channel (main.cu:111-114); in place allowed */
+int rt_finalize(rt_context *ctx, const float *accum_dev, float *fb_dev, int nx, int ny, int ns);
+/* Whole frame on one GPU straight into the reference's fb layout (device pointer, vec3 per pixel). */
+int rt_render(rt_context *ctx, const rt_render_args *args, float *fb_dev, rt_render_stats *stats);
+/* Same with a HOST destination: render + device->host copy (what the reference does through managed memory). */
+int rt_render_to_host(rt_context *ctx, const rt_render_args *args, float *fb_host, rt_render_stats *stats);
+
+/* ---- output: replaces output_to_stream (main.cu:321-333) -------------------------------------------------- */
+/* P3 text, byte-identical to the reference writer.  Returns bytes needed when buf == NULL. */
+size_t rt_format_ppm(const float *fb_host, int nx, int ny, char *buf, size_t cap);
+
+/* ---- device memory helpers for hosts without a CUDA runtime binding ---------------------------------------- */
+int rt_malloc(rt_context *ctx, size_t bytes, void **dev_ptr);
+int rt_free(rt_context *ctx, void *dev_ptr);
+int rt_memcpy_to_host(rt_context *ctx, void *host, const void *dev, size_t bytes);
+int rt_synchronize(rt_context *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -149,10 +149,11 @@ void rto_camera_init(rto_camera *c, int nx, int ny, int arith) {
         c->origin[k] = O[k];
         c->u[k] = U[k]; c->v[k] = Vv[k]; c->w[k] = W[k];
         if (arith == RTO_ARITH_DEVICE) {
-            /* origin - hw*u - hh*v - focus*w */
+            /* origin - hw*u - hh*v - focus*w: the first two products are fused into the subtraction; focus*w
+             * is a compile-time constant in the reference (folded, so rounded on its own) */
             float t = fmaf(-hw, U[k], O[k]);
             t = fmaf(-hh, Vv[k], t);
-            c->lower_left_corner[k] = fmaf(-focus, W[k], t);
+            c->lower_left_corner[k] = t - focus * W[k];
         } else {
             c->lower_left_corner[k] = ((O[k] - hw * U[k]) - hh * Vv[k]) - focus * W[k];
         }
