@@ -1,0 +1,307 @@
+#!/usr/bin/env python
+"""bench.py — the render hot path on N B200s, BASELINE.json's metric (Mrays/s, ms/frame).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config C3|C1|C2|C5] [--shard tiles|spp]
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...      (one rank per GPU, NCCL)
+
+A "step" is one frame of the workload: render_init + render of the reference (main.cu:424-429), i.e. what its
+"took X seconds" brackets.  `value` is whole-job Mrays/s (closest-hit queries / device time, max over ranks) with
+the scene, octree and camera resident in HBM; `e2e` is the same metric through the public API with HOST buffers
+(sphere descriptors uploaded, octree rebuilt, frame copied back to pinned host memory inside the timed region).
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CONFIGS = {
+    # name: (n, spl, use_octree, nx, ny, ns, description)
+    "C1": (488, 30, 0, 1200, 800, 10, "C1: RTIOW scene, 488 spheres, flat hitable_list, 1200x800, 10 spp, FP32"),
+    "C2": (488, 30, 1, 1200, 800, 10, "C2: 488 spheres, octree SPHERES_PER_LEAF=30, 1200x800, 10 spp, FP32"),
+    "C3": (100000, 300, 1, 3840, 2160, 64, "C3: 100k random spheres, octree SPHERES_PER_LEAF=300, 3840x2160, 64 spp, FP32"),
+    "C5": (1000000, 3000, 1, 7680, 4320, 256, "C5: 1M random spheres, octree SPHERES_PER_LEAF=3000, 7680x4320, 256 spp, FP32"),
+}
+# CPU sample of the workload: every CPU_STRIDE-th pixel in x and y of the full frame, all ns samples
+CPU_STRIDE = {"C1": (4, 4), "C2": (2, 2), "C3": (16, 16), "C5": (96, 96)}
+# reference CUDA build on the same B200 (oracle/_ref/ref_cuda_*, measured with tests/golden/gen_ref_cuda.sh);
+# kept next to the number for context — the driver computes its own ratios
+REF_CUDA_MS = {"C1": 42.19, "C2": 325.12, "C3": 177654.47}
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.proc = index, [], None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([c.strip() for c in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self) -> dict:
+        if self.proc:
+            self.proc.terminate()
+        sm = sorted(float(r[1]) for r in self.rows if len(r) > 2 and r[1].replace(".", "").isdigit())
+        mx = [float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 9:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(self.rows)}
+
+
+def cpu_reference_sample(cfg: str, threads: int = 0):
+    """The reference's own code on the host cores (oracle/_ref/libref_host_*.so: its headers + color() compiled for
+    the CPU, OpenMP over rows), or the oracle port when that library is absent.  Returns (Mrays/s, info)."""
+    import __graft_entry__ as entry
+    O = entry.load_oracle()
+    n, spl, octree, nx, ny, ns, _ = CONFIGS[cfg]
+    sx, sy = CPU_STRIDE[cfg]
+    cores = threads or os.cpu_count() or 1
+    params = O.make_params(nx, ny, ns, octree, spl, O.ARITH_HOST, step=(sx, sy), threads=cores)
+    sample = f"pixels (i%{sx}==0, j%{sy}==0) of the {nx}x{ny} frame, all {ns} spp"
+    variant = f"{'oct' if octree else 'brute'}_spl{spl}"
+    if O.RefHost.available(variant):
+        rh = O.RefHost(variant).create_world(n, 0.1, nx, ny)
+        saved, devnull = os.dup(1), os.open(os.devnull, os.O_WRONLY)
+        os.dup2(devnull, 1)            # the reference printf's when it drops spheres
+        try:
+            if octree:
+                rh.build_octree()
+            t0 = time.perf_counter()
+            _, _, ctr = rh.render(params)
+            dt = time.perf_counter() - t0
+        finally:
+            os.dup2(saved, 1)
+            os.close(saved)
+            os.close(devnull)
+        rh.destroy()
+        kind = "reference"
+    else:
+        sph, _ = O.create_world(n)
+        blob = O.build_octree(sph, spl)[0] if octree else None
+        cam = O.camera(nx, ny, O.ARITH_HOST)
+        t0 = time.perf_counter()
+        _, _, ctr = O.render(sph, cam, params, blob)
+        dt = time.perf_counter() - t0
+        kind = "port"
+    return ctr["rays"] / dt / 1e6, {"cores": cores, "kind": kind, "sample": sample, "seconds": dt, "rays": ctr["rays"]}
+
+
+def run_reference_arm(args):
+    """--impl reference: the reference's CPU implementation of the path, all host threads, bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cfg = args.config
+    n, spl, octree, nx, ny, ns, desc = CONFIGS[cfg]
+    vals, info = [], None
+    for _ in range(max(0, args.warmup if args.warmup < 2 else 1)):      # CPU code needs no GPU-style warm-up
+        pass
+    t_all = time.perf_counter()
+    for _ in range(args.steps):
+        v, info = cpu_reference_sample(cfg)
+        vals.append(v)
+    value = sum(vals) / len(vals)
+    line = {"impl": "reference", "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * (time.perf_counter() - t_all) / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": desc, "n_spheres": n, "spheres_per_leaf": spl, "use_octree": octree, "nx": nx, "ny": ny, "ns": ns},
+            "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": info["cores"], "kind": info["kind"], "sample": info["sample"]},
+            "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="C3", choices=sorted(CONFIGS))
+    ap.add_argument("--shard", default="tiles", choices=["tiles", "spp"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import __graft_entry__ as entry
+    pkg = entry.load_package()
+    from dd2360_raytracing_b200 import multigpu as mg
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+
+    n, spl, octree, nx, ny, ns, desc = CONFIGS[args.config]
+    rt = pkg.RayTracer(local_rank)
+    stream = torch.cuda.current_stream()
+    rt.set_stream(stream.cuda_stream)
+    rt.create_world(n, 0.1)
+    bst = rt.build_octree(spl) if octree else None
+    rt.set_camera(nx, ny)
+    accum = torch.empty((ny, nx, 3), dtype=torch.float32, device=dev)
+    fb = torch.empty_like(accum) if rank == 0 else accum
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
+    mode = pkg.SHARD_TILES if args.shard == "tiles" else pkg.SHARD_SPP
+
+    def step(want_stats):
+        if world == 1:
+            return rt.render_device(rt.args(nx, ny, ns, octree), fb.data_ptr(), want_stats=want_stats)
+        return mg.render_sharded(rt, accum, fb, nx, ny, ns, bool(octree), rank, world, mode, dist, want_stats=want_stats)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 0)):
+        step(False)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    rays_local, kernel_ms = 0, []
+    barrier()
+    for k in range(args.steps):
+        flush.zero_()                                  # L2 flush between timed iterations (untimed)
+        ev[k][0].record(stream)
+        st = step(True)                                # reads the ray counter back: syncs the stream
+        ev[k][1].record(stream)
+        rays_local += st["rays"]
+        kernel_ms.append(st["kernel_ms"])
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    t = torch.tensor([sum(step_ms), float(rays_local)], dtype=torch.float64, device=dev)
+    if world > 1:
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone()
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        total_ms, total_rays = float(tmax[0]), float(tsum[1])
+    else:
+        total_ms, total_rays = float(t[0]), float(t[1])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    value = total_rays / (total_ms * 1e-3) / 1e6
+    launches_per_step = 1 if world == 1 else 2          # render (+ finalize on rank 0); the reduce is NCCL's kernel
+    line = {"metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": desc, "n_spheres": n, "spheres_per_leaf": spl, "use_octree": octree, "nx": nx, "ny": ny, "ns": ns,
+                       "max_depth": 50, "seed": "curand_init(1984+pixel_index,0,0)", "sharding": "none" if world == 1 else args.shard,
+                       "collective": None if world == 1 else "one NCCL reduce-sum of the linear radiance buffer per frame",
+                       "l2": "flushed between timed steps (256 MiB memset, untimed); each step times one whole frame",
+                       "rays_per_frame": total_rays / args.steps, "octree_build_ms": bst["build_ms"] if bst else None},
+            "clocks": clocks, "gpu_launches": launches_per_step * args.steps,
+            "kernel_ms_per_step": sum(kernel_ms) / len(kernel_ms)}
+    if args.config in REF_CUDA_MS:
+        line["ref_cuda_build_same_b200"] = {"ms_per_frame": REF_CUDA_MS[args.config],
+                                            "source": "tests/golden/ref_cuda/manifest.json (oracle/_ref/ref_cuda_*, sm_100 recompile)"}
+
+    # ---- end to end through the public API with HOST buffers (N = world ranks; rank 0 measures its own share) ----
+    spheres = rt.spheres()
+    host_fb = torch.empty((ny, nx, 3), dtype=torch.float32).pin_memory()
+    e2e_rays, e2e_t = 0, 0.0
+    if world == 1:
+        import ctypes as C
+        for k in range(args.steps + 1):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            rt.upload_world(spheres)                           # host -> device: sphere descriptors (SoA split on the way)
+            if octree:
+                rt.build_octree(spl)
+            a = rt.args(nx, ny, ns, octree)
+            stt = pkg.RenderStats()
+            rt._ck(rt.L.rt_render_to_host(rt._ctx, C.byref(a), C.c_void_p(host_fb.data_ptr()), C.byref(stt)), "rt_render_to_host")
+            dt = time.perf_counter() - t0
+            if k > 0:                                          # first pass warms the allocations
+                e2e_rays += stt.rays
+                e2e_t += dt
+        line["e2e"] = {"value": e2e_rays / e2e_t / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": int(n * 36),
+                       "d2h_bytes_per_step": int(nx * ny * 12 + 40), "ms_per_step": 1e3 * e2e_t / args.steps,
+                       "includes": "scene upload, GPU octree build, render, frame copy to pinned host memory"}
+    else:
+        line["e2e"] = None
+
+    # ---- roofline of the dominant kernel (k_render): FP32 issue, SURVEY §8(d) formula with measured S, B ----
+    try:
+        peak = rt.ffma_peak_tflops()
+        rti = pkg.RayTracer(local_rank, instrumented=True)
+        rti.create_world(n, 0.1)
+        if octree:
+            rti.build_octree(spl)
+        probe = torch.empty((ny, nx, 3), dtype=torch.float32, device=dev)
+        ps = rti.render_device(rti.args(nx, ny, 1, octree), probe.data_ptr())
+        S, B = ps["sphere_tests"] / ps["rays"], ps["node_tests"] / ps["rays"]
+        flop_per_ray = 5 + 18 * S + 12 * B + 80
+        km = sum(kernel_ms) / len(kernel_ms)
+        achieved = (total_rays / args.steps / world) * flop_per_ray / (km * 1e-3) / 1e12
+        traffic = None
+        pj = os.path.join(ROOT, "profiles", "roofline_inputs.json")
+        if os.path.exists(pj):
+            traffic = json.load(open(pj)).get(args.config, {}).get("dram_bytes_per_launch")
+        line["roofline"] = {"bound": "fp32", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                            "traffic": traffic, "kernel": "k_render", "flop_per_ray": flop_per_ray,
+                            "sphere_tests_per_ray": S, "node_tests_per_ray": B,
+                            "peak_source": "measured here: dense FFMA microbenchmark (rt_ffma_peak); MEASURED_PEAKS.json has no FP32 figure",
+                            "note": "FP32 issue is the bounding unit (SURVEY §8d); HBM traffic is the 12 B/pixel frame only"}
+        rti.close()
+    except Exception as e:                                     # the roofline probe must never cost the bench line
+        line["roofline"] = {"bound": "fp32", "error": str(e)}
+
+    # ---- reported CPU baseline: the reference's own code on this box's host cores, bounded sample ----
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            v, info = cpu_reference_sample(args.config)
+            line["cpu_baseline"] = {"value": v, "unit": "Mrays/s", "cores": info["cores"], "kind": info["kind"],
+                                    "sample": info["sample"], "seconds": info["seconds"]}
+        except Exception as e:
+            line["cpu_baseline"] = {"error": str(e)}
+    print(json.dumps(line), flush=True)
+    rt.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

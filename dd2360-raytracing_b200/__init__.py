@@ -21,6 +21,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "librt_b200.so")
+LIB_COUNTERS_PATH = os.path.join(HERE, "librt_b200_counters.so")   # same kernels + work counters (roofline inputs)
 INCLUDE_DIR = os.path.normpath(os.path.join(HERE, "..", "include"))
 
 MAT_NONE, MAT_LAMBERTIAN, MAT_METAL, MAT_DIELECTRIC = -1, 0, 1, 2
@@ -36,9 +37,9 @@ SPHERE_DTYPE = np.dtype(
 ABI_SYMBOLS = [
     "rt_abi_version", "rt_create", "rt_destroy", "rt_last_error", "rt_set_stream", "rt_device_info",
     "rt_scene_generate", "rt_scene_upload", "rt_scene_download", "rt_scene_size", "rt_camera_set", "rt_camera_get",
-    "rt_octree_build", "rt_octree_reference_bytes", "rt_octree_export_reference",
+    "rt_octree_build", "rt_octree_reference_bytes", "rt_octree_export_reference", "rt_octree_debug_read", "rt_trace_rays",
     "rt_render_accumulate", "rt_finalize", "rt_render", "rt_render_to_host", "rt_format_ppm",
-    "rt_malloc", "rt_free", "rt_memcpy_to_host", "rt_synchronize",
+    "rt_ffma_peak", "rt_malloc", "rt_free", "rt_memcpy_to_host", "rt_synchronize",
 ]
 
 
@@ -104,11 +105,14 @@ def load_library(path: str | None = None) -> C.CDLL:
         "rt_octree_build": (i32, [vp, i32, C.POINTER(OctreeStats)]),
         "rt_octree_reference_bytes": (sz, [i32]),
         "rt_octree_export_reference": (i32, [vp, vp, sz]),
+        "rt_octree_debug_read": (sz, [vp, i32, vp, sz]),
+        "rt_trace_rays": (i32, [vp, i32, i32, vp, vp, vp, vp]),
         "rt_render_accumulate": (i32, [vp, C.POINTER(RenderArgs), vp, C.POINTER(RenderStats)]),
         "rt_finalize": (i32, [vp, vp, vp, i32, i32, i32]),
         "rt_render": (i32, [vp, C.POINTER(RenderArgs), vp, C.POINTER(RenderStats)]),
         "rt_render_to_host": (i32, [vp, C.POINTER(RenderArgs), vp, C.POINTER(RenderStats)]),
         "rt_format_ppm": (sz, [vp, i32, i32, vp, sz]),
+        "rt_ffma_peak": (i32, [vp, C.POINTER(f32), C.POINTER(f32)]),
         "rt_malloc": (i32, [vp, sz, C.POINTER(vp)]),
         "rt_free": (i32, [vp, vp]),
         "rt_memcpy_to_host": (i32, [vp, vp, vp, sz]),
@@ -143,8 +147,8 @@ def quantise(fb: np.ndarray) -> np.ndarray:
 class RayTracer:
     """One context per GPU: mirrors the reference's main() call sequence over the C ABI."""
 
-    def __init__(self, device: int = 0):
-        self.L = load_library()
+    def __init__(self, device: int = 0, instrumented: bool = False):
+        self.L = load_library(LIB_COUNTERS_PATH) if instrumented else load_library()
         self._ctx = C.c_void_p()
         rc = self.L.rt_create(device, C.byref(self._ctx))
         if rc != 0:
@@ -217,6 +221,30 @@ class RayTracer:
         self._ck(self.L.rt_octree_export_reference(self._ctx, blob.ctypes.data, n), "rt_octree_export_reference")
         return blob
 
+    def debug_tree(self) -> dict:
+        """Test hook: the internal traversal arrays as raw bytes."""
+        names = ["nodes", "node_ext", "cells", "cell_ext", "vox_start", "vox_refs", "big_refs"]
+        out = {}
+        for k, name in enumerate(names):
+            n = self.L.rt_octree_debug_read(self._ctx, k, None, 0)
+            buf = np.zeros(max(n, 1), dtype=np.uint8)
+            if n:
+                got = self.L.rt_octree_debug_read(self._ctx, k, buf.ctypes.data, n)
+                assert got == n
+            out[name] = buf[:n]
+        return out
+
+    def trace_rays(self, origins: np.ndarray, dirs: np.ndarray, use_octree: bool):
+        """Test hook: closest hit per ray -> (idx[n] int32, t[n] float32)."""
+        o = np.ascontiguousarray(origins, dtype=np.float32)
+        d = np.ascontiguousarray(dirs, dtype=np.float32)
+        n = len(o)
+        idx = np.zeros(n, dtype=np.int32)
+        t = np.zeros(n, dtype=np.float32)
+        self._ck(self.L.rt_trace_rays(self._ctx, int(use_octree), n, o.ctypes.data, d.ctypes.data, idx.ctypes.data, t.ctypes.data),
+                 "rt_trace_rays")
+        return idx, t
+
     # -- render (main.cu:424-429) --
     @staticmethod
     def args(nx, ny, ns, use_octree, max_depth=50, shard_mode=SHARD_NONE, shard_rank=0, shard_count=1,
@@ -245,6 +273,12 @@ class RayTracer:
 
     def finalize(self, accum_dev_ptr: int, fb_dev_ptr: int, nx, ny, ns):
         self._ck(self.L.rt_finalize(self._ctx, C.c_void_p(accum_dev_ptr), C.c_void_p(fb_dev_ptr), nx, ny, ns), "rt_finalize")
+
+    def ffma_peak_tflops(self) -> float:
+        """Measured dense FP32 FFMA rate (TFLOP/s) of this GPU: the FP32 roofline denominator."""
+        t, ms = C.c_float(), C.c_float()
+        self._ck(self.L.rt_ffma_peak(self._ctx, C.byref(t), C.byref(ms)), "rt_ffma_peak")
+        return float(t.value)
 
     def synchronize(self):
         self._ck(self.L.rt_synchronize(self._ctx), "rt_synchronize")

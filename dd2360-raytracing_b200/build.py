@@ -12,6 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "librt_b200.so")
+LIB_COUNTERS = os.path.join(HERE, "librt_b200_counters.so")   # same code with -DRT_COUNTERS: work counters for the roofline
 CLI = os.path.join(HERE, "RayTracing")
 SOURCES = ["rt_abi.cu", "rt_render.cu", "rt_octree.cu"]
 HEADERS = ["rt_math.cuh", "rt_types.h", "rt_shade.cuh", "rt_trace.cuh", "rt_build.cuh", "rt_octree.h", "rt_render.h",
@@ -34,30 +35,36 @@ def _stale(target: str, deps: list[str]) -> bool:
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 
+def _build_lib(target: str, extra: list[str], tag: str, env: dict, verbose: bool) -> None:
+    objs = []
+    os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
+    procs = []
+    for src in SOURCES:
+        obj = os.path.join(HERE, "build", src.replace(".cu", f"{tag}.o"))
+        objs.append(obj)
+        cmd = [_nvcc(), *NVCC_FLAGS, *extra, "-Xptxas", "-v", "-c", os.path.join(CSRC, src), "-o", obj]
+        procs.append((src, subprocess.Popen(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    log = []
+    for src, p in procs:
+        out, _ = p.communicate()
+        log.append(f"== {src}\n{out}")
+        if p.returncode != 0:
+            raise RuntimeError(f"nvcc failed for {src}:\n{out}")
+    with open(os.path.join(HERE, "build", f"ptxas{tag}.log"), "w") as f:
+        f.write("\n".join(log))
+    if verbose:
+        print("\n".join(log))
+    subprocess.run([_nvcc(), "-shared", "-o", target, *objs, "-lcudart_static", "-lpthread", "-ldl", "-lrt"],
+                   check=True, env=env)
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS] + [os.path.abspath(__file__)]
     env = {k: v for k, v in os.environ.items() if k not in ("CC", "CXX")}
     if force or _stale(LIB, deps):
-        objs = []
-        os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
-        procs = []
-        for src in SOURCES:
-            obj = os.path.join(HERE, "build", src.replace(".cu", ".o"))
-            objs.append(obj)
-            cmd = [_nvcc(), *NVCC_FLAGS, "-Xptxas", "-v", "-c", os.path.join(CSRC, src), "-o", obj]
-            procs.append((src, subprocess.Popen(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
-        log = []
-        for src, p in procs:
-            out, _ = p.communicate()
-            log.append(f"== {src}\n{out}")
-            if p.returncode != 0:
-                raise RuntimeError(f"nvcc failed for {src}:\n{out}")
-        with open(os.path.join(HERE, "build", "ptxas.log"), "w") as f:
-            f.write("\n".join(log))
-        if verbose:
-            print("\n".join(log))
-        subprocess.run([_nvcc(), "-shared", "-o", LIB, *objs, "-lcudart_static", "-lpthread", "-ldl", "-lrt"],
-                       check=True, env=env)
+        _build_lib(LIB, [], "", env, verbose)
+    if force or _stale(LIB_COUNTERS, deps):
+        _build_lib(LIB_COUNTERS, ["-DRT_COUNTERS"], "_counters", env, False)
     cli_src = os.path.join(CSRC, "raytracing_main.cpp")
     if os.path.exists(cli_src) and (force or _stale(CLI, [cli_src, LIB])):
         subprocess.run(["g++", "-O2", "-std=c++17", "-I", os.path.join(HERE, "..", "include"), cli_src, "-o", CLI,

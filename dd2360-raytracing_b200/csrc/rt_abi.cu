@@ -323,6 +323,12 @@ extern "C" int rt_octree_export_reference(rt_context *ctx, void *host_blob, size
     return RT_OK;
 }
 
+extern "C" size_t rt_octree_debug_read(rt_context *ctx, int which, void *host, size_t cap) {
+    if (!ctx) return 0;
+    cudaSetDevice(ctx->device);
+    return ctx->octree->debug_read(ctx->stream, which, host, cap);
+}
+
 // ---- render -----------------------------------------------------------------------------------------------------
 static int do_render(rt_context *ctx, const rt_render_args *a, float *out_dev, bool finalize, rt_render_stats *stats) {
     if (!ctx || !a || !out_dev) return fail(ctx, RT_ERR_INVALID, "render: null argument");
@@ -373,6 +379,7 @@ static int do_render(rt_context *ctx, const rt_render_args *a, float *out_dev, b
     if (owned * 32 > 0xfffffff0ll) return fail(ctx, RT_ERR_INVALID, "render: image too large for the 32-bit work queue");
     p.total_items = (uint32_t)(owned * 32);
     p.finalize = finalize ? 1 : 0;
+    p.stage_tree = getenv("RT_NO_SMEM_TREE") ? 0 : 1;
     p.out = out_dev;
     p.work_counter = ctx->work_counter;
     p.counters = ctx->counters;
@@ -382,17 +389,42 @@ static int do_render(rt_context *ctx, const rt_render_args *a, float *out_dev, b
     CK(launch_render(p, a->use_octree != 0, ctx->prop.multiProcessorCount, ctx->prop.sharedMemPerBlockOptin, ctx->stream, &blocks));
     CK(cudaEventRecord(ctx->ev1, ctx->stream));
     if (stats) {
-        unsigned long long c[2] = {0, 0};
+        unsigned long long c[5] = {0, 0, 0, 0, 0};
         CK(cudaMemcpyAsync(c, ctx->counters, sizeof c, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaEventSynchronize(ctx->ev1));
         CK(cudaStreamSynchronize(ctx->stream));
         memset(stats, 0, sizeof *stats);
         stats->rays = c[0]; stats->paths = c[1];
+        stats->sphere_tests = c[2]; stats->node_tests = c[3];   // zero unless built with -DRT_COUNTERS
         float ms = 0;
         cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
         stats->kernel_ms = ms;
         stats->launches = 1;
     }
+    return RT_OK;
+}
+
+// test hook: closest hit of caller-supplied rays (host arrays of 3 floats per ray)
+extern "C" int rt_trace_rays(rt_context *ctx, int use_octree, int n, const float *org, const float *dir, int *out_idx, float *out_t) {
+    if (!ctx || n < 1 || !org || !dir || !out_idx || !out_t) return fail(ctx, RT_ERR_INVALID, "rt_trace_rays: bad arguments");
+    if (ctx->n < 1) return fail(ctx, RT_ERR_STATE, "rt_trace_rays: no scene");
+    if (use_octree && !ctx->octree->built) return fail(ctx, RT_ERR_STATE, "rt_trace_rays: no octree built");
+    CK(cudaSetDevice(ctx->device));
+    float *d_o = nullptr, *d_d = nullptr, *d_t = nullptr;
+    int *d_i = nullptr;
+    CK(cudaMalloc(&d_o, (size_t)n * 12)); CK(cudaMalloc(&d_d, (size_t)n * 12));
+    CK(cudaMalloc(&d_t, (size_t)n * 4)); CK(cudaMalloc(&d_i, (size_t)n * 4));
+    CK(cudaMemcpyAsync(d_o, org, (size_t)n * 12, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_d, dir, (size_t)n * 12, cudaMemcpyHostToDevice, ctx->stream));
+    RenderLaunch p;
+    memset(&p, 0, sizeof p);
+    p.scene.geom = ctx->geom; p.scene.matl = ctx->matl; p.scene.tag = ctx->tag; p.scene.n = ctx->n;
+    if (use_octree) p.tree = ctx->octree->view();
+    CK(launch_trace_rays(p, use_octree != 0, d_o, d_d, n, d_i, d_t, ctx->stream));
+    CK(cudaMemcpyAsync(out_idx, d_i, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(out_t, d_t, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(d_o); cudaFree(d_d); cudaFree(d_t); cudaFree(d_i);
     return RT_OK;
 }
 
@@ -457,6 +489,40 @@ extern "C" size_t rt_format_ppm(const float *fb, int nx, int ny, char *buf, size
         }
     }
     return off;
+}
+
+// ---- FP32 roofline denominator: dense FFMA issue rate of this GPU, measured -------------------------------------
+__global__ void __launch_bounds__(256) k_ffma_peak(float *out, int iters, float a, float b) {
+    float x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int u = 0; u < 16; u++) {
+            x0 = __fmaf_rn(x0, a, b); x1 = __fmaf_rn(x1, a, b); x2 = __fmaf_rn(x2, a, b); x3 = __fmaf_rn(x3, a, b);
+            x4 = __fmaf_rn(x4, a, b); x5 = __fmaf_rn(x5, a, b); x6 = __fmaf_rn(x6, a, b); x7 = __fmaf_rn(x7, a, b);
+        }
+    }
+    const float s = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+    if (s == 12345.678f) out[0] = s;   // keeps the chain alive, never true in practice
+}
+
+extern "C" int rt_ffma_peak(rt_context *ctx, float *tflops, float *ms_out) {
+    if (!ctx || !tflops) return RT_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    const int blocks = ctx->prop.multiProcessorCount * 8, threads = 256, iters = 4096;
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; rep++) {
+        CK(cudaEventRecord(ctx->ev0, ctx->stream));
+        k_ffma_peak<<<blocks, threads, 0, ctx->stream>>>(reinterpret_cast<float *>(ctx->counters), iters, 1.000001f, 1e-7f);
+        CK(cudaEventRecord(ctx->ev1, ctx->stream));
+        CK(cudaEventSynchronize(ctx->ev1));
+        float ms = 0;
+        cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+        if (rep > 0 && ms < best) best = ms;
+    }
+    const double flops = 2.0 * 8 * 16 * (double)iters * blocks * threads;
+    *tflops = (float)(flops / (best * 1e-3) / 1e12);
+    if (ms_out) *ms_out = best;
+    return RT_OK;
 }
 
 // ---- device memory helpers -----------------------------------------------------------------------------------------

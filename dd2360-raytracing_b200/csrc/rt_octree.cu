@@ -588,6 +588,27 @@ cudaError_t OctreeBuilder::export_reference(cudaStream_t st, void *host_blob, si
     return cudaGetLastError();
 }
 
+size_t OctreeBuilder::debug_read(cudaStream_t st, int which, void *host, size_t cap_bytes) const {
+    if (!built) return 0;
+    const void *src = nullptr;
+    size_t bytes = 0;
+    switch (which) {
+        case 0: src = d.nodes; bytes = (size_t)counts.node_count * sizeof(TreeNode); break;
+        case 1: src = d.node_ext; bytes = (size_t)counts.node_count * sizeof(TreeExtent); break;
+        case 2: src = d.cells; bytes = (size_t)counts.cell_count * sizeof(CellGrid); break;
+        case 3: src = d.cell_ext; bytes = (size_t)counts.cell_count * sizeof(TreeExtent); break;
+        case 4: src = d.vox_start; bytes = ((size_t)counts.total_voxels + 1) * 4; break;
+        case 5: src = d.vox_refs; bytes = (size_t)total_refs * 4; break;
+        case 6: src = d.big_refs; bytes = (size_t)counts.cell_count * kMaxBigPerCell * 4; break;
+        default: return 0;
+    }
+    if (!host) return bytes;
+    if (cap_bytes < bytes) return 0;
+    if (bytes && cudaMemcpyAsync(host, src, bytes, cudaMemcpyDeviceToHost, st) != cudaSuccess) return 0;
+    cudaStreamSynchronize(st);
+    return bytes;
+}
+
 TreeView OctreeBuilder::view() const {
     TreeView v;
     memset(&v, 0, sizeof v);

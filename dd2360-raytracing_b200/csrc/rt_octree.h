@@ -29,6 +29,9 @@ public:
     // the tree in the reference's own layout (acceleration_structure.h:23-61), assembled on the GPU on demand
     cudaError_t export_reference(cudaStream_t st, void *host_blob, size_t bytes);
     TreeView view() const;
+    // test hook: copy one internal array to the host (0 nodes, 1 node_ext, 2 cells, 3 cell_ext, 4 vox_start,
+    // 5 vox_refs, 6 big_refs); returns the byte size when host == nullptr
+    size_t debug_read(cudaStream_t st, int which, void *host, size_t cap) const;
 
     bool built = false, blob_valid = false;
     int spl = 0, n_spheres = 0, leaf_count_h = 0;

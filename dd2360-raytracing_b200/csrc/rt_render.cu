@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(kRenderThreads, 4) k_render(const __grid_const
         uint32_t total = 0;
         if (threadIdx.x == 0) mbar_init(&bar, 1);
         __syncthreads();
-        if (OCTREE) {
+        if (OCTREE && p.stage_tree) {
             const uint32_t nb = (uint32_t)tv.node_count * sizeof(TreeNode), eb = (uint32_t)tv.node_count * sizeof(TreeExtent);
             const uint32_t cb = (uint32_t)tv.cell_count * sizeof(CellGrid), xb = (uint32_t)tv.cell_count * sizeof(TreeExtent);
             unsigned char *s_nodes = cur; cur += nb;
@@ -134,6 +134,8 @@ __global__ void __launch_bounds__(kRenderThreads, 4) k_render(const __grid_const
     rng.d = rng.v0 = rng.v1 = rng.v2 = rng.v3 = rng.v4 = 0;
     vec3f o = mk(0, 0, 0), d = mk(0, 0, 1), att = mk(1, 1, 1), col = mk(0, 0, 0);
     uint32_t nrays = 0, npaths = 0;
+    TraceCounters tc;
+    tc.sphere_tests = tc.node_tests = tc.voxel_steps = 0;
     bool exhausted = false;
     uint32_t first_item = gwarp * 32u + lane;   // the first claim needs no atomic: the queue head starts past the grid
     bool first = true;
@@ -180,9 +182,9 @@ __global__ void __launch_bounds__(kRenderThreads, 4) k_render(const __grid_const
             // ---- one iteration of color()'s loop (main.cu:47-73) ----
             nrays++;
             Hit h;
-            if (OCTREE) h = trace_tree(sc, tv, &p.tree.planes[0][0], o, d);
-            else if (GEOM_SMEM) h = trace_list(geom_s, sc.tag, sc.n, o, d);
-            else h = trace_list(sc.geom, sc.tag, sc.n, o, d);
+            if (OCTREE) h = trace_tree(sc, tv, &p.tree.planes[0][0], o, d, tc);
+            else if (GEOM_SMEM) h = trace_list(geom_s, sc.tag, sc.n, o, d, tc);
+            else h = trace_list(sc.geom, sc.tag, sc.n, o, d, tc);
             bool sample_done = false;
             vec3f contrib = mk(0, 0, 0);
             if (h.idx >= 0) {
@@ -234,6 +236,33 @@ __global__ void __launch_bounds__(kRenderThreads, 4) k_render(const __grid_const
         atomicAdd(p.counters + 0, r64);
         atomicAdd(p.counters + 1, p64);
     }
+#ifdef RT_COUNTERS
+    unsigned long long c64[3] = {tc.sphere_tests, tc.node_tests, tc.voxel_steps};
+    for (int k = 0; k < 3; k++) {
+        for (int off = 16; off > 0; off >>= 1) c64[k] += __shfl_xor_sync(0xffffffffu, c64[k], off);
+        if (lane == 0) atomicAdd(p.counters + 2 + k, c64[k]);
+    }
+#endif
+}
+
+// Closest hit for caller-supplied rays (test hook: per-ray parity against the oracle's hitTree / hitable_list::hit)
+__global__ void k_trace_rays(const __grid_constant__ RenderLaunch p, int octree, const float *__restrict__ org,
+                             const float *__restrict__ dir, int n, int *__restrict__ out_idx, float *__restrict__ out_t) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const vec3f o = mk(org[3 * i], org[3 * i + 1], org[3 * i + 2]), d = mk(dir[3 * i], dir[3 * i + 1], dir[3 * i + 2]);
+    TraceCounters tc;
+    tc.sphere_tests = tc.node_tests = tc.voxel_steps = 0;
+    const Hit h = octree ? trace_tree(p.scene, p.tree, &p.tree.planes[0][0], o, d, tc)
+                         : trace_list(p.scene.geom, p.scene.tag, p.scene.n, o, d, tc);
+    out_idx[i] = h.idx;
+    out_t[i] = h.t;
+}
+
+cudaError_t launch_trace_rays(const RenderLaunch &p, bool octree, const float *org, const float *dir, int n, int *out_idx,
+                              float *out_t, cudaStream_t st) {
+    k_trace_rays<<<(n + 127) / 128, 128, 0, st>>>(p, octree ? 1 : 0, org, dir, n, out_idx, out_t);
+    return cudaGetLastError();
 }
 
 // fb = sqrt(accum * (1/ns)) (main.cu:111-114), for frames assembled from shards
@@ -276,7 +305,7 @@ cudaError_t launch_render(const RenderLaunch &p, bool octree, int sm_count, size
     if (octree) {
         const size_t smem = (size_t)p.tree.node_count * (sizeof(TreeNode) + sizeof(TreeExtent)) +
                             (size_t)p.tree.cell_count * (sizeof(CellGrid) + sizeof(TreeExtent));
-        return launch_variant<true, false>(p, smem, sm_count, st, blocks_out);
+        return launch_variant<true, false>(p, p.stage_tree ? smem : 0, sm_count, st, blocks_out);
     }
     const size_t geom_bytes = (size_t)p.scene.n * sizeof(float4);
     if (geom_bytes + 1024 <= smem_limit) return launch_variant<false, true>(p, geom_bytes, sm_count, st, blocks_out);

@@ -20,6 +20,7 @@ struct RenderLaunch {
     int tile_first, tile_stride;   // this shard owns tiles tile_first + k*tile_stride
     uint32_t total_items;    // owned tiles * 32
     unsigned long long seed_offset;   // added to the per-pixel seed 1984 + pixel_index (spp shards)
+    int stage_tree;          // 1: stage nodes/boxes/cells in shared memory (default); 0: read them through L1/L2
     int finalize;            // 1: write sqrt(sum/ns) (main.cu:111-115); 0: write the linear sum
     float *out;              // nx*ny*3 floats
     uint32_t *work_counter;  // queue head
@@ -30,6 +31,8 @@ cudaError_t upload_camera(const CameraData &cam, cudaStream_t st);
 cudaError_t upload_camera_from_device(const CameraData *cam_dev, cudaStream_t st);
 cudaError_t launch_render(const RenderLaunch &p, bool octree, int sm_count, size_t smem_limit, cudaStream_t st,
                           int *blocks_out);
+cudaError_t launch_trace_rays(const RenderLaunch &p, bool octree, const float *org, const float *dir, int n, int *out_idx,
+                              float *out_t, cudaStream_t st);
 cudaError_t launch_finalize(const float *accum, float *fb, int nx, int ny, int ns, cudaStream_t st);
 
 }  // namespace rt

@@ -31,19 +31,30 @@ struct Hit {
     int idx;
 };
 
+// Work counters of the instrumented build (-DRT_COUNTERS -> librt_b200_counters.so); compiled out otherwise.
+struct TraceCounters {
+    uint32_t sphere_tests, node_tests, voxel_steps;
+};
+#ifdef RT_COUNTERS
+#define RT_COUNT(field) (tc.field++)
+#else
+#define RT_COUNT(field) ((void)0)
+#endif
+
 // Ties: two DIFFERENT spheres with bit-identical t keep whichever is tested first, here as in the reference
 // (strict '<').  Voxel reference lists are sorted at build time, so the outcome is deterministic run to run;
 // it could differ from the reference's pick only for such exact ties, which the generated scenes do not produce.
 
 // ---- flat list: every sphere, SoA float4, warp-uniform address (broadcast) ------------------------------------
 template <typename GeomPtr>
-RT_HD Hit trace_list(const GeomPtr geom, const int *tag, const int n, const vec3f o, const vec3f d) {
+RT_HD Hit trace_list(const GeomPtr geom, const int *tag, const int n, const vec3f o, const vec3f d, TraceCounters &tc) {
     Hit h;
     h.t = kTMax; h.idx = -1;
     const float a = dot3(d, d);
     for (int i = 0; i < n; i++) {
         const float4 s = geom[i];
         float t;
+        RT_COUNT(sphere_tests);
         // slots create_world never wrote carry radius 0 and tag NONE: skipped
         if (sphere_test(s, o, d, a, h.t, t) && RT_LDG(tag + i) >= 0) { h.t = t; h.idx = i; }
     }
@@ -87,7 +98,7 @@ RT_HD bool ray_box(const RayPre &r, const float *lo, const float *hi, const floa
 
 // Walk one cell's sub-grid with a 3D-DDA and test the spheres registered in every voxel the ray crosses.
 RT_HD void trace_cell(const SceneView &sc, const TreeView &tv, const CellGrid &g, const RayPre &r, float t0, float t1,
-                      Hit &h) {
+                      Hit &h, TraceCounters &tc) {
     const int nx = (int)(g.dims & 1023u), ny = (int)((g.dims >> 10) & 1023u), nz = (int)(g.dims >> 20);
     // entry point, nudged inside; clamp handles rounding at the faces
     const float te = fmaxf(t0, 0.0f);
@@ -112,12 +123,14 @@ RT_HD void trace_cell(const SceneView &sc, const TreeView &tv, const CellGrid &g
     for (int step = 0; step < max_steps; step++) {
         // a later voxel can only hold hits at t >= t_in (minus the float slack)
         if (t_in > h.t * (1.0f + kTSlackRel) + kTSlackAbs) break;
+        RT_COUNT(voxel_steps);
         const uint32_t v = g.vox_base + (uint32_t)((iz * ny + iy) * nx + ix);
         const uint32_t b = RT_LDG(tv.vox_start + v), e = RT_LDG(tv.vox_start + v + 1);
         for (uint32_t k = b; k < e; k++) {
             const int idx = (int)RT_LDG(tv.vox_refs + k);
             const float4 s = RT_LDG(sc.geom + idx);
             float t;
+            RT_COUNT(sphere_tests);
             if (sphere_test(s, r.o, r.d, r.a, h.t, t)) { h.t = t; h.idx = idx; }
         }
         // step to the neighbour the ray enters next
@@ -130,7 +143,8 @@ RT_HD void trace_cell(const SceneView &sc, const TreeView &tv, const CellGrid &g
 
 // acceleration_structure.h:319-342 hitTree, re-organised (see the header comment)
 // `planes` = the 3 x 9 slab plane coordinates (kept in the kernel's constant parameter space)
-RT_HD Hit trace_tree(const SceneView &sc, const TreeView &tv, const float *planes, const vec3f o, const vec3f d) {
+RT_HD Hit trace_tree(const SceneView &sc, const TreeView &tv, const float *planes, const vec3f o, const vec3f d,
+                    TraceCounters &tc) {
     Hit h;
     h.t = kTMax; h.idx = -1;
     RayPre r;
@@ -139,6 +153,7 @@ RT_HD Hit trace_tree(const SceneView &sc, const TreeView &tv, const float *plane
     r.inv = mk(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
     {   // ground sphere first (:322-332)
         float t;
+        RT_COUNT(sphere_tests);
         if (sphere_test(RT_LDG(sc.geom), o, d, r.a, kTMax, t)) { h.t = t; h.idx = 0; }
     }
     // front-to-back child order: flip the child bits along which the ray travels in the negative direction
@@ -148,11 +163,13 @@ RT_HD Hit trace_tree(const SceneView &sc, const TreeView &tv, const float *plane
         const int c1 = root.child[k1 ^ flip];
         if (c1 == 0) continue;   // 0 = absent, as in the reference (the root is nobody's child)
         float te, tx;
+        RT_COUNT(node_tests);
         if (!ray_box(r, tv.node_ext[c1].lo, tv.node_ext[c1].hi, h.t * (1.0f + kTSlackRel) + kTSlackAbs, te, tx)) continue;
         const TreeNode &n1 = tv.nodes[c1];
         for (int k2 = 0; k2 < 8; k2++) {
             const int c2 = n1.child[k2 ^ flip];
             if (c2 == 0) continue;
+            RT_COUNT(node_tests);
             if (!ray_box(r, tv.node_ext[c2].lo, tv.node_ext[c2].hi, h.t * (1.0f + kTSlackRel) + kTSlackAbs, te, tx)) continue;
             const TreeNode &n2 = tv.nodes[c2];
             for (int k3 = 0; k3 < 8; k3++) {
@@ -161,9 +178,11 @@ RT_HD Hit trace_tree(const SceneView &sc, const TreeView &tv, const float *plane
                 const TreeNode &n3 = tv.nodes[c3];
                 if (n3.first_cell == 0xffffffffu) continue;   // nothing traceable stored in this cell
                 const int cell = (int)n3.first_cell;
+                RT_COUNT(node_tests);
                 if (!ray_box(r, tv.cell_ext[cell].lo, tv.cell_ext[cell].hi, h.t * (1.0f + kTSlackRel) + kTSlackAbs, te, tx))
                     continue;
                 // the reference only looks into this cell when the infinite line crosses its AABB
+                RT_COUNT(node_tests);
                 if (!ref_line_test(o, d, planes[n3.ix], planes[kPlanes + n3.iy], planes[2 * kPlanes + n3.iz],
                                    planes[n3.ix + 1], planes[kPlanes + n3.iy + 1], planes[2 * kPlanes + n3.iz + 1]))
                     continue;
@@ -173,11 +192,12 @@ RT_HD Hit trace_tree(const SceneView &sc, const TreeView &tv, const float *plane
                 for (uint32_t k = 0; k < nb; k++) {
                     const int idx = (int)RT_LDG(tv.big_refs + bb + k);
                     float t;
+                    RT_COUNT(sphere_tests);
                     if (sphere_test(RT_LDG(sc.geom + idx), o, d, r.a, h.t, t)) { h.t = t; h.idx = idx; }
                 }
                 // small spheres: walk the sub-grid where the ray overlaps it
                 if (g.dims && ray_box(r, g.org, g.hi, h.t * (1.0f + kTSlackRel) + kTSlackAbs, te, tx))
-                    trace_cell(sc, tv, g, r, te, tx, h);
+                    trace_cell(sc, tv, g, r, te, tx, h, tc);
             }
         }
     }

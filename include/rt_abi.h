@@ -109,6 +109,13 @@ size_t rt_octree_reference_bytes(int spheres_per_leaf);      /* sizeof(Octree) f
 /* the tree in the reference's own memory layout (acceleration_structure.h:23-61), for the bit-exact check */
 int rt_octree_export_reference(rt_context *ctx, void *host_blob, size_t bytes);
 
+/* test hook: read one internal traversal array back (0 nodes, 1 node extents, 2 cells, 3 cell extents, 4 voxel
+ * offsets, 5 voxel references, 6 big-sphere lists).  Returns the byte size (host == NULL) or bytes copied. */
+size_t rt_octree_debug_read(rt_context *ctx, int which, void *host, size_t cap);
+
+/* test hook: closest hit (sphere index or -1, and t) of n caller-supplied rays — hitTree / hitable_list::hit per ray */
+int rt_trace_rays(rt_context *ctx, int use_octree, int n, const float *org, const float *dir, int *out_idx, float *out_t);
+
 /* ---- render: replaces render_init + render (main.cu:424-429) ---------------------------------------------- */
 /* Renders this rank's shard into `accum_dev` (device pointer, nx*ny*3 floats): LINEAR radiance sums (before
  * /ns and sqrt), zero where the shard owns nothing, so that shards add up (main.cu:119-142 semantics). */
@@ -123,6 +130,9 @@ int rt_render_to_host(rt_context *ctx, const rt_render_args *args, float *fb_hos
 /* ---- output: replaces output_to_stream (main.cu:321-333) -------------------------------------------------- */
 /* P3 text, byte-identical to the reference writer.  Returns bytes needed when buf == NULL. */
 size_t rt_format_ppm(const float *fb_host, int nx, int ny, char *buf, size_t cap);
+
+/* ---- measurement: dense FP32 FFMA rate of this GPU (2 flop per FFMA), the denominator of the FP32 roofline -------- */
+int rt_ffma_peak(rt_context *ctx, float *tflops, float *kernel_ms);
 
 /* ---- device memory helpers for hosts without a CUDA runtime binding ---------------------------------------- */
 int rt_malloc(rt_context *ctx, size_t bytes, void **dev_ptr);

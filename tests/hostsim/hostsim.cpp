@@ -165,8 +165,9 @@ extern "C" {
 
 // camera22: origin, llc, horizontal, vertical, u, v, w, lens_radius (taken from the oracle so that only the
 // hot path is under test here)
-int hs_render(const hs_sphere *sph, int n, const float *camera22, const void *blob, const hs_params *p, float density,
-              float *fb_gamma, float *fb_linear, hs_counters *ctr_out, uint64_t *build_stats /* voxels, refs */) {
+static int render_core(const hs_sphere *sph, int n, const float *camera22, const void *blob, const hs_params *p, float density,
+              float *fb_gamma, float *fb_linear, hs_counters *ctr_out, uint64_t *build_stats /* voxels, refs */,
+              const TreeView *given) {
     std::vector<float4> geom((size_t)n), matl((size_t)n);
     std::vector<int> tag((size_t)n);
     for (int i = 0; i < n; i++) {
@@ -179,7 +180,10 @@ int hs_render(const hs_sphere *sph, int n, const float *camera22, const void *bl
     HostTree T;
     TreeView tv;
     memset(&tv, 0, sizeof tv);
-    if (p->use_octree) {
+    if (p->use_octree && given) {
+        tv = *given;
+        make_planes(T.planes);
+    } else if (p->use_octree) {
         build_host_tree(geom, tag, static_cast<const int32_t *>(blob), p->spl, density, T);
         tv.nodes = T.nodes.data(); tv.node_ext = T.node_ext.data(); tv.cells = T.cells.data();
         tv.cell_ext = T.cell_ext.data(); tv.vox_start = T.vox_start.data(); tv.vox_refs = T.vox_refs.data();
@@ -212,8 +216,9 @@ int hs_render(const hs_sphere *sph, int n, const float *camera22, const void *bl
                     c.paths++;
                     for (int depth = 0; depth < p->max_depth; depth++) {
                         c.rays++;
-                        Hit h = p->use_octree ? trace_tree(sc, tv, &T.planes[0][0], o, d)
-                                              : trace_list(sc.geom, sc.tag, sc.n, o, d);
+                        TraceCounters tcn{};
+                        Hit h = p->use_octree ? trace_tree(sc, tv, &T.planes[0][0], o, d, tcn)
+                                              : trace_list(sc.geom, sc.tag, sc.n, o, d, tcn);
                         if (h.idx >= 0) {
                             vec3f hp, hn, a, dn;
                             hit_point(geom[(size_t)h.idx], o, d, h.t, hp, hn);
@@ -242,6 +247,49 @@ int hs_render(const hs_sphere *sph, int n, const float *camera22, const void *bl
     }
     if (ctr_out) *ctr_out = total;
     return 0;
+}
+
+
+int hs_render(const hs_sphere *sph, int n, const float *camera22, const void *blob, const hs_params *p, float density,
+              float *fb_gamma, float *fb_linear, hs_counters *ctr_out, uint64_t *build_stats) {
+    return render_core(sph, n, camera22, blob, p, density, fb_gamma, fb_linear, ctr_out, build_stats, nullptr);
+}
+
+// Same renderer over traversal arrays produced elsewhere (the GPU build, read back with rt_octree_debug_read).
+int hs_render_with_tree(const hs_sphere *sph, int n, const float *camera22, const hs_params *p, float *fb_gamma,
+                        hs_counters *ctr_out, const void *nodes, int node_count, const void *node_ext, const void *cells,
+                        int cell_count, const void *cell_ext, const void *vox_start, const void *vox_refs, const void *big_refs) {
+    TreeView tv;
+    memset(&tv, 0, sizeof tv);
+    tv.nodes = static_cast<const TreeNode *>(nodes); tv.node_ext = static_cast<const TreeExtent *>(node_ext);
+    tv.cells = static_cast<const CellGrid *>(cells); tv.cell_ext = static_cast<const TreeExtent *>(cell_ext);
+    tv.vox_start = static_cast<const uint32_t *>(vox_start); tv.vox_refs = static_cast<const uint32_t *>(vox_refs);
+    tv.big_refs = static_cast<const uint32_t *>(big_refs);
+    tv.node_count = node_count; tv.cell_count = cell_count;
+    return render_core(sph, n, camera22, nullptr, p, 0.f, fb_gamma, nullptr, ctr_out, nullptr, &tv);
+}
+
+// Host-built traversal arrays, for comparison with the ones the GPU build produces (rt_octree_debug_read):
+// which = 0 nodes, 1 node_ext, 2 cells, 3 cell_ext, 4 vox_start, 5 vox_refs, 6 big_refs.  Returns bytes.
+size_t hs_tree_dump(const hs_sphere *sph, int n, const void *blob, int spl, float density, int which, void *out, size_t cap) {
+    std::vector<float4> geom((size_t)n);
+    std::vector<int> tag((size_t)n);
+    for (int i = 0; i < n; i++) { geom[(size_t)i] = make_float4(sph[i].cx, sph[i].cy, sph[i].cz, sph[i].radius); tag[(size_t)i] = sph[i].mat; }
+    HostTree T;
+    build_host_tree(geom, tag, static_cast<const int32_t *>(blob), spl, density, T);
+    const void *src = nullptr;
+    size_t bytes = 0;
+    switch (which) {
+        case 0: src = T.nodes.data(); bytes = T.nodes.size() * sizeof(TreeNode); break;
+        case 1: src = T.node_ext.data(); bytes = T.node_ext.size() * sizeof(TreeExtent); break;
+        case 2: src = T.cells.data(); bytes = T.cells.size() * sizeof(CellGrid); break;
+        case 3: src = T.cell_ext.data(); bytes = T.cell_ext.size() * sizeof(TreeExtent); break;
+        case 4: src = T.vox_start.data(); bytes = T.vox_start.size() * 4; break;
+        case 5: src = T.vox_refs.data(); bytes = T.vox_refs.size() * 4; break;
+        case 6: src = T.big_refs.data(); bytes = T.big_refs.size() * 4; break;
+    }
+    if (out && cap >= bytes && bytes) memcpy(out, src, bytes);
+    return bytes;
 }
 
 }  // extern "C"
