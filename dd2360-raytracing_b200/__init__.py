@@ -223,7 +223,7 @@ class RayTracer:
 
     def debug_tree(self) -> dict:
         """Test hook: the internal traversal arrays as raw bytes."""
-        names = ["nodes", "node_ext", "cells", "cell_ext", "vox_start", "vox_refs", "big_refs"]
+        names = ["grid", "vox", "refs", "ent_off", "ent_cell", "big_refs", "sph_flag"]
         out = {}
         for k, name in enumerate(names):
             n = self.L.rt_octree_debug_read(self._ctx, k, None, 0)

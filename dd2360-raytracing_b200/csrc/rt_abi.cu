@@ -306,7 +306,7 @@ extern "C" int rt_octree_build(rt_context *ctx, int spl, rt_octree_stats *stats)
         stats->entries = (int64_t)ctx->octree->stats_h[0];
         stats->dropped_full = (int64_t)ctx->octree->stats_h[1];
         stats->dropped_outside = (int64_t)ctx->octree->stats_h[2];
-        stats->fine_voxels = ctx->octree->counts.total_voxels;
+        stats->fine_voxels = ctx->octree->total_voxels;
         stats->fine_refs = ctx->octree->total_refs;
         stats->leaf_count = 0;   // known once the reference layout is exported
     }
@@ -379,7 +379,6 @@ static int do_render(rt_context *ctx, const rt_render_args *a, float *out_dev, b
     if (owned * 32 > 0xfffffff0ll) return fail(ctx, RT_ERR_INVALID, "render: image too large for the 32-bit work queue");
     p.total_items = (uint32_t)(owned * 32);
     p.finalize = finalize ? 1 : 0;
-    p.stage_tree = getenv("RT_NO_SMEM_TREE") ? 0 : 1;
     p.out = out_dev;
     p.work_counter = ctx->work_counter;
     p.counters = ctx->counters;

@@ -90,10 +90,11 @@ RT_HD bool shell_hits_box(const float4 s, const float pad, const float *lo, cons
 }
 
 
-// Sub-grid resolution for one cell: about `density` voxels per stored sphere, voxels as cubic as the bounding
-// box allows.  Fills org/hi/vs/inv_vs/dims; returns the voxel count (0 when there is nothing to grid).
-RT_HD uint32_t choose_grid(const float *lo, const float *hi, uint32_t live, float density, CellGrid &g) {
-    if (live == 0) { g.dims = 0; return 0; }
+// Grid resolution: about `density` voxels per gridded sphere, voxels as cubic as the bounding box allows.
+// Fills org/hi/vs/inv_vs/n*; returns the voxel count (0 when there is nothing to grid).  Runs on the host.
+inline uint32_t choose_grid(const float *lo, const float *hi, uint32_t live, float density, GridView &g) {
+    g.nx = g.ny = g.nz = 0;
+    if (live == 0) return 0;
     float sz[3];
     for (int k = 0; k < 3; k++) {
         g.org[k] = lo[k];
@@ -102,23 +103,23 @@ RT_HD uint32_t choose_grid(const float *lo, const float *hi, uint32_t live, floa
     }
     const float vol = sz[0] * sz[1] * sz[2];
     float target = density * (float)live;
-    target = fminf(fmaxf(target, 1.f), 4194304.f);
+    target = fminf(fmaxf(target, 1.f), 16777216.f);
     const float edge = cbrtf(vol / target);
-    uint32_t d[3];
+    int d[3];
     for (int k = 0; k < 3; k++) {
         float c = ceilf(sz[k] / edge);
-        c = fminf(fmaxf(c, 1.f), 1023.f);
-        d[k] = (uint32_t)c;
+        c = fminf(fmaxf(c, 1.f), 2047.f);
+        d[k] = (int)c;
         g.vs[k] = sz[k] / (float)d[k];
         g.inv_vs[k] = (float)d[k] / sz[k];
     }
-    g.dims = d[0] | d[1] << 10 | d[2] << 20;
-    return d[0] * d[1] * d[2];
+    g.nx = d[0]; g.ny = d[1]; g.nz = d[2];
+    return (uint32_t)d[0] * (uint32_t)d[1] * (uint32_t)d[2];
 }
 
 // voxel index range (inclusive, clamped) a padded sphere can touch along each axis
-RT_HD void voxel_range(const CellGrid &g, const float4 s, float pad, int *v0, int *v1) {
-    const int n[3] = {(int)(g.dims & 1023u), (int)((g.dims >> 10) & 1023u), (int)(g.dims >> 20)};
+RT_HD void voxel_range(const GridView &g, const float4 s, float pad, int *v0, int *v1) {
+    const int n[3] = {g.nx, g.ny, g.nz};
     const float c[3] = {s.x, s.y, s.z};
     const float r = s.w + pad;
     for (int k = 0; k < 3; k++) {
@@ -128,7 +129,7 @@ RT_HD void voxel_range(const CellGrid &g, const float4 s, float pad, int *v0, in
         v1[k] = b > n[k] - 1 ? n[k] - 1 : b;
     }
 }
-RT_HD void voxel_box(const CellGrid &g, int x, int y, int z, float *lo, float *hi) {
+RT_HD void voxel_box(const GridView &g, int x, int y, int z, float *lo, float *hi) {
     lo[0] = g.org[0] + (float)x * g.vs[0]; hi[0] = g.org[0] + (float)(x + 1) * g.vs[0];
     lo[1] = g.org[1] + (float)y * g.vs[1]; hi[1] = g.org[1] + (float)(y + 1) * g.vs[1];
     lo[2] = g.org[2] + (float)z * g.vs[2]; hi[2] = g.org[2] + (float)(z + 1) * g.vs[2];

@@ -1,23 +1,27 @@
 // rt_octree.cu — parallel GPU build of (a) the traversal structure the render kernel uses and (b) the tree in the
 // reference's own memory layout, bit-exact against the serial buildOctree (acceleration_structure.h:195-217).
 //
-// Pipeline (one stream, no host round trip except two size read-backs needed to allocate):
-//   k_classify     sphere -> per-axis level-3 slab ranges (reference `intersects` semantics), entry count,
-//                  per-cell histogram (shared-memory privatised)
-//   scan           entry offsets                                             (cub::DeviceScan)
-//   k_emit         (Morton cell key, sphere index) pairs in sphere order
-//   radix sort     stable, 9 key bits -> cell-major, sphere-ascending         (cub::DeviceRadixSort)
-//   k_cell_grid    per cell: big/small split, bounding box of the stored list, sub-grid dimensions
-//   k_assemble     one block: first-touch numbering of nodes (reference order), packed 32-byte nodes,
-//                  content extents bottom-up, voxel bases
-//   k_vox_count / scan / k_vox_fill / k_vox_sort   sphere-surface x voxel incidence lists
-//   (on export)    k_leaf_number, k_blob_nodes, k_blob_leaves -> reference `Octree` blob
+// Pipeline (one stream; three small read-backs size the allocations):
+//   k_classify      sphere -> per-axis level-3 slab ranges (reference `intersects` semantics), entry count,
+//                   per-cell histogram (shared-memory privatised)
+//   scan            entry offsets (also the per-sphere cell lists of VisView)       (cub::DeviceScan)
+//   k_emit          (Morton cell key, sphere index) pairs in sphere order
+//   radix sort      stable, 9 key bits -> cell-major, sphere-ascending              (cub::DeviceRadixSort)
+//   k_mark_entries  in-cell rank -> which entries the reference drops ("Leaf nodes full"), which spheres are stored
+//   k_number_nodes  one block: first-touch numbering of the nodes = the serial creation order
+//   k_grid_prep     big/small split, bounding box and count of the spheres that go into the grid
+//   (host)          grid resolution
+//   k_vox_pass x2 + scan + k_vox_finish   sphere-surface x voxel incidence lists, sorted, {start,count} per voxel
+//   (on export)     k_leaf_number, k_blob_nodes, k_blob_leaves -> reference `Octree` blob
 // CUB (shipped inside the CUDA toolkit, header-only) provides the device-wide scan and radix sort; everything
 // else is hand-written.
 #include <cub/cub.cuh>
 #include <cuda_runtime.h>
 #include <limits.h>
 #include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
 
 #include "rt_build.cuh"
 #include "rt_octree.h"
@@ -64,7 +68,7 @@ __global__ void k_classify(const float4 *__restrict__ geom, int n, BuildPlanes P
 }
 
 __global__ void k_emit(const uint32_t *__restrict__ ranges, const uint32_t *__restrict__ ent_off, int n,
-                       uint32_t *__restrict__ keys, uint32_t *__restrict__ vals) {
+                       uint32_t *__restrict__ keys, uint32_t *__restrict__ vals, uint16_t *__restrict__ ent_cell) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint32_t p = ranges[i];
@@ -74,8 +78,10 @@ __global__ void k_emit(const uint32_t *__restrict__ ranges, const uint32_t *__re
     for (int x = xl; x <= xh; x++)
         for (int y = yl; y <= yh; y++)
             for (int z = zl; z <= zh; z++) {
-                keys[o] = (uint32_t)morton_of(x, y, z);
+                const uint32_t m = (uint32_t)morton_of(x, y, z);
+                keys[o] = m;
                 vals[o] = (uint32_t)i;
+                ent_cell[o] = (uint16_t)m;      // sphere-major: the cells sphere i was inserted into (VisView)
                 o++;
             }
 }
@@ -96,109 +102,43 @@ __global__ void k_cell_scan(const uint32_t *__restrict__ cell_count, uint32_t *_
     if (t == 0) cell_start[0] = 0;
 }
 
-// One block per level-3 cell: split big/small, bound the stored list, choose the sub-grid.
-__global__ void k_cell_grid(const float4 *__restrict__ geom, const int *__restrict__ tag,
-                            const uint32_t *__restrict__ vals, const uint32_t *__restrict__ cell_start, int spl,
-                            BuildPlanes P, float density, uint8_t *__restrict__ entry_flag, CellGrid *__restrict__ raw,
-                            uint32_t *__restrict__ big_refs, uint32_t *__restrict__ nvox,
-                            unsigned long long *__restrict__ stats /* [0]=stored entries, [1]=dropped_full */) {
-    const int m = blockIdx.x;
-    const uint32_t b = cell_start[m], e = cell_start[m + 1];
-    const uint32_t count = e - b;
-    const uint32_t cap = 8u * (uint32_t)spl;                       // 8 buckets of SPHERES_PER_LEAF (:110-136)
-    const uint32_t stored = count < cap ? count : cap;
-    __shared__ uint32_t s_big_n, s_live;
-    __shared__ uint32_t s_big[kMaxBigPerCell];
-    __shared__ float s_lo[3][32], s_hi[3][32];
-    if (threadIdx.x == 0) { s_big_n = 0; s_live = 0; }
-    __syncthreads();
-    int ix, iy, iz;
-    morton_to_xyz(m, ix, iy, iz);
-    const float ex = P.p[0][ix + 1] - P.p[0][ix], ey = P.p[1][iy + 1] - P.p[1][iy], ez = P.p[2][iz + 1] - P.p[2][iz];
-    const float big_r = kBigRadiusFrac * fmaxf(ex, fmaxf(ey, ez));
-    // phase A: flags
-    for (uint32_t k = threadIdx.x; k < count; k += blockDim.x) {
-        uint8_t f = 2;                                              // dropped by the reference, or undefined slot
-        if (k < stored) {
-            const int idx = (int)vals[b + k];
-            if (tag[idx] >= 0) {
-                f = 0;
-                if (geom[idx].w > big_r) {
-                    const uint32_t slot = atomicAdd(&s_big_n, 1u);
-                    if (slot < (uint32_t)kMaxBigPerCell) { s_big[slot] = (uint32_t)idx; f = 1; }
-                }
-            }
+// Per sorted entry: the reference stores the first 8*SPL entries of a cell and drops the rest (:110-136).
+__global__ void k_mark_entries(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ vals,
+                               const uint32_t *__restrict__ cell_start, uint32_t E, int spl,
+                               const uint32_t *__restrict__ ranges, const uint32_t *__restrict__ ent_off,
+                               uint16_t *__restrict__ ent_cell, uint8_t *__restrict__ sph_flag,
+                               unsigned long long *__restrict__ stats /* [0] stored, [1] dropped_full */) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    bool stored = false, dropped = false;
+    if (p < E) {
+        const uint32_t m = keys[p], S = vals[p];
+        const uint32_t pos = p - cell_start[m];
+        dropped = pos >= 8u * (uint32_t)spl;
+        stored = !dropped;
+        if (dropped) {
+            // locate this entry in the sphere's own (x, y, z)-ordered list
+            const uint32_t r = ranges[S];
+            const int yl = (r >> 8) & 15, yh = (r >> 12) & 15, zl = (r >> 16) & 15, zh = (r >> 20) & 15, xl = r & 15;
+            int ix, iy, iz;
+            morton_to_xyz((int)m, ix, iy, iz);
+            const uint32_t local = (uint32_t)(((ix - xl) * (yh - yl + 1) + (iy - yl)) * (zh - zl + 1) + (iz - zl));
+            ent_cell[ent_off[S] + local] = (uint16_t)(m | kEntDropped);
+        } else {
+            sph_flag[S] = 1;          // stored in at least one cell (benign race: every writer writes 1)
         }
-        entry_flag[b + k] = f;
     }
-    __syncthreads();
-    // phase B: bounding box of the small stored spheres
-    float lo[3] = {3e38f, 3e38f, 3e38f}, hi[3] = {-3e38f, -3e38f, -3e38f};
-    uint32_t live = 0;
-    for (uint32_t k = threadIdx.x; k < stored; k += blockDim.x) {
-        if (entry_flag[b + k] != 0) continue;
-        const float4 s = geom[vals[b + k]];
-        const float r = s.w + sphere_pad(s.w);
-        lo[0] = fminf(lo[0], s.x - r); hi[0] = fmaxf(hi[0], s.x + r);
-        lo[1] = fminf(lo[1], s.y - r); hi[1] = fmaxf(hi[1], s.y + r);
-        lo[2] = fminf(lo[2], s.z - r); hi[2] = fmaxf(hi[2], s.z + r);
-        live++;
-    }
-    for (int o = 16; o > 0; o >>= 1) {
-        for (int k = 0; k < 3; k++) {
-            lo[k] = fminf(lo[k], __shfl_xor_sync(0xffffffffu, lo[k], o));
-            hi[k] = fmaxf(hi[k], __shfl_xor_sync(0xffffffffu, hi[k], o));
-        }
-        live += __shfl_xor_sync(0xffffffffu, live, o);
-    }
-    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-    if (l == 0) {
-        for (int k = 0; k < 3; k++) { s_lo[k][w] = lo[k]; s_hi[k][w] = hi[k]; }
-        atomicAdd(&s_live, live);
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const int nw = blockDim.x >> 5;
-        for (int k = 0; k < 3; k++)
-            for (int j = 1; j < nw; j++) { s_lo[k][0] = fminf(s_lo[k][0], s_lo[k][j]); s_hi[k][0] = fmaxf(s_hi[k][0], s_hi[k][j]); }
-        CellGrid g;
-        memset(&g, 0, sizeof g);
-        g.morton = (uint32_t)m;
-        uint32_t nb = s_big_n < (uint32_t)kMaxBigPerCell ? s_big_n : (uint32_t)kMaxBigPerCell;
-        // ascending order keeps the traversal deterministic
-        for (uint32_t a = 1; a < nb; a++) {
-            uint32_t v = s_big[a];
-            int j = (int)a - 1;
-            while (j >= 0 && s_big[j] > v) { s_big[j + 1] = s_big[j]; j--; }
-            s_big[j + 1] = v;
-        }
-        for (uint32_t a = 0; a < nb; a++) big_refs[m * kMaxBigPerCell + a] = s_big[a];
-        g.big = nb;   // begin is filled in by k_assemble (dense cell index)
-        float glo[3], ghi[3];
-        for (int k = 0; k < 3; k++) { glo[k] = s_lo[k][0]; ghi[k] = s_hi[k][0]; }
-        const uint32_t voxels = choose_grid(glo, ghi, s_live, density, g);
-        raw[m] = g;
-        nvox[m] = voxels;
-        atomicAdd(&stats[0], (unsigned long long)stored);
-        atomicAdd(&stats[1], (unsigned long long)(count - stored));
+    const unsigned ms = __ballot_sync(0xffffffffu, stored), md = __ballot_sync(0xffffffffu, dropped);
+    if ((threadIdx.x & 31) == 0) {
+        if (ms) atomicAdd(&stats[0], (unsigned long long)__popc(ms));
+        if (md) atomicAdd(&stats[1], (unsigned long long)__popc(md));
     }
 }
 
-// One block (1024 threads): number the nodes in the reference's creation order and emit the traversal arrays.
-__global__ void k_assemble(const uint32_t *__restrict__ vals, const uint32_t *__restrict__ cell_start,
-                           const float4 *__restrict__ geom, const CellGrid *__restrict__ raw,
-                           const uint32_t *__restrict__ nvox, const uint32_t *__restrict__ big_refs_in, BuildPlanes P,
-                           TreeNode *__restrict__ nodes, TreeExtent *__restrict__ node_ext, CellGrid *__restrict__ cells,
-                           TreeExtent *__restrict__ cell_ext, uint32_t *__restrict__ big_refs_out,
-                           int *__restrict__ node_of_potential, int *__restrict__ dense_of_morton,
-                           BuildCounts *__restrict__ out) {
+// One block (1024 threads): number the nodes in the reference's creation order.
+__global__ void k_number_nodes(const uint32_t *__restrict__ vals, const uint32_t *__restrict__ cell_start,
+                               int *__restrict__ node_of_potential, BuildCounts *__restrict__ out) {
     __shared__ int first[kNumberNodes];      // first sphere index touching the potential node
-    __shared__ int nidx[kNumberNodes];       // reference node index or -1
-    __shared__ int dense[kCells];
-    __shared__ uint32_t vbase[kCells];
-    __shared__ float elo[kNumberNodes][3], ehi[kNumberNodes][3];
     const int t = threadIdx.x;
-    // level 3
     if (t < kCells) {
         const uint32_t b = cell_start[t], e = cell_start[t + 1];
         first[level_base(3) + t] = e > b ? (int)vals[b] : INT_MAX;   // lists ascend, so the head is the first toucher
@@ -211,111 +151,71 @@ __global__ void k_assemble(const uint32_t *__restrict__ vals, const uint32_t *__
     if (t == 0) first[0] = -1;   // the root always exists and is created before any insertion (:200-206)
     __syncthreads();
     // creation order = sort by (first toucher, pre-order position); rank by counting (585^2 compares)
-    int my_level = 0, my_path = 0;
     if (t < kNumberNodes) {
-        my_level = t >= level_base(3) ? 3 : (t >= level_base(2) ? 2 : (t >= level_base(1) ? 1 : 0));
-        my_path = t - level_base(my_level);
+        const int my_level = t >= level_base(3) ? 3 : (t >= level_base(2) ? 2 : (t >= level_base(1) ? 1 : 0));
         int rank = -1;
         if (first[t] != INT_MAX) {
-            const long long mykey = ((long long)first[t] << 12) | preorder_key(my_level, my_path);
+            const long long mykey = (long long)first[t] * 4096 + preorder_key(my_level, t - level_base(my_level));
             rank = 0;
             for (int j = 0; j < kNumberNodes; j++) {
                 if (first[j] == INT_MAX) continue;
                 const int lv = j >= level_base(3) ? 3 : (j >= level_base(2) ? 2 : (j >= level_base(1) ? 1 : 0));
-                const long long key = ((long long)first[j] << 12) | preorder_key(lv, j - level_base(lv));
-                rank += key < mykey;
+                rank += ((long long)first[j] * 4096 + preorder_key(lv, j - level_base(lv))) < mykey;
             }
         }
-        nidx[t] = rank;
         node_of_potential[t] = rank;
     }
-    // dense cell numbering (Morton order) over cells that have anything to trace, and voxel bases
     if (t == 0) {
-        int c = 0;
-        uint32_t vb = 0;
-        for (int m = 0; m < kCells; m++) {
-            const bool live = nvox[m] > 0 || (raw[m].big & 0xff) > 0;
-            dense[m] = live ? c++ : -1;
-            vbase[m] = vb;
-            vb += nvox[m];
-        }
-        out->cell_count = c;
-        out->total_voxels = vb;
         int nc = 0;
         for (int j = 0; j < kNumberNodes; j++) nc += first[j] != INT_MAX;
         out->node_count = nc;
     }
-    __syncthreads();
-    // cells + their extents
-    if (t < kCells) {
-        dense_of_morton[t] = dense[t];
-        const int id = level_base(3) + t;
-        for (int k = 0; k < 3; k++) { elo[id][k] = 3e38f; ehi[id][k] = -3e38f; }
-        if (dense[t] >= 0) {
-            CellGrid g = raw[t];
-            g.vox_base = vbase[t];
-            const uint32_t nb = g.big & 0xff;
-            g.big = ((uint32_t)dense[t] * kMaxBigPerCell) << 8 | nb;
-            if (g.dims) for (int k = 0; k < 3; k++) { elo[id][k] = g.org[k]; ehi[id][k] = g.hi[k]; }
-            for (uint32_t a = 0; a < nb; a++) {
-                const uint32_t idx = big_refs_in[t * kMaxBigPerCell + a];
-                big_refs_out[dense[t] * kMaxBigPerCell + a] = idx;
-                const float4 s = geom[idx];
+}
+
+// order-preserving float <-> uint map, so that atomicMin/atomicMax on uints order floats
+__device__ __forceinline__ uint32_t f2ord(float f) { const uint32_t b = __float_as_uint(f); return b ^ ((b >> 31) ? 0xffffffffu : 0x80000000u); }
+inline float ord2f(uint32_t o) { const uint32_t b = o ^ ((o >> 31) ? 0x80000000u : 0xffffffffu); float f; memcpy(&f, &b, 4); return f; }
+
+// Which spheres go into the grid, which are "big", and the bounding box of the gridded ones.
+// sph_flag: 0 = not traceable (undefined slot, outside the root box, or every entry dropped), 1 = gridded, 2 = big.
+__global__ void k_grid_prep(const float4 *__restrict__ geom, const int *__restrict__ tag, int n, float big_r,
+                            uint8_t *__restrict__ sph_flag, GridPrep *__restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    float lo[3] = {3e38f, 3e38f, 3e38f}, hi[3] = {-3e38f, -3e38f, -3e38f};
+    uint32_t live = 0;
+    if (i < n) {
+        uint8_t f = sph_flag[i];
+        if (f && tag[i] < 0) f = 0;                       // undefined slots are never hit
+        if (f) {
+            const float4 s = geom[i];
+            if (s.w > big_r) {
+                const uint32_t slot = atomicAdd(&out->nbig, 1u);
+                if (slot < (uint32_t)kMaxBig) { out->big[slot] = (uint32_t)i; f = 2; }
+            }
+            if (f == 1) {
                 const float r = s.w + sphere_pad(s.w);
-                elo[id][0] = fminf(elo[id][0], s.x - r); ehi[id][0] = fmaxf(ehi[id][0], s.x + r);
-                elo[id][1] = fminf(elo[id][1], s.y - r); ehi[id][1] = fmaxf(ehi[id][1], s.y + r);
-                elo[id][2] = fminf(elo[id][2], s.z - r); ehi[id][2] = fmaxf(ehi[id][2], s.z + r);
+                lo[0] = s.x - r; hi[0] = s.x + r; lo[1] = s.y - r; hi[1] = s.y + r; lo[2] = s.z - r; hi[2] = s.z + r;
+                live = 1;
             }
-            cells[dense[t]] = g;
-            TreeExtent x;
-            for (int k = 0; k < 3; k++) { x.lo[k] = elo[id][k]; x.hi[k] = ehi[id][k]; }
-            x.pad[0] = x.pad[1] = 0.f;
-            cell_ext[dense[t]] = x;
         }
+        sph_flag[i] = f;
     }
-    __syncthreads();
-    for (int lv = 2; lv >= 0; lv--) {    // extents bottom-up
-        const int cnt = 1 << (3 * lv);
-        if (t < cnt) {
-            const int id = level_base(lv) + t;
-            for (int k = 0; k < 3; k++) { elo[id][k] = 3e38f; ehi[id][k] = -3e38f; }
-            for (int c = 0; c < 8; c++) {
-                const int ch = level_base(lv + 1) + t * 8 + c;
-                for (int k = 0; k < 3; k++) { elo[id][k] = fminf(elo[id][k], elo[ch][k]); ehi[id][k] = fmaxf(ehi[id][k], ehi[ch][k]); }
-            }
+    for (int o = 16; o > 0; o >>= 1) {
+        for (int k = 0; k < 3; k++) {
+            lo[k] = fminf(lo[k], __shfl_xor_sync(0xffffffffu, lo[k], o));
+            hi[k] = fmaxf(hi[k], __shfl_xor_sync(0xffffffffu, hi[k], o));
         }
-        __syncthreads();
+        live += __shfl_xor_sync(0xffffffffu, live, o);
     }
-    if (t < kNumberNodes && nidx[t] >= 0) {
-        TreeNode nd;
-        memset(&nd, 0, sizeof nd);
-        nd.level = (uint8_t)my_level;
-        int ix = 0, iy = 0, iz = 0;
-        for (int l = 0; l < my_level; l++) {
-            const int c = (my_path >> (3 * (my_level - 1 - l))) & 7;
-            ix = (ix << 1) | (c >> 2); iy = (iy << 1) | ((c >> 1) & 1); iz = (iz << 1) | (c & 1);
-        }
-        nd.ix = (uint8_t)ix; nd.iy = (uint8_t)iy; nd.iz = (uint8_t)iz;
-        if (my_level < 3) {
-            for (int c = 0; c < 8; c++) {
-                const int ch = nidx[level_base(my_level + 1) + my_path * 8 + c];
-                nd.child[c] = ch >= 0 ? (uint16_t)ch : (uint16_t)0;    // 0 = absent, as in the reference
-            }
-        } else {
-            nd.first_cell = dense[my_path] >= 0 ? (uint32_t)dense[my_path] : 0xffffffffu;
-        }
-        nodes[nidx[t]] = nd;
-        TreeExtent x;
-        for (int k = 0; k < 3; k++) { x.lo[k] = elo[t][k]; x.hi[k] = ehi[t][k]; }
-        x.pad[0] = x.pad[1] = 0.f;
-        node_ext[nidx[t]] = x;
+    if ((threadIdx.x & 31) == 0 && live) {
+        for (int k = 0; k < 3; k++) { atomicMin(&out->lo[k], f2ord(lo[k])); atomicMax(&out->hi[k], f2ord(hi[k])); }
+        atomicAdd(&out->live, live);
     }
 }
 
-// enumerate the voxels of `g` crossed by the (padded) surface of sphere s
+// enumerate the voxels crossed by the (padded) surface of sphere s
 template <typename F>
-__device__ __forceinline__ void for_each_voxel(const CellGrid &g, const float4 s, F f) {
-    const int nx = (int)(g.dims & 1023u), ny = (int)((g.dims >> 10) & 1023u);
+__device__ __forceinline__ void for_each_voxel(const GridView &g, const float4 s, F f) {
     const float pad = sphere_pad(s.w);
     int v0[3], v1[3];
     voxel_range(g, s, pad, v0, v1);
@@ -324,32 +224,26 @@ __device__ __forceinline__ void for_each_voxel(const CellGrid &g, const float4 s
             for (int x = v0[0]; x <= v1[0]; x++) {
                 float lo[3], hi[3];
                 voxel_box(g, x, y, z, lo, hi);
-                if (shell_hits_box(s, pad, lo, hi)) f(g.vox_base + (uint32_t)((z * ny + y) * nx + x));
+                if (shell_hits_box(s, pad, lo, hi)) f((uint32_t)(((size_t)z * g.ny + y) * g.nx + x));
             }
 }
 
 template <bool FILL>
-__global__ void k_vox_pass(const float4 *__restrict__ geom, const uint32_t *__restrict__ keys,
-                           const uint32_t *__restrict__ vals, const uint8_t *__restrict__ entry_flag, uint32_t E,
-                           const int *__restrict__ dense_of_morton, const CellGrid *__restrict__ cells,
-                           uint32_t *__restrict__ counter, const uint32_t *__restrict__ vox_start,
-                           uint32_t *__restrict__ refs) {
-    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= E) return;
-    if (entry_flag[p] != 0) return;
-    const int dc = dense_of_morton[keys[p]];
-    if (dc < 0) return;
-    const CellGrid g = cells[dc];
-    if (!g.dims) return;
-    const uint32_t idx = vals[p];
-    const float4 s = geom[idx];
+__global__ void k_vox_pass(const float4 *__restrict__ geom, const uint8_t *__restrict__ sph_flag, int n,
+                           const __grid_constant__ GridView g, uint32_t *__restrict__ counter,
+                           const uint32_t *__restrict__ vox_start, uint32_t *__restrict__ refs) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || sph_flag[i] != 1) return;
+    const float4 s = geom[i];
     for_each_voxel(g, s, [&](uint32_t v) {
         const uint32_t slot = atomicAdd(&counter[v], 1u);
-        if (FILL) refs[vox_start[v] + slot] = idx;
+        if (FILL) refs[vox_start[v] + slot] = (uint32_t)i;
     });
 }
 
-__global__ void k_vox_sort(const uint32_t *__restrict__ vox_start, uint32_t total_voxels, uint32_t *__restrict__ refs) {
+// per voxel: ascending order (deterministic traversal) and the {start, count} record the render kernel reads
+__global__ void k_vox_finish(const uint32_t *__restrict__ vox_start, uint32_t total_voxels, uint32_t *__restrict__ refs,
+                             uint2 *__restrict__ vox) {
     const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= total_voxels) return;
     const uint32_t b = vox_start[v], e = vox_start[v + 1];
@@ -359,6 +253,7 @@ __global__ void k_vox_sort(const uint32_t *__restrict__ vox_start, uint32_t tota
         while (j > b && refs[j - 1] > x) { refs[j] = refs[j - 1]; j--; }
         refs[j] = x;
     }
+    vox[v] = make_uint2(b, e - b);
 }
 
 // ---- reference-layout blob ------------------------------------------------------------------------------------
@@ -463,13 +358,12 @@ static cudaError_t ensure(T *&ptr, size_t &cap, size_t need) {
     return e;
 }
 
-OctreeBuilder::OctreeBuilder() { memset(&d, 0, sizeof d); memset(&cap, 0, sizeof cap); make_planes(planes); }
+OctreeBuilder::OctreeBuilder() { memset(&d, 0, sizeof d); memset(&cap, 0, sizeof cap); memset(&grid, 0, sizeof grid); make_planes(planes); }
 
 OctreeBuilder::~OctreeBuilder() {
     void *ptrs[] = {d.ranges, d.ent_count, d.ent_off, d.keys, d.vals, d.keys_sorted, d.vals_sorted, d.cell_count,
-                    d.cell_start, d.entry_flag, d.raw, d.big_raw, d.nvox, d.stats, d.nodes, d.node_ext, d.cells,
-                    d.cell_ext, d.big_refs, d.node_of_potential, d.dense_of_morton, d.counts, d.vox_count, d.vox_start,
-                    d.vox_refs, d.cub_tmp, d.leaf_index, d.blob};
+                    d.cell_start, d.ent_cell, d.sph_flag, d.stats, d.node_of_potential, d.counts, d.prep, d.big_refs,
+                    d.vox_count, d.vox_start, d.vox_refs, d.vox, d.cub_tmp, d.leaf_index, d.blob};
     for (void *p : ptrs) if (p) cudaFree(p);
 }
 
@@ -480,26 +374,21 @@ cudaError_t OctreeBuilder::build(cudaStream_t st, const float4 *geom, const int 
     RT_CUDA(ensure(d.ranges, cap.ranges, (size_t)n + 1));
     RT_CUDA(ensure(d.ent_count, cap.ent_count, (size_t)n + 1));
     RT_CUDA(ensure(d.ent_off, cap.ent_off, (size_t)n + 1));
+    RT_CUDA(ensure(d.sph_flag, cap.sph_flag, (size_t)n + 1));
     if (!d.cell_count) {
         RT_CUDA(cudaMalloc(&d.cell_count, kCells * 4));
         RT_CUDA(cudaMalloc(&d.cell_start, (kCells + 1) * 4));
-        RT_CUDA(cudaMalloc(&d.raw, kCells * sizeof(CellGrid)));
-        RT_CUDA(cudaMalloc(&d.big_raw, kCells * kMaxBigPerCell * 4));
-        RT_CUDA(cudaMalloc(&d.nvox, kCells * 4));
         RT_CUDA(cudaMalloc(&d.stats, 4 * 8));
-        RT_CUDA(cudaMalloc(&d.nodes, kNumberNodes * sizeof(TreeNode)));
-        RT_CUDA(cudaMalloc(&d.node_ext, kNumberNodes * sizeof(TreeExtent)));
-        RT_CUDA(cudaMalloc(&d.cells, kCells * sizeof(CellGrid)));
-        RT_CUDA(cudaMalloc(&d.cell_ext, kCells * sizeof(TreeExtent)));
-        RT_CUDA(cudaMalloc(&d.big_refs, kCells * kMaxBigPerCell * 4));
         RT_CUDA(cudaMalloc(&d.node_of_potential, kNumberNodes * 4));
-        RT_CUDA(cudaMalloc(&d.dense_of_morton, kCells * 4));
         RT_CUDA(cudaMalloc(&d.counts, sizeof(BuildCounts)));
+        RT_CUDA(cudaMalloc(&d.prep, sizeof(GridPrep)));
+        RT_CUDA(cudaMalloc(&d.big_refs, kMaxBig * 4));
         RT_CUDA(cudaMalloc(&d.leaf_index, kCells * 8 * 4 + 4));
     }
     RT_CUDA(cudaMemsetAsync(d.cell_count, 0, kCells * 4, st));
     RT_CUDA(cudaMemsetAsync(d.stats, 0, 4 * 8, st));
     RT_CUDA(cudaMemsetAsync(d.ent_count + n, 0, 4, st));
+    RT_CUDA(cudaMemsetAsync(d.sph_flag, 0, (size_t)n + 1, st));
     const int tb = 256;
     k_classify<<<(n + tb - 1) / tb, tb, 0, st>>>(geom, n, planes, d.ranges, d.ent_count, d.cell_count, d.stats + 2);
     size_t tmp = 0;
@@ -514,8 +403,8 @@ cudaError_t OctreeBuilder::build(cudaStream_t st, const float4 *geom, const int 
     RT_CUDA(ensure(d.vals, cap.vals, (size_t)E + 1));
     RT_CUDA(ensure(d.keys_sorted, cap.keys_sorted, (size_t)E + 1));
     RT_CUDA(ensure(d.vals_sorted, cap.vals_sorted, (size_t)E + 1));
-    RT_CUDA(ensure(d.entry_flag, cap.entry_flag, (size_t)E + 1));
-    k_emit<<<(n + tb - 1) / tb, tb, 0, st>>>(d.ranges, d.ent_off, n, d.keys, d.vals);
+    RT_CUDA(ensure(d.ent_cell, cap.ent_cell, (size_t)E + 2));
+    k_emit<<<(n + tb - 1) / tb, tb, 0, st>>>(d.ranges, d.ent_off, n, d.keys, d.vals, d.ent_cell);
     if (E > 0) {
         tmp = 0;
         cub::DeviceRadixSort::SortPairs(nullptr, tmp, d.keys, d.keys_sorted, d.vals, d.vals_sorted, (int)E, 0, 9, st);
@@ -523,36 +412,53 @@ cudaError_t OctreeBuilder::build(cudaStream_t st, const float4 *geom, const int 
         cub::DeviceRadixSort::SortPairs(d.cub_tmp, tmp, d.keys, d.keys_sorted, d.vals, d.vals_sorted, (int)E, 0, 9, st);
     }
     k_cell_scan<<<1, kCells, 0, st>>>(d.cell_count, d.cell_start);
-    k_cell_grid<<<kCells, 256, 0, st>>>(geom, tag, d.vals_sorted, d.cell_start, spl, planes, density, d.entry_flag, d.raw,
-                                       d.big_raw, d.nvox, d.stats);
-    k_assemble<<<1, 1024, 0, st>>>(d.vals_sorted, d.cell_start, geom, d.raw, d.nvox, d.big_raw, planes, d.nodes, d.node_ext,
-                                  d.cells, d.cell_ext, d.big_refs, d.node_of_potential, d.dense_of_morton, d.counts);
+    if (E > 0)
+        k_mark_entries<<<(E + tb - 1) / tb, tb, 0, st>>>(d.keys_sorted, d.vals_sorted, d.cell_start, E, spl, d.ranges, d.ent_off,
+                                                        d.ent_cell, d.sph_flag, d.stats);
+    k_number_nodes<<<1, 1024, 0, st>>>(d.vals_sorted, d.cell_start, d.node_of_potential, d.counts);
+    // grid over the small stored spheres
+    GridPrep init;
+    memset(&init, 0, sizeof init);
+    for (int k = 0; k < 3; k++) { init.lo[k] = 0xffffffffu; init.hi[k] = 0u; }
+    RT_CUDA(cudaMemcpyAsync(d.prep, &init, sizeof init, cudaMemcpyHostToDevice, st));
+    const float big_r = kBigRadiusFrac * fmaxf(planes.p[0][1] - planes.p[0][0], fmaxf(planes.p[1][1] - planes.p[1][0], planes.p[2][1] - planes.p[2][0]));
+    k_grid_prep<<<(n + tb - 1) / tb, tb, 0, st>>>(geom, tag, n, big_r, d.sph_flag, d.prep);
+    GridPrep prep;
+    RT_CUDA(cudaMemcpyAsync(&prep, d.prep, sizeof prep, cudaMemcpyDeviceToHost, st));
     RT_CUDA(cudaMemcpyAsync(&counts, d.counts, sizeof counts, cudaMemcpyDeviceToHost, st));
     RT_CUDA(cudaMemcpyAsync(stats_h, d.stats, 4 * 8, cudaMemcpyDeviceToHost, st));
     RT_CUDA(cudaStreamSynchronize(st));
-    const uint32_t V = counts.total_voxels;
+    nbig = (int)(prep.nbig < (uint32_t)kMaxBig ? prep.nbig : (uint32_t)kMaxBig);
+    std::sort(prep.big, prep.big + nbig);       // ascending: deterministic traversal order
+    RT_CUDA(cudaMemcpyAsync(d.big_refs, prep.big, kMaxBig * 4, cudaMemcpyHostToDevice, st));
+    float lo[3], hi[3];
+    for (int k = 0; k < 3; k++) { lo[k] = ord2f(prep.lo[k]); hi[k] = ord2f(prep.hi[k]); }
+    memset(&grid, 0, sizeof grid);
+    const uint32_t V = choose_grid(lo, hi, prep.live, density, grid);
+    total_voxels = V;
+    total_refs = 0;
     RT_CUDA(ensure(d.vox_count, cap.vox_count, (size_t)V + 2));
     RT_CUDA(ensure(d.vox_start, cap.vox_start, (size_t)V + 2));
-    RT_CUDA(cudaMemsetAsync(d.vox_count, 0, ((size_t)V + 2) * 4, st));
-    if (E > 0 && V > 0)
-        k_vox_pass<false><<<(E + tb - 1) / tb, tb, 0, st>>>(geom, d.keys_sorted, d.vals_sorted, d.entry_flag, E,
-                                                            d.dense_of_morton, d.cells, d.vox_count, nullptr, nullptr);
-    tmp = 0;
-    cub::DeviceScan::ExclusiveSum(nullptr, tmp, d.vox_count, d.vox_start, (int)V + 1, st);
-    RT_CUDA(ensure(d.cub_tmp, cap.cub, tmp));
-    cub::DeviceScan::ExclusiveSum(d.cub_tmp, tmp, d.vox_count, d.vox_start, (int)V + 1, st);
-    uint32_t R_h = 0;
-    RT_CUDA(cudaMemcpyAsync(&R_h, d.vox_start + V, 4, cudaMemcpyDeviceToHost, st));
-    RT_CUDA(cudaStreamSynchronize(st));
-    total_refs = R_h;
-    RT_CUDA(ensure(d.vox_refs, cap.vox_refs, (size_t)total_refs + 1));
-    RT_CUDA(cudaMemsetAsync(d.vox_count, 0, ((size_t)V + 2) * 4, st));
-    if (E > 0 && V > 0) {
-        k_vox_pass<true><<<(E + tb - 1) / tb, tb, 0, st>>>(geom, d.keys_sorted, d.vals_sorted, d.entry_flag, E,
-                                                           d.dense_of_morton, d.cells, d.vox_count, d.vox_start, d.vox_refs);
-        k_vox_sort<<<(V + tb - 1) / tb, tb, 0, st>>>(d.vox_start, V, d.vox_refs);
+    RT_CUDA(ensure(d.vox, cap.vox, (size_t)V + 1));
+    if (V > 0) {
+        RT_CUDA(cudaMemsetAsync(d.vox_count, 0, ((size_t)V + 2) * 4, st));
+        k_vox_pass<false><<<(n + tb - 1) / tb, tb, 0, st>>>(geom, d.sph_flag, n, grid, d.vox_count, nullptr, nullptr);
+        tmp = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, tmp, d.vox_count, d.vox_start, (int)V + 1, st);
+        RT_CUDA(ensure(d.cub_tmp, cap.cub, tmp));
+        cub::DeviceScan::ExclusiveSum(d.cub_tmp, tmp, d.vox_count, d.vox_start, (int)V + 1, st);
+        uint32_t R_h = 0;
+        RT_CUDA(cudaMemcpyAsync(&R_h, d.vox_start + V, 4, cudaMemcpyDeviceToHost, st));
+        RT_CUDA(cudaStreamSynchronize(st));
+        total_refs = R_h;
+        RT_CUDA(ensure(d.vox_refs, cap.vox_refs, (size_t)total_refs + 1));
+        RT_CUDA(cudaMemsetAsync(d.vox_count, 0, ((size_t)V + 2) * 4, st));
+        k_vox_pass<true><<<(n + tb - 1) / tb, tb, 0, st>>>(geom, d.sph_flag, n, grid, d.vox_count, d.vox_start, d.vox_refs);
+        k_vox_finish<<<(V + tb - 1) / tb, tb, 0, st>>>(d.vox_start, V, d.vox_refs, d.vox);
     }
     RT_CUDA(cudaGetLastError());
+    grid.vox = d.vox;
+    grid.refs = d.vox_refs;
     built = true;
     n_spheres = n;
     return cudaSuccess;
@@ -592,14 +498,19 @@ size_t OctreeBuilder::debug_read(cudaStream_t st, int which, void *host, size_t 
     if (!built) return 0;
     const void *src = nullptr;
     size_t bytes = 0;
+    float desc[15];
     switch (which) {
-        case 0: src = d.nodes; bytes = (size_t)counts.node_count * sizeof(TreeNode); break;
-        case 1: src = d.node_ext; bytes = (size_t)counts.node_count * sizeof(TreeExtent); break;
-        case 2: src = d.cells; bytes = (size_t)counts.cell_count * sizeof(CellGrid); break;
-        case 3: src = d.cell_ext; bytes = (size_t)counts.cell_count * sizeof(TreeExtent); break;
-        case 4: src = d.vox_start; bytes = ((size_t)counts.total_voxels + 1) * 4; break;
-        case 5: src = d.vox_refs; bytes = (size_t)total_refs * 4; break;
-        case 6: src = d.big_refs; bytes = (size_t)counts.cell_count * kMaxBigPerCell * 4; break;
+        case 0:   // grid descriptor: org, hi, vs, inv_vs (12 floats) + nx, ny, nz (3 ints)
+            for (int k = 0; k < 3; k++) { desc[k] = grid.org[k]; desc[3 + k] = grid.hi[k]; desc[6 + k] = grid.vs[k]; desc[9 + k] = grid.inv_vs[k]; }
+            memcpy(desc + 12, &grid.nx, 4); memcpy(desc + 13, &grid.ny, 4); memcpy(desc + 14, &grid.nz, 4);
+            if (host && cap_bytes >= sizeof desc) memcpy(host, desc, sizeof desc);
+            return sizeof desc;
+        case 1: src = d.vox; bytes = (size_t)total_voxels * sizeof(uint2); break;
+        case 2: src = d.vox_refs; bytes = (size_t)total_refs * 4; break;
+        case 3: src = d.ent_off; bytes = ((size_t)n_spheres + 1) * 4; break;
+        case 4: src = d.ent_cell; bytes = (size_t)E * 2; break;
+        case 5: src = d.big_refs; bytes = (size_t)nbig * 4; break;
+        case 6: src = d.sph_flag; bytes = (size_t)n_spheres; break;
         default: return 0;
     }
     if (!host) return bytes;
@@ -612,9 +523,11 @@ size_t OctreeBuilder::debug_read(cudaStream_t st, int which, void *host, size_t 
 TreeView OctreeBuilder::view() const {
     TreeView v;
     memset(&v, 0, sizeof v);
-    v.nodes = d.nodes; v.node_ext = d.node_ext; v.cells = d.cells; v.cell_ext = d.cell_ext;
-    v.vox_start = d.vox_start; v.vox_refs = d.vox_refs; v.big_refs = d.big_refs;
-    v.node_count = counts.node_count; v.cell_count = counts.cell_count;
+    v.grid = grid;
+    v.vis.ent_off = d.ent_off;
+    v.vis.ent_cell = d.ent_cell;
+    v.big_refs = d.big_refs;
+    v.nbig = nbig;
     for (int a = 0; a < 3; a++) for (int i = 0; i < kPlanes; i++) v.planes[a][i] = planes.p[a][i];
     return v;
 }

@@ -12,8 +12,12 @@ struct BuildPlanes {
     float p[3][kPlanes];
 };
 struct BuildCounts {
-    int node_count, cell_count;
-    uint32_t total_voxels;
+    int node_count;
+};
+struct GridPrep {                 // k_grid_prep output: bounding box (order-preserving uint encoding), counts, big list
+    uint32_t lo[3], hi[3];
+    uint32_t live, nbig;
+    uint32_t big[kMaxBig];
 };
 
 class OctreeBuilder {
@@ -29,13 +33,16 @@ public:
     // the tree in the reference's own layout (acceleration_structure.h:23-61), assembled on the GPU on demand
     cudaError_t export_reference(cudaStream_t st, void *host_blob, size_t bytes);
     TreeView view() const;
-    // test hook: copy one internal array to the host (0 nodes, 1 node_ext, 2 cells, 3 cell_ext, 4 vox_start,
-    // 5 vox_refs, 6 big_refs); returns the byte size when host == nullptr
+    // test hook: copy one internal array to the host (0 grid descriptor, 1 voxel records, 2 voxel references,
+    // 3 per-sphere entry offsets, 4 per-sphere cell lists, 5 big list, 6 sphere flags); returns the byte size when
+    // host == nullptr
     size_t debug_read(cudaStream_t st, int which, void *host, size_t cap) const;
 
     bool built = false, blob_valid = false;
     int spl = 0, n_spheres = 0, leaf_count_h = 0;
-    uint32_t E = 0, total_refs = 0;
+    int nbig = 0;
+    uint32_t E = 0, total_refs = 0, total_voxels = 0;
+    GridView grid;
     BuildCounts counts{};
     unsigned long long stats_h[4] = {0, 0, 0, 0};   // stored entries, dropped_full, dropped_outside, -
     BuildPlanes planes;
@@ -43,25 +50,22 @@ public:
 private:
     struct {
         uint32_t *ranges, *ent_count, *ent_off, *keys, *vals, *keys_sorted, *vals_sorted, *cell_count, *cell_start;
-        uint8_t *entry_flag;
-        CellGrid *raw;
-        uint32_t *big_raw, *nvox;
+        uint16_t *ent_cell;
+        uint8_t *sph_flag;
         unsigned long long *stats;
-        TreeNode *nodes;
-        TreeExtent *node_ext;
-        CellGrid *cells;
-        TreeExtent *cell_ext;
-        uint32_t *big_refs;
-        int *node_of_potential, *dense_of_morton;
+        int *node_of_potential;
         BuildCounts *counts;
+        GridPrep *prep;
+        uint32_t *big_refs;
         uint32_t *vox_count, *vox_start, *vox_refs;
+        uint2 *vox;
         uint8_t *cub_tmp;
         int *leaf_index;
         uint8_t *blob;
     } d;
     struct {
-        size_t ranges, ent_count, ent_off, keys, vals, keys_sorted, vals_sorted, entry_flag, vox_count, vox_start,
-            vox_refs, cub, blob;
+        size_t ranges, ent_count, ent_off, keys, vals, keys_sorted, vals_sorted, ent_cell, sph_flag, vox_count, vox_start,
+            vox_refs, vox, cub, blob;
     } cap;
 };
 

@@ -11,9 +11,9 @@
 //   * pixels are queued in 8x4 tiles so that the 32 lanes of a warp start on neighbouring pixels (coherent rays);
 //   * XORWOW state lives in registers and is seeded in place (render_init fused; no 48-byte state array);
 //   * spheres are SoA float4, materials are tag-dispatched (no device heap, no vtables);
-//   * the octree's packed nodes, content boxes and cell descriptors are staged once per block in shared memory
-//     with a TMA bulk copy (cp.async.bulk + mbarrier); in flat-list mode the whole float4 sphere array is staged
-//     the same way and swept with warp-uniform (broadcast) shared-memory reads.
+//   * octree mode never walks the tree: one uniform grid + the reference's cell-visibility rule (rt_trace.cuh);
+//   * flat-list mode stages the whole float4 sphere array once per block in shared memory with a TMA bulk copy
+//     (cp.async.bulk + mbarrier) and sweeps it with warp-uniform (broadcast) shared-memory reads.
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -85,43 +85,21 @@ __global__ void __launch_bounds__(kRenderThreads, 4) k_render(const __grid_const
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t bar;
 
-    // ---- stage the read-mostly structures in shared memory (TMA bulk copy) ----
-    SceneView sc = p.scene;
-    TreeView tv = p.tree;
+    // ---- flat-list mode: stage the whole float4 sphere array in shared memory with a TMA bulk copy ----
+    const SceneView sc = p.scene;
     const float4 *geom_s = nullptr;
-    {
-        unsigned char *cur = smem_raw;
-        uint32_t total = 0;
-        if (threadIdx.x == 0) mbar_init(&bar, 1);
-        __syncthreads();
-        if (OCTREE && p.stage_tree) {
-            const uint32_t nb = (uint32_t)tv.node_count * sizeof(TreeNode), eb = (uint32_t)tv.node_count * sizeof(TreeExtent);
-            const uint32_t cb = (uint32_t)tv.cell_count * sizeof(CellGrid), xb = (uint32_t)tv.cell_count * sizeof(TreeExtent);
-            unsigned char *s_nodes = cur; cur += nb;
-            unsigned char *s_next = cur; cur += eb;
-            unsigned char *s_cells = cur; cur += cb;
-            unsigned char *s_cext = cur; cur += xb;
-            total = nb + eb + cb + xb;
-            if (threadIdx.x == 0) {
-                mbar_expect_tx(&bar, total);
-                stage_bulk(s_nodes, p.tree.nodes, nb, &bar);
-                stage_bulk(s_next, p.tree.node_ext, eb, &bar);
-                if (cb) stage_bulk(s_cells, p.tree.cells, cb, &bar);
-                if (xb) stage_bulk(s_cext, p.tree.cell_ext, xb, &bar);
-            }
-            tv.nodes = reinterpret_cast<const TreeNode *>(s_nodes);
-            tv.node_ext = reinterpret_cast<const TreeExtent *>(s_next);
-            tv.cells = reinterpret_cast<const CellGrid *>(s_cells);
-            tv.cell_ext = reinterpret_cast<const TreeExtent *>(s_cext);
-        } else if (GEOM_SMEM) {
-            total = (uint32_t)sc.n * sizeof(float4);
-            if (threadIdx.x == 0) {
-                mbar_expect_tx(&bar, total);
-                stage_bulk(cur, p.scene.geom, total, &bar);
-            }
-            geom_s = reinterpret_cast<const float4 *>(cur);
+    if (!OCTREE && GEOM_SMEM) {
+        const uint32_t total = (uint32_t)sc.n * sizeof(float4);
+        if (threadIdx.x == 0) {
+            mbar_init(&bar, 1);
         }
-        if (total) mbar_wait(&bar, 0);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            mbar_expect_tx(&bar, total);
+            stage_bulk(smem_raw, p.scene.geom, total, &bar);
+        }
+        geom_s = reinterpret_cast<const float4 *>(smem_raw);
+        mbar_wait(&bar, 0);
     }
 
     const unsigned lane = threadIdx.x & 31u;
@@ -182,7 +160,7 @@ __global__ void __launch_bounds__(kRenderThreads, 4) k_render(const __grid_const
             // ---- one iteration of color()'s loop (main.cu:47-73) ----
             nrays++;
             Hit h;
-            if (OCTREE) h = trace_tree(sc, tv, &p.tree.planes[0][0], o, d, tc);
+            if (OCTREE) h = trace_tree(sc, p.tree, &p.tree.planes[0][0], o, d, tc);
             else if (GEOM_SMEM) h = trace_list(geom_s, sc.tag, sc.n, o, d, tc);
             else h = trace_list(sc.geom, sc.tag, sc.n, o, d, tc);
             bool sample_done = false;
@@ -302,11 +280,7 @@ static cudaError_t launch_variant(const RenderLaunch &p, size_t smem, int sm_cou
 
 cudaError_t launch_render(const RenderLaunch &p, bool octree, int sm_count, size_t smem_limit, cudaStream_t st,
                           int *blocks_out) {
-    if (octree) {
-        const size_t smem = (size_t)p.tree.node_count * (sizeof(TreeNode) + sizeof(TreeExtent)) +
-                            (size_t)p.tree.cell_count * (sizeof(CellGrid) + sizeof(TreeExtent));
-        return launch_variant<true, false>(p, p.stage_tree ? smem : 0, sm_count, st, blocks_out);
-    }
+    if (octree) return launch_variant<true, false>(p, 0, sm_count, st, blocks_out);
     const size_t geom_bytes = (size_t)p.scene.n * sizeof(float4);
     if (geom_bytes + 1024 <= smem_limit) return launch_variant<false, true>(p, geom_bytes, sm_count, st, blocks_out);
     return launch_variant<false, false>(p, 0, sm_count, st, blocks_out);

@@ -20,7 +20,6 @@ struct RenderLaunch {
     int tile_first, tile_stride;   // this shard owns tiles tile_first + k*tile_stride
     uint32_t total_items;    // owned tiles * 32
     unsigned long long seed_offset;   // added to the per-pixel seed 1984 + pixel_index (spp shards)
-    int stage_tree;          // 1: stage nodes/boxes/cells in shared memory (default); 0: read them through L1/L2
     int finalize;            // 1: write sqrt(sum/ns) (main.cu:111-115); 0: write the linear sum
     float *out;              // nx*ny*3 floats
     uint32_t *work_counter;  // queue head

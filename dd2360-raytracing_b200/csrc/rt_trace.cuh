@@ -7,9 +7,12 @@
 //               AABB passes the reference's infinite-LINE slab test (intersect_ray_aabb, :226-244, evaluated here
 //               with the same float operations).  A parent box contains its children and float subtraction and
 //               division are monotone, so a passing cell implies passing ancestors.
-// What this file is free to do, and does: visit cells front to back, skip cells and voxels the RAY cannot reach
-// before the current closest hit, and look only at the spheres whose surface crosses the voxels the ray walks
-// (a per-cell uniform sub-grid, 3D-DDA).  All pruning is conservative (margins below), so the minimum is unchanged.
+// The octree query never walks the tree.  Candidates come from one uniform grid over the small spheres, walked
+// with a 3D-DDA in a single flat loop (every lane of a warp executes the same advance / test body, which is what
+// keeps the warp converged), plus a short list of big spheres.  A candidate that would become the closest hit is
+// accepted only if one of the cells that store it passes the reference's line test (VisView) — that reproduces the
+// reference's quirks exactly: spheres dropped on bucket overflow, spheres outside the root box, hits the line test
+// never reaches.  All pruning is conservative (margins below), so the minimum is unchanged.
 #pragma once
 #include "rt_shade.cuh"
 
@@ -88,61 +91,48 @@ RT_HD bool ray_box(const RayPre &r, const float *lo, const float *hi, const floa
     const float tx0 = (lo[0] - r.o.x) * r.inv.x, tx1 = (hi[0] - r.o.x) * r.inv.x;
     const float ty0 = (lo[1] - r.o.y) * r.inv.y, ty1 = (hi[1] - r.o.y) * r.inv.y;
     const float tz0 = (lo[2] - r.o.z) * r.inv.z, tz1 = (hi[2] - r.o.z) * r.inv.z;
-    float t0 = fmaxf(fmaxf(fminf(tx0, tx1), fminf(ty0, ty1)), fmaxf(fminf(tz0, tz1), 0.0f));
-    float t1 = fminf(fminf(fmaxf(tx0, tx1), fmaxf(ty0, ty1)), fminf(fmaxf(tz0, tz1), t_far));
+    const float t0 = fmaxf(fmaxf(fminf(tx0, tx1), fminf(ty0, ty1)), fmaxf(fminf(tz0, tz1), 0.0f));
+    const float t1 = fminf(fminf(fmaxf(tx0, tx1), fmaxf(ty0, ty1)), fminf(fmaxf(tz0, tz1), t_far));
     t_enter = t0;
     t_exit = t1;
-    // slack: the boxes are padded at build time; this covers the rounding of the products above
+    // slack: the box is padded at build time; this covers the rounding of the products above
     return t0 <= t1 * (1.0f + 1e-5f) + 1e-6f;
 }
 
-// Walk one cell's sub-grid with a 3D-DDA and test the spheres registered in every voxel the ray crosses.
-RT_HD void trace_cell(const SceneView &sc, const TreeView &tv, const CellGrid &g, const RayPre &r, float t0, float t1,
-                      Hit &h, TraceCounters &tc) {
-    const int nx = (int)(g.dims & 1023u), ny = (int)((g.dims >> 10) & 1023u), nz = (int)(g.dims >> 20);
-    // entry point, nudged inside; clamp handles rounding at the faces
-    const float te = fmaxf(t0, 0.0f);
-    int ix = (int)floorf((r.o.x + r.d.x * te - g.org[0]) * g.inv_vs[0]);
-    int iy = (int)floorf((r.o.y + r.d.y * te - g.org[1]) * g.inv_vs[1]);
-    int iz = (int)floorf((r.o.z + r.d.z * te - g.org[2]) * g.inv_vs[2]);
-    ix = imin(imax(ix, 0), nx - 1);
-    iy = imin(imax(iy, 0), ny - 1);
-    iz = imin(imax(iz, 0), nz - 1);
-    const int sx = r.d.x >= 0.0f ? 1 : -1, sy = r.d.y >= 0.0f ? 1 : -1, sz = r.d.z >= 0.0f ? 1 : -1;
-    // parameter at which the ray leaves the current voxel along each axis
-    float tmx = (g.org[0] + (float)(ix + (sx > 0)) * g.vs[0] - r.o.x) * r.inv.x;
-    float tmy = (g.org[1] + (float)(iy + (sy > 0)) * g.vs[1] - r.o.y) * r.inv.y;
-    float tmz = (g.org[2] + (float)(iz + (sz > 0)) * g.vs[2] - r.o.z) * r.inv.z;
-    const float dtx = fabsf(g.vs[0] * r.inv.x), dty = fabsf(g.vs[1] * r.inv.y), dtz = fabsf(g.vs[2] * r.inv.z);
-    // a zero direction component never advances that axis
-    if (!(fabsf(r.d.x) > 0.0f)) tmx = kTMax;
-    if (!(fabsf(r.d.y) > 0.0f)) tmy = kTMax;
-    if (!(fabsf(r.d.z) > 0.0f)) tmz = kTMax;
-    float t_in = te;
-    const int max_steps = nx + ny + nz + 3;
-    for (int step = 0; step < max_steps; step++) {
-        // a later voxel can only hold hits at t >= t_in (minus the float slack)
-        if (t_in > h.t * (1.0f + kTSlackRel) + kTSlackAbs) break;
-        RT_COUNT(voxel_steps);
-        const uint32_t v = g.vox_base + (uint32_t)((iz * ny + iy) * nx + ix);
-        const uint32_t b = RT_LDG(tv.vox_start + v), e = RT_LDG(tv.vox_start + v + 1);
-        for (uint32_t k = b; k < e; k++) {
-            const int idx = (int)RT_LDG(tv.vox_refs + k);
-            const float4 s = RT_LDG(sc.geom + idx);
-            float t;
-            RT_COUNT(sphere_tests);
-            if (sphere_test(s, r.o, r.d, r.a, h.t, t)) { h.t = t; h.idx = idx; }
+// 9-bit Morton id (3 bits per level, x bit highest — the child index of acceleration_structure.h:150-165) -> cell coords
+RT_HD void cell_xyz(const int m, int &ix, int &iy, int &iz) {
+    ix = ((m >> 8) & 1) << 2 | ((m >> 5) & 1) << 1 | ((m >> 2) & 1);
+    iy = ((m >> 7) & 1) << 2 | ((m >> 4) & 1) << 1 | ((m >> 1) & 1);
+    iz = ((m >> 6) & 1) << 2 | ((m >> 3) & 1) << 1 | (m & 1);
+}
+
+// The reference's visibility rule for sphere `idx`: some level-3 cell that STORES it is crossed by the ray's line.
+// `last_ok` caches the last cell that passed for this ray (neighbouring candidates mostly share it).
+#if defined(__CUDA_ARCH__)
+__device__ __noinline__
+#else
+inline
+#endif
+bool sphere_visible(const VisView vis, const float *planes, const int idx, const vec3f o, const vec3f d, int &last_ok,
+                    TraceCounters &tc) {
+    const uint32_t b = RT_LDG(vis.ent_off + idx), e = RT_LDG(vis.ent_off + idx + 1);
+    for (uint32_t k = b; k < e; k++) {
+        const int c = (int)RT_LDG(vis.ent_cell + k);
+        if (c == last_ok) return true;
+        if (c & kEntDropped) continue;                       // the reference never stored it there (:135)
+        int ix, iy, iz;
+        cell_xyz(c, ix, iy, iz);
+        RT_COUNT(node_tests);
+        if (ref_line_test(o, d, planes[ix], planes[kPlanes + iy], planes[2 * kPlanes + iz], planes[ix + 1],
+                          planes[kPlanes + iy + 1], planes[2 * kPlanes + iz + 1])) {
+            last_ok = c;
+            return true;
         }
-        // step to the neighbour the ray enters next
-        if (tmx <= tmy && tmx <= tmz) { t_in = tmx; ix += sx; tmx += dtx; if ((unsigned)ix >= (unsigned)nx) break; }
-        else if (tmy <= tmz)          { t_in = tmy; iy += sy; tmy += dty; if ((unsigned)iy >= (unsigned)ny) break; }
-        else                          { t_in = tmz; iz += sz; tmz += dtz; if ((unsigned)iz >= (unsigned)nz) break; }
-        if (t_in > t1 * (1.0f + 1e-5f) + 1e-6f) break;
     }
+    return false;
 }
 
 // acceleration_structure.h:319-342 hitTree, re-organised (see the header comment)
-// `planes` = the 3 x 9 slab plane coordinates (kept in the kernel's constant parameter space)
 RT_HD Hit trace_tree(const SceneView &sc, const TreeView &tv, const float *planes, const vec3f o, const vec3f d,
                     TraceCounters &tc) {
     Hit h;
@@ -150,54 +140,72 @@ RT_HD Hit trace_tree(const SceneView &sc, const TreeView &tv, const float *plane
     RayPre r;
     r.o = o; r.d = d;
     r.a = dot3(d, d);
-    r.inv = mk(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
-    {   // ground sphere first (:322-332)
+    {   // ground sphere first, unconditionally (:322-332)
         float t;
         RT_COUNT(sphere_tests);
         if (sphere_test(RT_LDG(sc.geom), o, d, r.a, kTMax, t)) { h.t = t; h.idx = 0; }
     }
-    // front-to-back child order: flip the child bits along which the ray travels in the negative direction
-    const int flip = (d.x < 0.0f ? 4 : 0) | (d.y < 0.0f ? 2 : 0) | (d.z < 0.0f ? 1 : 0);
-    const TreeNode &root = tv.nodes[0];
-    for (int k1 = 0; k1 < 8; k1++) {
-        const int c1 = root.child[k1 ^ flip];
-        if (c1 == 0) continue;   // 0 = absent, as in the reference (the root is nobody's child)
-        float te, tx;
-        RT_COUNT(node_tests);
-        if (!ray_box(r, tv.node_ext[c1].lo, tv.node_ext[c1].hi, h.t * (1.0f + kTSlackRel) + kTSlackAbs, te, tx)) continue;
-        const TreeNode &n1 = tv.nodes[c1];
-        for (int k2 = 0; k2 < 8; k2++) {
-            const int c2 = n1.child[k2 ^ flip];
-            if (c2 == 0) continue;
-            RT_COUNT(node_tests);
-            if (!ray_box(r, tv.node_ext[c2].lo, tv.node_ext[c2].hi, h.t * (1.0f + kTSlackRel) + kTSlackAbs, te, tx)) continue;
-            const TreeNode &n2 = tv.nodes[c2];
-            for (int k3 = 0; k3 < 8; k3++) {
-                const int c3 = n2.child[k3 ^ flip];
-                if (c3 == 0) continue;
-                const TreeNode &n3 = tv.nodes[c3];
-                if (n3.first_cell == 0xffffffffu) continue;   // nothing traceable stored in this cell
-                const int cell = (int)n3.first_cell;
-                RT_COUNT(node_tests);
-                if (!ray_box(r, tv.cell_ext[cell].lo, tv.cell_ext[cell].hi, h.t * (1.0f + kTSlackRel) + kTSlackAbs, te, tx))
-                    continue;
-                // the reference only looks into this cell when the infinite line crosses its AABB
-                RT_COUNT(node_tests);
-                if (!ref_line_test(o, d, planes[n3.ix], planes[kPlanes + n3.iy], planes[2 * kPlanes + n3.iz],
-                                   planes[n3.ix + 1], planes[kPlanes + n3.iy + 1], planes[2 * kPlanes + n3.iz + 1]))
-                    continue;
-                const CellGrid &g = tv.cells[cell];
-                // big spheres of this cell: tested directly
-                const uint32_t nb = g.big & 0xffu, bb = g.big >> 8;
-                for (uint32_t k = 0; k < nb; k++) {
-                    const int idx = (int)RT_LDG(tv.big_refs + bb + k);
-                    float t;
-                    RT_COUNT(sphere_tests);
-                    if (sphere_test(RT_LDG(sc.geom + idx), o, d, r.a, h.t, t)) { h.t = t; h.idx = idx; }
-                }
-                // small spheres: walk the sub-grid where the ray overlaps it
-                if (g.dims && ray_box(r, g.org, g.hi, h.t * (1.0f + kTSlackRel) + kTSlackAbs, te, tx))
-                    trace_cell(sc, tv, g, r, te, tx, h, tc);
+    int last_ok = -1;
+    for (int k = 0; k < tv.nbig; k++) {   // big spheres: tested directly
+        const int idx = (int)RT_LDG(tv.big_refs + k);
+        float t;
+        RT_COUNT(sphere_tests);
+        if (sphere_test(RT_LDG(sc.geom + idx), o, d, r.a, h.t, t) && sphere_visible(tv.vis, planes, idx, o, d, last_ok, tc)) {
+            h.t = t; h.idx = idx;
+        }
+    }
+    const GridView &g = tv.grid;
+    if (g.nx == 0) return h;
+    r.inv = mk(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+    float te, tx;
+    if (!ray_box(r, g.org, g.hi, h.t * (1.0f + kTSlackRel) + kTSlackAbs, te, tx)) return h;
+
+    // ---- 3D-DDA over the grid, one flat loop: every iteration = (advance to the next voxel if the current list is
+    //      exhausted) + (one sphere test if the list is not empty) ----
+    int ix = (int)floorf((o.x + d.x * te - g.org[0]) * g.inv_vs[0]);
+    int iy = (int)floorf((o.y + d.y * te - g.org[1]) * g.inv_vs[1]);
+    int iz = (int)floorf((o.z + d.z * te - g.org[2]) * g.inv_vs[2]);
+    ix = imin(imax(ix, 0), g.nx - 1);
+    iy = imin(imax(iy, 0), g.ny - 1);
+    iz = imin(imax(iz, 0), g.nz - 1);
+    const int sx = d.x >= 0.0f ? 1 : -1, sy = d.y >= 0.0f ? 1 : -1, sz = d.z >= 0.0f ? 1 : -1;
+    // ray parameter at which the ray leaves the current voxel along each axis; an axis the ray does not move along
+    // never advances
+    float tmx = fabsf(d.x) > 0.0f ? (g.org[0] + (float)(ix + (sx > 0)) * g.vs[0] - o.x) * r.inv.x : kTMax;
+    float tmy = fabsf(d.y) > 0.0f ? (g.org[1] + (float)(iy + (sy > 0)) * g.vs[1] - o.y) * r.inv.y : kTMax;
+    float tmz = fabsf(d.z) > 0.0f ? (g.org[2] + (float)(iz + (sz > 0)) * g.vs[2] - o.z) * r.inv.z : kTMax;
+    const float dtx = fabsf(g.vs[0] * r.inv.x), dty = fabsf(g.vs[1] * r.inv.y), dtz = fabsf(g.vs[2] * r.inv.z);
+    uint32_t k, e;
+    {
+        RT_COUNT(voxel_steps);
+        const uint2 v = RT_LDG(g.vox + ((size_t)(iz * g.ny + iy) * g.nx + ix));
+        k = v.x; e = v.x + v.y;
+    }
+    int budget = g.nx + g.ny + g.nz + 4;       // hard bound on voxel steps: the loop always terminates
+    bool walking = true;
+    while (walking) {
+        if (k >= e) {
+            // step into the neighbour the ray enters next; t_in is where it enters
+            float t_in;
+            if (tmx <= tmy && tmx <= tmz) { t_in = tmx; ix += sx; tmx += dtx; walking = (unsigned)ix < (unsigned)g.nx; }
+            else if (tmy <= tmz)          { t_in = tmy; iy += sy; tmy += dty; walking = (unsigned)iy < (unsigned)g.ny; }
+            else                          { t_in = tmz; iz += sz; tmz += dtz; walking = (unsigned)iz < (unsigned)g.nz; }
+            // a later voxel can only hold hits at t >= t_in (minus the float slack); also stop at the grid exit
+            if (t_in > h.t * (1.0f + kTSlackRel) + kTSlackAbs || t_in > tx * (1.0f + 1e-5f) + 1e-6f || --budget < 0) walking = false;
+            if (walking) {
+                RT_COUNT(voxel_steps);
+                const uint2 v = RT_LDG(g.vox + ((size_t)(iz * g.ny + iy) * g.nx + ix));
+                k = v.x; e = v.x + v.y;
+            }
+        }
+        if (walking && k < e) {
+            const int idx = (int)RT_LDG(g.refs + k);
+            k++;
+            const float4 s = RT_LDG(sc.geom + idx);
+            float t;
+            RT_COUNT(sphere_tests);
+            if (sphere_test(s, o, d, r.a, h.t, t) && sphere_visible(tv.vis, planes, idx, o, d, last_ok, tc)) {
+                h.t = t; h.idx = idx;
             }
         }
     }

@@ -20,42 +20,29 @@ struct CameraData {
 };
 
 // ---- traversal structure (internal; NOT the reference layout) ------------------------------------------------
-// 32-byte packed octree node.  The reference AABB of a node is implied by (level, ix, iy, iz) on the fixed grid,
-// so the node only carries its children and the bounding box of what it actually contains.
-//   child[k]  : node index of child k (k = (x_high<<2)|(y_high<<1)|z_high, acceleration_structure.h:150-165);
-//               for a level-3 node: k = 0 holds the cell-descriptor index; 0xFFFF = absent
-//   ext_*     : AABB of the spheres stored below this node, half-precision-free: uint16 fixed point over the
-//               padded root box would lose exactness we do not need here, so they live in TreeExtent instead.
-struct alignas(32) TreeNode {
-    uint16_t child[8];      // 16 B
-    uint8_t level, ix, iy, iz;   // integer coordinates at this node's own level (0..(1<<level)-1)
-    uint32_t first_cell;    // level-3: index into cells[]; else unused
-    uint32_t pad[2];
-};
-static_assert(sizeof(TreeNode) == 32, "TreeNode must stay 32 bytes");
+// The reference's result is  argmin t  over  {ground} U { spheres stored in a level-3 cell whose AABB the ray's
+// infinite line crosses }  (acceleration_structure.h:226-342).  That is evaluated here as
+//   (1) find candidate spheres with ONE uniform grid over all "small" spheres (3D-DDA, surface x voxel lists) plus
+//       a short list of "big" spheres tested directly, and
+//   (2) for a candidate that would become the closest hit, check the reference's visibility rule: does any cell
+//       that STORES the sphere (i.e. was not dropped on bucket overflow) pass the line/AABB slab test?
+// so the octree is never walked: only its per-sphere cell lists (VisView) and its slab planes are needed.
+constexpr int kMaxBig = 64;                 // big spheres tested directly (beyond that they go into the grid)
+constexpr float kBigRadiusFrac = 0.25f;     // big: radius > this x longest level-3 cell edge
+constexpr uint16_t kEntDropped = 0x8000;    // VisView::ent_cell flag: entry dropped by the reference ("Leaf nodes full")
 
-// conservative AABB of the content of a node / cell (padded at build time); 24 bytes + pad = 32
-struct alignas(16) TreeExtent {
-    float lo[3], hi[3];
-    float pad[2];
+struct GridView {
+    float org[3], hi[3];        // grid box
+    float vs[3], inv_vs[3];     // voxel size and its reciprocal
+    int nx, ny, nz;             // 0 = no grid
+    const uint2 *vox;           // {first reference, reference count} per voxel
+    const uint32_t *refs;       // sphere indices, ascending inside a voxel
 };
 
-// Per level-3 cell: a uniform sub-grid over the bounding box of the cell's stored SMALL spheres, plus a short
-// list of BIG spheres (radius > kBigRadiusFrac * longest cell edge) that are tested directly when the cell is
-// visited, so that one huge sphere does not coarsen the grid of a thousand small ones.
-constexpr int kMaxBigPerCell = 16;
-constexpr float kBigRadiusFrac = 0.25f;
-struct alignas(16) CellGrid {
-    float org[3];           // grid origin (min corner)
-    uint32_t vox_base;      // first voxel of this grid in vox_start[]
-    float inv_vs[3];        // 1 / voxel size
-    uint32_t dims;          // nx | ny<<10 | nz<<20   (each <= 1023); 0 = no grid (big spheres only)
-    float vs[3];            // voxel size
-    uint32_t big;           // big_begin << 8 | big_count
-    float hi[3];            // grid max corner
-    uint32_t morton;        // which level-3 cell this is
+struct VisView {
+    const uint32_t *ent_off;    // n + 1 offsets: the cells sphere i was inserted into are ent_cell[ent_off[i] .. ent_off[i+1])
+    const uint16_t *ent_cell;   // Morton id of the level-3 cell | kEntDropped
 };
-static_assert(sizeof(CellGrid) == 64, "CellGrid is 64 bytes");
 
 struct SceneView {
     const float4 *geom;     // {cx, cy, cz, radius} per sphere
@@ -65,14 +52,10 @@ struct SceneView {
 };
 
 struct TreeView {
-    const TreeNode *nodes;      // node_count entries, node 0 = root
-    const TreeExtent *node_ext; // per node
-    const CellGrid *cells;      // per existing level-3 cell
-    const TreeExtent *cell_ext;
-    const uint32_t *vox_start;  // total_voxels + 1
-    const uint32_t *vox_refs;   // sphere indices
-    const uint32_t *big_refs;   // kMaxBigPerCell slots per cell
-    int node_count, cell_count;
+    GridView grid;
+    VisView vis;
+    const uint32_t *big_refs;   // nbig sphere indices, ascending
+    int nbig;
     float planes[3][kPlanes];   // slab plane coordinates per axis (exact floats of the reference subdivision)
 };
 

@@ -109,8 +109,9 @@ size_t rt_octree_reference_bytes(int spheres_per_leaf);      /* sizeof(Octree) f
 /* the tree in the reference's own memory layout (acceleration_structure.h:23-61), for the bit-exact check */
 int rt_octree_export_reference(rt_context *ctx, void *host_blob, size_t bytes);
 
-/* test hook: read one internal traversal array back (0 nodes, 1 node extents, 2 cells, 3 cell extents, 4 voxel
- * offsets, 5 voxel references, 6 big-sphere lists).  Returns the byte size (host == NULL) or bytes copied. */
+/* test hook: read one internal traversal array back (0 grid descriptor, 1 voxel records, 2 voxel references,
+ * 3 per-sphere entry offsets, 4 per-sphere cell lists, 5 big-sphere list, 6 sphere flags).  Returns the byte size
+ * (host == NULL) or bytes copied. */
 size_t rt_octree_debug_read(rt_context *ctx, int which, void *host, size_t cap);
 
 /* test hook: closest hit (sphere index or -1, and t) of n caller-supplied rays — hitTree / hitable_list::hit per ray */

@@ -63,9 +63,7 @@ def hostsim():
     if not os.path.exists(so) or any(os.path.getmtime(f) > os.path.getmtime(so) for f in [src] + hdrs):
         subprocess.run(["g++", "-O2", "-std=c++17", "-fopenmp", "-ffp-contract=off", "-fPIC", "-shared",
                         "-I/usr/local/cuda/include", src, "-o", so], check=True)
-    L = C.CDLL(so)
-    L.hs_tree_dump.restype = C.c_size_t
-    return L
+    return C.CDLL(so)
 
 
 @pytest.fixture(scope="session")

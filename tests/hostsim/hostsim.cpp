@@ -28,11 +28,10 @@ struct hs_params { int nx, ny, ns, use_octree, spl, arith, seed_mode, max_depth,
 struct hs_counters { uint64_t rays, sphere_tests, aabb_tests, paths; uint32_t max_depth; };
 
 struct HostTree {
-    std::vector<TreeNode> nodes;
-    std::vector<TreeExtent> node_ext;
-    std::vector<CellGrid> cells;
-    std::vector<TreeExtent> cell_ext;
-    std::vector<uint32_t> vox_start, vox_refs, big_refs;
+    std::vector<uint2> vox;
+    std::vector<uint32_t> refs, big_refs, ent_off;
+    std::vector<uint16_t> ent_cell;
+    GridView grid;
     float planes[3][kPlanes];
 };
 
@@ -45,120 +44,83 @@ static void make_planes(float P[3][kPlanes]) {
     }
 }
 
+// Rebuild the traversal structure on the host from a reference-layout Octree blob: the per-sphere lists of cells that
+// STORE the sphere come straight from the reference's leaf buckets.
 static void build_host_tree(const std::vector<float4> &geom, const std::vector<int> &tag, const int32_t *blob, int spl,
                             float density, HostTree &T) {
     make_planes(T.planes);
+    const int n = (int)geom.size();
     const int32_t *bn = blob;
     const int32_t *bl = blob + kNumberNodes * kNodeInts;
     const int32_t *cnt = bl + (size_t)(kNumberLeafs + 1) * (size_t)(spl + 1);
     const int node_count = cnt[0];
-    T.nodes.assign((size_t)node_count, TreeNode{});
-    T.node_ext.assign((size_t)node_count, TreeExtent{});
-    for (auto &x : T.node_ext) for (int k = 0; k < 3; k++) { x.lo[k] = 3e38f; x.hi[k] = -3e38f; }
-    T.vox_start.clear(); T.vox_start.push_back(0);
     auto plane_index = [&](int a, float v) { for (int i = 0; i < kPlanes; i++) if (T.planes[a][i] == v) return i; return -1; };
+    std::vector<std::vector<uint16_t>> cells_of((size_t)n);
     for (int ni = 0; ni < node_count; ni++) {
         const int32_t *nd = bn + ni * kNodeInts;
+        if (nd[0] != 3) continue;
         const float *bx = reinterpret_cast<const float *>(nd + 1);
-        TreeNode &tn = T.nodes[(size_t)ni];
-        memset(&tn, 0, sizeof tn);
-        tn.level = (uint8_t)nd[0];
-        const int sh = 3 - nd[0];
-        tn.ix = (uint8_t)(plane_index(0, bx[0]) >> sh);
-        tn.iy = (uint8_t)(plane_index(1, bx[1]) >> sh);
-        tn.iz = (uint8_t)(plane_index(2, bx[2]) >> sh);
-        tn.first_cell = 0xffffffffu;
-        if (nd[0] < 3) {
-            for (int c = 0; c < 8; c++) tn.child[c] = (uint16_t)nd[7 + c];
-            continue;
-        }
-        // level 3: gather the stored list from the leaf buckets
-        std::vector<uint32_t> small, big;
-        const float ex = T.planes[0][tn.ix + 1] - T.planes[0][tn.ix], ey = T.planes[1][tn.iy + 1] - T.planes[1][tn.iy],
-                    ez = T.planes[2][tn.iz + 1] - T.planes[2][tn.iz];
-        const float big_r = kBigRadiusFrac * fmaxf(ex, fmaxf(ey, ez));
+        const int m = morton_of(plane_index(0, bx[0]), plane_index(1, bx[1]), plane_index(2, bx[2]));
         for (int c = 0; c < 8; c++) {
             const int leaf = nd[7 + c];
             if (leaf == 0) break;
             const int32_t *lf = bl + (size_t)leaf * (size_t)(spl + 1);
-            for (int j = 0; j < lf[spl]; j++) {
-                const uint32_t idx = (uint32_t)lf[j];
-                if (tag[idx] < 0) continue;
-                if (geom[idx].w > big_r && (int)big.size() < kMaxBigPerCell) big.push_back(idx);
-                else small.push_back(idx);
-            }
+            for (int j = 0; j < lf[spl]; j++) cells_of[(size_t)lf[j]].push_back((uint16_t)m);
         }
-        if (small.empty() && big.empty()) continue;
-        CellGrid g;
-        memset(&g, 0, sizeof g);
-        g.morton = (uint32_t)morton_of(tn.ix, tn.iy, tn.iz);
-        float lo[3] = {3e38f, 3e38f, 3e38f}, hi[3] = {-3e38f, -3e38f, -3e38f};
+    }
+    T.ent_off.assign((size_t)n + 1, 0);
+    for (int i = 0; i < n; i++) {
+        T.ent_off[(size_t)i] = (uint32_t)T.ent_cell.size();
+        T.ent_cell.insert(T.ent_cell.end(), cells_of[(size_t)i].begin(), cells_of[(size_t)i].end());
+    }
+    T.ent_off[(size_t)n] = (uint32_t)T.ent_cell.size();
+    const float big_r = kBigRadiusFrac * 2.75f;
+    std::vector<uint32_t> small;
+    float lo[3] = {3e38f, 3e38f, 3e38f}, hi[3] = {-3e38f, -3e38f, -3e38f};
+    for (int i = 1; i < n; i++) {
+        if (tag[(size_t)i] < 0 || cells_of[(size_t)i].empty()) continue;
+        const float4 s = geom[(size_t)i];
+        if (s.w > big_r && (int)T.big_refs.size() < kMaxBig) { T.big_refs.push_back((uint32_t)i); continue; }
+        small.push_back((uint32_t)i);
+        const float r = s.w + sphere_pad(s.w);
+        lo[0] = fminf(lo[0], s.x - r); hi[0] = fmaxf(hi[0], s.x + r);
+        lo[1] = fminf(lo[1], s.y - r); hi[1] = fmaxf(hi[1], s.y + r);
+        lo[2] = fminf(lo[2], s.z - r); hi[2] = fmaxf(hi[2], s.z + r);
+    }
+    memset(&T.grid, 0, sizeof T.grid);
+    const uint32_t voxels = choose_grid(lo, hi, (uint32_t)small.size(), density, T.grid);
+    if (voxels) {
+        std::vector<std::vector<uint32_t>> lists(voxels);
         for (uint32_t idx : small) {
             const float4 s = geom[idx];
-            const float r = s.w + sphere_pad(s.w);
-            lo[0] = fminf(lo[0], s.x - r); hi[0] = fmaxf(hi[0], s.x + r);
-            lo[1] = fminf(lo[1], s.y - r); hi[1] = fmaxf(hi[1], s.y + r);
-            lo[2] = fminf(lo[2], s.z - r); hi[2] = fmaxf(hi[2], s.z + r);
+            const float pad = sphere_pad(s.w);
+            int v0[3], v1[3];
+            voxel_range(T.grid, s, pad, v0, v1);
+            for (int z = v0[2]; z <= v1[2]; z++)
+                for (int y = v0[1]; y <= v1[1]; y++)
+                    for (int x = v0[0]; x <= v1[0]; x++) {
+                        float blo[3], bhi[3];
+                        voxel_box(T.grid, x, y, z, blo, bhi);
+                        if (shell_hits_box(s, pad, blo, bhi)) lists[((size_t)z * T.grid.ny + y) * T.grid.nx + x].push_back(idx);
+                    }
         }
-        const uint32_t voxels = choose_grid(lo, hi, (uint32_t)small.size(), density, g);
-        g.vox_base = (uint32_t)T.vox_start.size() - 1;
-        const int dense = (int)T.cells.size();
-        g.big = ((uint32_t)dense * kMaxBigPerCell) << 8 | (uint32_t)big.size();
-        T.big_refs.resize((size_t)(dense + 1) * kMaxBigPerCell, 0);
-        std::sort(big.begin(), big.end());
-        for (size_t a = 0; a < big.size(); a++) T.big_refs[(size_t)dense * kMaxBigPerCell + a] = big[a];
-        if (voxels) {
-            std::vector<std::vector<uint32_t>> lists(voxels);
-            const int gx = (int)(g.dims & 1023u), gy = (int)((g.dims >> 10) & 1023u);
-            for (uint32_t idx : small) {
-                const float4 s = geom[idx];
-                const float pad = sphere_pad(s.w);
-                int v0[3], v1[3];
-                voxel_range(g, s, pad, v0, v1);
-                for (int z = v0[2]; z <= v1[2]; z++)
-                    for (int y = v0[1]; y <= v1[1]; y++)
-                        for (int x = v0[0]; x <= v1[0]; x++) {
-                            float blo[3], bhi[3];
-                            voxel_box(g, x, y, z, blo, bhi);
-                            if (shell_hits_box(s, pad, blo, bhi)) lists[(size_t)((z * gy + y) * gx + x)].push_back(idx);
-                        }
-            }
-            for (auto &l : lists) {
-                std::sort(l.begin(), l.end());
-                T.vox_refs.insert(T.vox_refs.end(), l.begin(), l.end());
-                T.vox_start.push_back((uint32_t)T.vox_refs.size());
-            }
+        T.vox.resize(voxels);
+        for (uint32_t v = 0; v < voxels; v++) {
+            std::sort(lists[v].begin(), lists[v].end());
+            T.vox[v].x = (uint32_t)T.refs.size();
+            T.vox[v].y = (uint32_t)lists[v].size();
+            T.refs.insert(T.refs.end(), lists[v].begin(), lists[v].end());
         }
-        TreeExtent xe;
-        for (int k = 0; k < 3; k++) { xe.lo[k] = voxels ? g.org[k] : 3e38f; xe.hi[k] = voxels ? g.hi[k] : -3e38f; }
-        for (uint32_t idx : big) {
-            const float4 s = geom[idx];
-            const float r = s.w + sphere_pad(s.w);
-            xe.lo[0] = fminf(xe.lo[0], s.x - r); xe.hi[0] = fmaxf(xe.hi[0], s.x + r);
-            xe.lo[1] = fminf(xe.lo[1], s.y - r); xe.hi[1] = fmaxf(xe.hi[1], s.y + r);
-            xe.lo[2] = fminf(xe.lo[2], s.z - r); xe.hi[2] = fmaxf(xe.hi[2], s.z + r);
-        }
-        xe.pad[0] = xe.pad[1] = 0;
-        tn.first_cell = (uint32_t)dense;
-        T.cells.push_back(g);
-        T.cell_ext.push_back(xe);
-        T.node_ext[(size_t)ni] = xe;
     }
-    // extents bottom-up (children always have larger indices than their parent in creation order? not
-    // guaranteed across subtrees, so iterate by level)
-    for (int lv = 2; lv >= 0; lv--)
-        for (int ni = 0; ni < node_count; ni++) {
-            if (T.nodes[(size_t)ni].level != lv) continue;
-            TreeExtent &x = T.node_ext[(size_t)ni];
-            for (int c = 0; c < 8; c++) {
-                const int ch = T.nodes[(size_t)ni].child[c];
-                if (!ch) continue;
-                for (int k = 0; k < 3; k++) {
-                    x.lo[k] = fminf(x.lo[k], T.node_ext[(size_t)ch].lo[k]);
-                    x.hi[k] = fmaxf(x.hi[k], T.node_ext[(size_t)ch].hi[k]);
-                }
-            }
-        }
+}
+
+static void view_of(const HostTree &T, TreeView &tv) {
+    memset(&tv, 0, sizeof tv);
+    tv.grid = T.grid;
+    tv.grid.vox = T.vox.data(); tv.grid.refs = T.refs.data();
+    tv.vis.ent_off = T.ent_off.data(); tv.vis.ent_cell = T.ent_cell.data();
+    tv.big_refs = T.big_refs.data(); tv.nbig = (int)T.big_refs.size();
+    memcpy(tv.planes, T.planes, sizeof tv.planes);
 }
 
 extern "C" {
@@ -183,13 +145,11 @@ static int render_core(const hs_sphere *sph, int n, const float *camera22, const
     if (p->use_octree && given) {
         tv = *given;
         make_planes(T.planes);
+        memcpy(tv.planes, T.planes, sizeof tv.planes);
     } else if (p->use_octree) {
         build_host_tree(geom, tag, static_cast<const int32_t *>(blob), p->spl, density, T);
-        tv.nodes = T.nodes.data(); tv.node_ext = T.node_ext.data(); tv.cells = T.cells.data();
-        tv.cell_ext = T.cell_ext.data(); tv.vox_start = T.vox_start.data(); tv.vox_refs = T.vox_refs.data();
-        tv.big_refs = T.big_refs.data();
-        tv.node_count = (int)T.nodes.size(); tv.cell_count = (int)T.cells.size();
-        if (build_stats) { build_stats[0] = T.vox_start.size() - 1; build_stats[1] = T.vox_refs.size(); }
+        view_of(T, tv);
+        if (build_stats) { build_stats[0] = T.vox.size(); build_stats[1] = T.refs.size(); }
     }
     CameraData cam;
     memcpy(&cam, camera22, sizeof cam);
@@ -217,7 +177,7 @@ static int render_core(const hs_sphere *sph, int n, const float *camera22, const
                     for (int depth = 0; depth < p->max_depth; depth++) {
                         c.rays++;
                         TraceCounters tcn{};
-                        Hit h = p->use_octree ? trace_tree(sc, tv, &T.planes[0][0], o, d, tcn)
+                        Hit h = p->use_octree ? trace_tree(sc, tv, &tv.planes[0][0], o, d, tcn)
                                               : trace_list(sc.geom, sc.tag, sc.n, o, d, tcn);
                         if (h.idx >= 0) {
                             vec3f hp, hn, a, dn;
@@ -255,41 +215,21 @@ int hs_render(const hs_sphere *sph, int n, const float *camera22, const void *bl
     return render_core(sph, n, camera22, blob, p, density, fb_gamma, fb_linear, ctr_out, build_stats, nullptr);
 }
 
-// Same renderer over traversal arrays produced elsewhere (the GPU build, read back with rt_octree_debug_read).
+// Same renderer over traversal arrays produced elsewhere (the GPU build, read back with rt_octree_debug_read):
+// grid_desc = 12 floats (org, hi, vs, inv_vs) + 3 ints (nx, ny, nz).
 int hs_render_with_tree(const hs_sphere *sph, int n, const float *camera22, const hs_params *p, float *fb_gamma,
-                        hs_counters *ctr_out, const void *nodes, int node_count, const void *node_ext, const void *cells,
-                        int cell_count, const void *cell_ext, const void *vox_start, const void *vox_refs, const void *big_refs) {
+                        hs_counters *ctr_out, const void *grid_desc, const void *vox, const void *refs,
+                        const void *ent_off, const void *ent_cell, const void *big_refs, int nbig) {
     TreeView tv;
     memset(&tv, 0, sizeof tv);
-    tv.nodes = static_cast<const TreeNode *>(nodes); tv.node_ext = static_cast<const TreeExtent *>(node_ext);
-    tv.cells = static_cast<const CellGrid *>(cells); tv.cell_ext = static_cast<const TreeExtent *>(cell_ext);
-    tv.vox_start = static_cast<const uint32_t *>(vox_start); tv.vox_refs = static_cast<const uint32_t *>(vox_refs);
-    tv.big_refs = static_cast<const uint32_t *>(big_refs);
-    tv.node_count = node_count; tv.cell_count = cell_count;
+    const float *gf = static_cast<const float *>(grid_desc);
+    const int *gi = reinterpret_cast<const int *>(gf + 12);
+    for (int k = 0; k < 3; k++) { tv.grid.org[k] = gf[k]; tv.grid.hi[k] = gf[3 + k]; tv.grid.vs[k] = gf[6 + k]; tv.grid.inv_vs[k] = gf[9 + k]; }
+    tv.grid.nx = gi[0]; tv.grid.ny = gi[1]; tv.grid.nz = gi[2];
+    tv.grid.vox = static_cast<const uint2 *>(vox); tv.grid.refs = static_cast<const uint32_t *>(refs);
+    tv.vis.ent_off = static_cast<const uint32_t *>(ent_off); tv.vis.ent_cell = static_cast<const uint16_t *>(ent_cell);
+    tv.big_refs = static_cast<const uint32_t *>(big_refs); tv.nbig = nbig;
     return render_core(sph, n, camera22, nullptr, p, 0.f, fb_gamma, nullptr, ctr_out, nullptr, &tv);
-}
-
-// Host-built traversal arrays, for comparison with the ones the GPU build produces (rt_octree_debug_read):
-// which = 0 nodes, 1 node_ext, 2 cells, 3 cell_ext, 4 vox_start, 5 vox_refs, 6 big_refs.  Returns bytes.
-size_t hs_tree_dump(const hs_sphere *sph, int n, const void *blob, int spl, float density, int which, void *out, size_t cap) {
-    std::vector<float4> geom((size_t)n);
-    std::vector<int> tag((size_t)n);
-    for (int i = 0; i < n; i++) { geom[(size_t)i] = make_float4(sph[i].cx, sph[i].cy, sph[i].cz, sph[i].radius); tag[(size_t)i] = sph[i].mat; }
-    HostTree T;
-    build_host_tree(geom, tag, static_cast<const int32_t *>(blob), spl, density, T);
-    const void *src = nullptr;
-    size_t bytes = 0;
-    switch (which) {
-        case 0: src = T.nodes.data(); bytes = T.nodes.size() * sizeof(TreeNode); break;
-        case 1: src = T.node_ext.data(); bytes = T.node_ext.size() * sizeof(TreeExtent); break;
-        case 2: src = T.cells.data(); bytes = T.cells.size() * sizeof(CellGrid); break;
-        case 3: src = T.cell_ext.data(); bytes = T.cell_ext.size() * sizeof(TreeExtent); break;
-        case 4: src = T.vox_start.data(); bytes = T.vox_start.size() * 4; break;
-        case 5: src = T.vox_refs.data(); bytes = T.vox_refs.size() * 4; break;
-        case 6: src = T.big_refs.data(); bytes = T.big_refs.size() * 4; break;
-    }
-    if (out && cap >= bytes && bytes) memcpy(out, src, bytes);
-    return bytes;
 }
 
 }  // extern "C"
