@@ -132,8 +132,10 @@ bool sphere_visible(const VisView vis, const float *planes, const int idx, const
     return false;
 }
 
-// acceleration_structure.h:319-342 hitTree, re-organised (see the header comment)
-RT_HD Hit trace_tree(const SceneView &sc, const TreeView &tv, const float *planes, const vec3f o, const vec3f d,
+// One pass over the candidates.  CHECKED = true applies the visibility rule to every candidate before it may become
+// the closest hit (always exact); CHECKED = false takes the plain minimum over all candidates.
+template <bool CHECKED>
+RT_HD Hit trace_walk(const SceneView &sc, const TreeView &tv, const float *planes, const vec3f o, const vec3f d,
                     TraceCounters &tc) {
     Hit h;
     h.t = kTMax; h.idx = -1;
@@ -150,7 +152,8 @@ RT_HD Hit trace_tree(const SceneView &sc, const TreeView &tv, const float *plane
         const int idx = (int)RT_LDG(tv.big_refs + k);
         float t;
         RT_COUNT(sphere_tests);
-        if (sphere_test(RT_LDG(sc.geom + idx), o, d, r.a, h.t, t) && sphere_visible(tv.vis, planes, idx, o, d, last_ok, tc)) {
+        if (sphere_test(RT_LDG(sc.geom + idx), o, d, r.a, h.t, t) &&
+            (!CHECKED || sphere_visible(tv.vis, planes, idx, o, d, last_ok, tc))) {
             h.t = t; h.idx = idx;
         }
     }
@@ -204,10 +207,25 @@ RT_HD Hit trace_tree(const SceneView &sc, const TreeView &tv, const float *plane
             const float4 s = RT_LDG(sc.geom + idx);
             float t;
             RT_COUNT(sphere_tests);
-            if (sphere_test(s, o, d, r.a, h.t, t) && sphere_visible(tv.vis, planes, idx, o, d, last_ok, tc)) {
+            if (sphere_test(s, o, d, r.a, h.t, t) && (!CHECKED || sphere_visible(tv.vis, planes, idx, o, d, last_ok, tc))) {
                 h.t = t; h.idx = idx;
             }
         }
+    }
+    return h;
+}
+
+// acceleration_structure.h:319-342 hitTree, re-organised (see the header comment).
+// Invisible candidates are rare (hits outside the root box, spheres dropped on bucket overflow), so: take the
+// minimum over ALL candidates first; if that sphere is visible it is also the minimum over the visible ones and
+// we are done — one visibility test per ray, made where the warp has reconverged.  Otherwise redo the walk with the
+// rule applied to every candidate.
+RT_HD Hit trace_tree(const SceneView &sc, const TreeView &tv, const float *planes, const vec3f o, const vec3f d,
+                    TraceCounters &tc) {
+    Hit h = trace_walk<false>(sc, tv, planes, o, d, tc);
+    if (h.idx > 0) {                        // the ground sphere (index 0) is tested unconditionally by the reference
+        int last_ok = -1;
+        if (!sphere_visible(tv.vis, planes, h.idx, o, d, last_ok, tc)) h = trace_walk<true>(sc, tv, planes, o, d, tc);
     }
     return h;
 }

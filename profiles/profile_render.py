@@ -23,3 +23,12 @@ for k in range(launches):
     st = rt.render_device(rt.args(nx, ny, ns, octree), fb.data_ptr())
     print(cfg, "spp", ns, "launch", k, "kernel_ms", round(st["kernel_ms"], 3), "Mrays/s", round(st["rays"] / st["kernel_ms"] / 1e3, 1))
 rt.close()
+if len(sys.argv) > 4 and sys.argv[4] == "counters":
+    rti = pkg.RayTracer(0, instrumented=True)
+    rti.create_world(n, 0.1)
+    if octree:
+        rti.build_octree(spl)
+    st = rti.render_device(rti.args(nx, ny, 1, octree), fb.data_ptr())
+    print("counters (1 spp): sphere_tests/ray", round(st["sphere_tests"] / st["rays"], 2), "visibility line tests/ray",
+          round(st["node_tests"] / st["rays"], 3), "rays/path", round(st["rays"] / st["paths"], 3))
+    rti.close()
