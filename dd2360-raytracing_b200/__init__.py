@@ -37,7 +37,7 @@ SPHERE_DTYPE = np.dtype(
 ABI_SYMBOLS = [
     "rt_abi_version", "rt_create", "rt_destroy", "rt_last_error", "rt_set_stream", "rt_device_info",
     "rt_scene_generate", "rt_scene_upload", "rt_scene_download", "rt_scene_size", "rt_camera_set", "rt_camera_get",
-    "rt_octree_build", "rt_octree_reference_bytes", "rt_octree_export_reference", "rt_octree_debug_read", "rt_trace_rays",
+    "rt_octree_build", "rt_octree_reference_bytes", "rt_octree_export_reference", "rt_octree_debug_read", "rt_debug_counters", "rt_trace_rays",
     "rt_render_accumulate", "rt_finalize", "rt_render", "rt_render_to_host", "rt_format_ppm",
     "rt_ffma_peak", "rt_malloc", "rt_free", "rt_memcpy_to_host", "rt_synchronize",
 ]
@@ -106,6 +106,7 @@ def load_library(path: str | None = None) -> C.CDLL:
         "rt_octree_reference_bytes": (sz, [i32]),
         "rt_octree_export_reference": (i32, [vp, vp, sz]),
         "rt_octree_debug_read": (sz, [vp, i32, vp, sz]),
+        "rt_debug_counters": (i32, [vp, vp]),
         "rt_trace_rays": (i32, [vp, i32, i32, vp, vp, vp, vp]),
         "rt_render_accumulate": (i32, [vp, C.POINTER(RenderArgs), vp, C.POINTER(RenderStats)]),
         "rt_finalize": (i32, [vp, vp, vp, i32, i32, i32]),
@@ -234,6 +235,12 @@ class RayTracer:
             out[name] = buf[:n]
         return out
 
+    def debug_counters(self) -> np.ndarray:
+        """Test hook: raw device counters of the last render (see rt_abi.h)."""
+        out = np.zeros(32, dtype=np.uint64)
+        self._ck(self.L.rt_debug_counters(self._ctx, out.ctypes.data), "rt_debug_counters")
+        return out
+
     def trace_rays(self, origins: np.ndarray, dirs: np.ndarray, use_octree: bool):
         """Test hook: closest hit per ray -> (idx[n] int32, t[n] float32)."""
         o = np.ascontiguousarray(origins, dtype=np.float32)
@@ -248,8 +255,12 @@ class RayTracer:
     # -- render (main.cu:424-429) --
     @staticmethod
     def args(nx, ny, ns, use_octree, max_depth=50, shard_mode=SHARD_NONE, shard_rank=0, shard_count=1,
-             seed_mode=SEED_HEAD) -> RenderArgs:
-        return RenderArgs(nx, ny, ns, max_depth, int(bool(use_octree)), seed_mode, shard_mode, shard_rank, shard_count)
+             seed_mode=SEED_HEAD, variant=0, max_rounds=0, tune=(0, 0)) -> RenderArgs:
+        a = RenderArgs(nx, ny, ns, max_depth, int(bool(use_octree)), seed_mode, shard_mode, shard_rank, shard_count)
+        a.reserved[3], a.reserved[4] = tune  # pool-kernel tuning knobs (0 = default)
+        a.reserved[2] = max_rounds           # pool-kernel watchdog (scheduling rounds per warp; 0 = off)
+        a.reserved[1] = variant              # kernel A/B knob (0 = default); every variant renders the same image
+        return a
 
     def render(self, nx, ny, ns, use_octree=True, **kw):
         """Whole frame with a HOST destination (render + device->host copy).  Returns (fb[ny,nx,3], stats)."""

@@ -36,6 +36,7 @@ struct rt_context {
     // octree
     OctreeBuilder *octree = nullptr;
     float grid_density = 4.0f;
+    int default_variant = 0;       // RT_RENDER_VARIANT: kernel A/B override for whole test runs (0 = automatic)
     // render scratch
     uint32_t *work_counter = nullptr;
     unsigned long long *counters = nullptr;
@@ -78,7 +79,7 @@ extern "C" int rt_create(int device, rt_context **out) {
     if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaGetDeviceProperties(&ctx->prop, device)) != cudaSuccess ||
         (e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = cudaEventCreate(&ctx->ev0)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev1)) != cudaSuccess ||
-        (e = cudaMalloc(&ctx->work_counter, 4)) != cudaSuccess || (e = cudaMalloc(&ctx->counters, 8 * 8)) != cudaSuccess ||
+        (e = cudaMalloc(&ctx->work_counter, 4)) != cudaSuccess || (e = cudaMalloc(&ctx->counters, 32 * 8)) != cudaSuccess ||
         (e = cudaMalloc(&ctx->cam_dev, sizeof(CameraData))) != cudaSuccess) {
         delete ctx;
         return (int)e;
@@ -87,6 +88,8 @@ extern "C" int rt_create(int device, rt_context **out) {
     ctx->octree = new OctreeBuilder();
     const char *dens = getenv("RT_GRID_DENSITY");
     if (dens && atof(dens) > 0) ctx->grid_density = (float)atof(dens);
+    const char *var = getenv("RT_RENDER_VARIANT");
+    if (var) ctx->default_variant = atoi(var);
     *out = ctx;
     return RT_OK;
 }
@@ -379,27 +382,44 @@ static int do_render(rt_context *ctx, const rt_render_args *a, float *out_dev, b
     if (owned * 32 > 0xfffffff0ll) return fail(ctx, RT_ERR_INVALID, "render: image too large for the 32-bit work queue");
     p.total_items = (uint32_t)(owned * 32);
     p.finalize = finalize ? 1 : 0;
+    p.variant = a->reserved[1] ? a->reserved[1] : ctx->default_variant;
+    p.tune_sticky = a->reserved[3] > 0 ? a->reserved[3] : 4;
+    p.tune_sticky_min = a->reserved[4] > 0 ? a->reserved[4] : 8;
+    p.max_rounds = a->reserved[2] > 0 ? (uint32_t)a->reserved[2] : 0x7fffffffu;            // A/B measurement knob; every variant renders the same image
     p.out = out_dev;
     p.work_counter = ctx->work_counter;
     p.counters = ctx->counters;
-    CK(cudaMemsetAsync(ctx->counters, 0, 8 * 8, ctx->stream));
+    CK(cudaMemsetAsync(ctx->counters, 0, 32 * 8, ctx->stream));
     int blocks = 0;
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
     CK(launch_render(p, a->use_octree != 0, ctx->prop.multiProcessorCount, ctx->prop.sharedMemPerBlockOptin, ctx->stream, &blocks));
     CK(cudaEventRecord(ctx->ev1, ctx->stream));
     if (stats) {
-        unsigned long long c[5] = {0, 0, 0, 0, 0};
+        unsigned long long c[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         CK(cudaMemcpyAsync(c, ctx->counters, sizeof c, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaEventSynchronize(ctx->ev1));
         CK(cudaStreamSynchronize(ctx->stream));
         memset(stats, 0, sizeof *stats);
         stats->rays = c[0]; stats->paths = c[1];
         stats->sphere_tests = c[2]; stats->node_tests = c[3];   // zero unless built with -DRT_COUNTERS
+        if (c[7]) {
+            return fail(ctx, RT_ERR_STATE, "render: scheduler watchdog tripped in %llu warps (w0|w1 %016llx, w2|rounds %016llx)",
+                        c[7], c[5], c[6]);
+        }
         float ms = 0;
         cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
         stats->kernel_ms = ms;
         stats->launches = 1;
     }
+    return RT_OK;
+}
+
+// test hook: the raw device counters of the last render (instrumented builds fill [8..27] with per-state scheduling data)
+extern "C" int rt_debug_counters(rt_context *ctx, uint64_t out[32]) {
+    if (!ctx || !out) return fail(ctx, RT_ERR_INVALID, "rt_debug_counters: null argument");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpyAsync(out, ctx->counters, 32 * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
     return RT_OK;
 }
 

@@ -382,7 +382,7 @@ cudaError_t OctreeBuilder::build(cudaStream_t st, const float4 *geom, const int 
         RT_CUDA(cudaMalloc(&d.node_of_potential, kNumberNodes * 4));
         RT_CUDA(cudaMalloc(&d.counts, sizeof(BuildCounts)));
         RT_CUDA(cudaMalloc(&d.prep, sizeof(GridPrep)));
-        RT_CUDA(cudaMalloc(&d.big_refs, kMaxBig * 4));
+        RT_CUDA(cudaMalloc(&d.big_refs, (kMaxBig + 1) * 4));   // [0] = ground sphere, then the big spheres
         RT_CUDA(cudaMalloc(&d.leaf_index, kCells * 8 * 4 + 4));
     }
     RT_CUDA(cudaMemsetAsync(d.cell_count, 0, kCells * 4, st));
@@ -430,7 +430,9 @@ cudaError_t OctreeBuilder::build(cudaStream_t st, const float4 *geom, const int 
     RT_CUDA(cudaStreamSynchronize(st));
     nbig = (int)(prep.nbig < (uint32_t)kMaxBig ? prep.nbig : (uint32_t)kMaxBig);
     std::sort(prep.big, prep.big + nbig);       // ascending: deterministic traversal order
-    RT_CUDA(cudaMemcpyAsync(d.big_refs, prep.big, kMaxBig * 4, cudaMemcpyHostToDevice, st));
+    prolog_h[0] = 0;
+    memcpy(prolog_h + 1, prep.big, kMaxBig * 4);
+    RT_CUDA(cudaMemcpyAsync(d.big_refs, prolog_h, (kMaxBig + 1) * 4, cudaMemcpyHostToDevice, st));
     float lo[3], hi[3];
     for (int k = 0; k < 3; k++) { lo[k] = ord2f(prep.lo[k]); hi[k] = ord2f(prep.hi[k]); }
     memset(&grid, 0, sizeof grid);
@@ -509,7 +511,7 @@ size_t OctreeBuilder::debug_read(cudaStream_t st, int which, void *host, size_t 
         case 2: src = d.vox_refs; bytes = (size_t)total_refs * 4; break;
         case 3: src = d.ent_off; bytes = ((size_t)n_spheres + 1) * 4; break;
         case 4: src = d.ent_cell; bytes = (size_t)E * 2; break;
-        case 5: src = d.big_refs; bytes = (size_t)nbig * 4; break;
+        case 5: src = d.big_refs + 1; bytes = (size_t)nbig * 4; break;
         case 6: src = d.sph_flag; bytes = (size_t)n_spheres; break;
         default: return 0;
     }
@@ -526,8 +528,8 @@ TreeView OctreeBuilder::view() const {
     v.grid = grid;
     v.vis.ent_off = d.ent_off;
     v.vis.ent_cell = d.ent_cell;
-    v.big_refs = d.big_refs;
-    v.nbig = nbig;
+    v.prolog = d.big_refs;
+    v.nprolog = 1 + nbig;
     for (int a = 0; a < 3; a++) for (int i = 0; i < kPlanes; i++) v.planes[a][i] = planes.p[a][i];
     return v;
 }

@@ -41,6 +41,7 @@ public:
     bool built = false, blob_valid = false;
     int spl = 0, n_spheres = 0, leaf_count_h = 0;
     int nbig = 0;
+    uint32_t prolog_h[kMaxBig + 1];   // staging for the async upload (must outlive build())
     uint32_t E = 0, total_refs = 0, total_voxels = 0;
     GridView grid;
     BuildCounts counts{};

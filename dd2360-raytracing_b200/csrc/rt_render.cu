@@ -223,6 +223,12 @@ __global__ void __launch_bounds__(kRenderThreads, 4) k_render(const __grid_const
 #endif
 }
 
+}  // namespace rt
+namespace rt {
+#include "rt_pool.cuh"
+}  // namespace rt
+namespace rt {
+
 // Closest hit for caller-supplied rays (test hook: per-ray parity against the oracle's hitTree / hitable_list::hit)
 __global__ void k_trace_rays(const __grid_constant__ RenderLaunch p, int octree, const float *__restrict__ org,
                              const float *__restrict__ dir, int n, int *__restrict__ out_idx, float *__restrict__ out_t) {
@@ -280,7 +286,16 @@ static cudaError_t launch_variant(const RenderLaunch &p, size_t smem, int sm_cou
 
 cudaError_t launch_render(const RenderLaunch &p, bool octree, int sm_count, size_t smem_limit, cudaStream_t st,
                           int *blocks_out) {
-    if (octree) return launch_variant<true, false>(p, 0, sm_count, st, blocks_out);
+    if (octree) {
+        switch (p.variant) {          // A/B measurement variants; all produce the same image
+            case 10: return pool::launch_pool<96, 4>(p, sm_count, st, blocks_out);
+            case 11: return pool::launch_pool<64, 6>(p, sm_count, st, blocks_out);
+            case 12: return pool::launch_pool<128, 3>(p, sm_count, st, blocks_out);
+            case 13: return pool::launch_pool<32, 8>(p, sm_count, st, blocks_out);
+            case 14: return pool::launch_pool<64, 4>(p, sm_count, st, blocks_out);
+            default: return launch_variant<true, false>(p, 0, sm_count, st, blocks_out);
+        }
+    }
     const size_t geom_bytes = (size_t)p.scene.n * sizeof(float4);
     if (geom_bytes + 1024 <= smem_limit) return launch_variant<false, true>(p, geom_bytes, sm_count, st, blocks_out);
     return launch_variant<false, false>(p, 0, sm_count, st, blocks_out);

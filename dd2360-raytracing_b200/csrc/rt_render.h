@@ -20,6 +20,9 @@ struct RenderLaunch {
     int tile_first, tile_stride;   // this shard owns tiles tile_first + k*tile_stride
     uint32_t total_items;    // owned tiles * 32
     unsigned long long seed_offset;   // added to the per-pixel seed 1984 + pixel_index (spp shards)
+    uint32_t max_rounds;     // pool kernel watchdog: scheduling rounds per warp before it gives up (host reports an error)
+    int tune_sticky, tune_sticky_min;   // pool kernel: TEST chunks per scheduling round, and the lane count that keeps it going
+    int variant;             // kernel variant for A/B measurements (rt_render_args.reserved[1]); 0 = default
     int finalize;            // 1: write sqrt(sum/ns) (main.cu:111-115); 0: write the linear sum
     float *out;              // nx*ny*3 floats
     uint32_t *work_counter;  // queue head

@@ -148,8 +148,8 @@ RT_HD Hit trace_walk(const SceneView &sc, const TreeView &tv, const float *plane
         if (sphere_test(RT_LDG(sc.geom), o, d, r.a, kTMax, t)) { h.t = t; h.idx = 0; }
     }
     int last_ok = -1;
-    for (int k = 0; k < tv.nbig; k++) {   // big spheres: tested directly
-        const int idx = (int)RT_LDG(tv.big_refs + k);
+    for (int k = 1; k < tv.nprolog; k++) {   // big spheres: tested directly (prolog[0] is the ground sphere)
+        const int idx = (int)RT_LDG(tv.prolog + k);
         float t;
         RT_COUNT(sphere_tests);
         if (sphere_test(RT_LDG(sc.geom + idx), o, d, r.a, h.t, t) &&

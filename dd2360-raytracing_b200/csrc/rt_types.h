@@ -54,8 +54,8 @@ struct SceneView {
 struct TreeView {
     GridView grid;
     VisView vis;
-    const uint32_t *big_refs;   // nbig sphere indices, ascending
-    int nbig;
+    const uint32_t *prolog;     // first candidate list of every ray: the ground sphere (index 0, tested unconditionally by
+    int nprolog;                // hitTree :322-332), then the big spheres in ascending order; nprolog = 1 + nbig
     float planes[3][kPlanes];   // slab plane coordinates per axis (exact floats of the reference subdivision)
 };
 

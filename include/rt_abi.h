@@ -114,6 +114,11 @@ int rt_octree_export_reference(rt_context *ctx, void *host_blob, size_t bytes);
  * (host == NULL) or bytes copied. */
 size_t rt_octree_debug_read(rt_context *ctx, int which, void *host, size_t cap);
 
+/* test hook: raw device counters of the last render call.  [0] rays, [1] paths; RT_COUNTERS builds add [2] sphere tests,
+ * [3] visibility line tests, [4] voxel steps and, for the pooled kernel, [8+s] scheduling rounds and [18+s] contexts
+ * processed per state s. */
+int rt_debug_counters(rt_context *ctx, uint64_t out[32]);
+
 /* test hook: closest hit (sphere index or -1, and t) of n caller-supplied rays — hitTree / hitable_list::hit per ray */
 int rt_trace_rays(rt_context *ctx, int use_octree, int n, const float *org, const float *dir, int *out_idx, float *out_t);
 

@@ -29,7 +29,7 @@ struct hs_counters { uint64_t rays, sphere_tests, aabb_tests, paths; uint32_t ma
 
 struct HostTree {
     std::vector<uint2> vox;
-    std::vector<uint32_t> refs, big_refs, ent_off;
+    std::vector<uint32_t> refs, big_refs, prolog, ent_off;
     std::vector<uint16_t> ent_cell;
     GridView grid;
     float planes[3][kPlanes];
@@ -114,12 +114,14 @@ static void build_host_tree(const std::vector<float4> &geom, const std::vector<i
     }
 }
 
-static void view_of(const HostTree &T, TreeView &tv) {
+static void view_of(HostTree &T, TreeView &tv) {
+    T.prolog.assign(1, 0u);
+    T.prolog.insert(T.prolog.end(), T.big_refs.begin(), T.big_refs.end());
     memset(&tv, 0, sizeof tv);
     tv.grid = T.grid;
     tv.grid.vox = T.vox.data(); tv.grid.refs = T.refs.data();
     tv.vis.ent_off = T.ent_off.data(); tv.vis.ent_cell = T.ent_cell.data();
-    tv.big_refs = T.big_refs.data(); tv.nbig = (int)T.big_refs.size();
+    tv.prolog = T.prolog.data(); tv.nprolog = (int)T.prolog.size();
     memcpy(tv.planes, T.planes, sizeof tv.planes);
 }
 
@@ -228,7 +230,9 @@ int hs_render_with_tree(const hs_sphere *sph, int n, const float *camera22, cons
     tv.grid.nx = gi[0]; tv.grid.ny = gi[1]; tv.grid.nz = gi[2];
     tv.grid.vox = static_cast<const uint2 *>(vox); tv.grid.refs = static_cast<const uint32_t *>(refs);
     tv.vis.ent_off = static_cast<const uint32_t *>(ent_off); tv.vis.ent_cell = static_cast<const uint16_t *>(ent_cell);
-    tv.big_refs = static_cast<const uint32_t *>(big_refs); tv.nbig = nbig;
+    std::vector<uint32_t> prolog(1, 0u);
+    prolog.insert(prolog.end(), static_cast<const uint32_t *>(big_refs), static_cast<const uint32_t *>(big_refs) + nbig);
+    tv.prolog = prolog.data(); tv.nprolog = (int)prolog.size();
     return render_core(sph, n, camera22, nullptr, p, 0.f, fb_gamma, nullptr, ctr_out, nullptr, &tv);
 }
 
