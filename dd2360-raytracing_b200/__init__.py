@@ -37,7 +37,7 @@ SPHERE_DTYPE = np.dtype(
 ABI_SYMBOLS = [
     "rt_abi_version", "rt_create", "rt_destroy", "rt_last_error", "rt_set_stream", "rt_device_info",
     "rt_scene_generate", "rt_scene_upload", "rt_scene_download", "rt_scene_size", "rt_camera_set", "rt_camera_get",
-    "rt_octree_build", "rt_octree_reference_bytes", "rt_octree_export_reference", "rt_octree_debug_read", "rt_debug_counters", "rt_trace_rays",
+    "rt_octree_build", "rt_octree_reference_bytes", "rt_octree_export_reference", "rt_octree_debug_read", "rt_xorwow_state", "rt_debug_counters", "rt_trace_rays",
     "rt_render_accumulate", "rt_finalize", "rt_render", "rt_render_to_host", "rt_format_ppm",
     "rt_ffma_peak", "rt_malloc", "rt_free", "rt_memcpy_to_host", "rt_synchronize",
 ]
@@ -106,6 +106,7 @@ def load_library(path: str | None = None) -> C.CDLL:
         "rt_octree_reference_bytes": (sz, [i32]),
         "rt_octree_export_reference": (i32, [vp, vp, sz]),
         "rt_octree_debug_read": (sz, [vp, i32, vp, sz]),
+        "rt_xorwow_state": (i32, [C.c_uint64, C.c_uint64, vp]),
         "rt_debug_counters": (i32, [vp, vp]),
         "rt_trace_rays": (i32, [vp, i32, i32, vp, vp, vp, vp]),
         "rt_render_accumulate": (i32, [vp, C.POINTER(RenderArgs), vp, C.POINTER(RenderStats)]),
@@ -137,6 +138,15 @@ def format_ppm(fb: np.ndarray) -> bytes:
     buf = C.create_string_buffer(need)
     L.rt_format_ppm(fb.ctypes.data, nx, ny, buf, need)
     return buf.raw[:need]
+
+
+def xorwow_state(seed: int, subsequence: int) -> np.ndarray:
+    """{d, v0..v4} after curand_init(seed, subsequence, 0), from the library's own skip-ahead matrices (host side)."""
+    out = np.zeros(6, dtype=np.uint32)
+    rc = load_library().rt_xorwow_state(seed, subsequence, out.ctypes.data)
+    if rc != 0:
+        raise RtError(f"rt_xorwow_state failed ({rc})")
+    return out
 
 
 def quantise(fb: np.ndarray) -> np.ndarray:

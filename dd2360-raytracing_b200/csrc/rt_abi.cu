@@ -14,6 +14,7 @@
 #include "rt_math.cuh"
 #include "rt_octree.h"
 #include "rt_render.h"
+#include "rt_xorwow_skip.h"
 
 using namespace rt;
 
@@ -45,7 +46,16 @@ struct rt_context {
     float *pinned = nullptr;
     size_t pinned_bytes = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // RT_SEED_UPSTREAM: skip-ahead matrices (device copy) and the per-pixel stream states
+    uint32_t *skip_tables = nullptr;
+    uint32_t *seed_states = nullptr;
+    size_t seed_states_words = 0;
 };
+
+static const std::vector<uint32_t> &host_skip_tables() {
+    static const std::vector<uint32_t> t = make_skip_tables();      // derived once per process (a few ms)
+    return t;
+}
 
 static int fail(rt_context *ctx, int code, const char *fmt, ...) {
     char buf[512];
@@ -101,6 +111,7 @@ extern "C" void rt_destroy(rt_context *ctx) {
     delete ctx->octree;
     cudaFree(ctx->geom); cudaFree(ctx->matl); cudaFree(ctx->tag); cudaFree(ctx->cam_dev);
     cudaFree(ctx->work_counter); cudaFree(ctx->counters); cudaFree(ctx->scratch_fb);
+    cudaFree(ctx->skip_tables); cudaFree(ctx->seed_states);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -338,8 +349,7 @@ static int do_render(rt_context *ctx, const rt_render_args *a, float *out_dev, b
     if (a->nx < 1 || a->ny < 1 || a->ns < 1) return fail(ctx, RT_ERR_INVALID, "render: bad nx/ny/ns");
     if (ctx->n < 1) return fail(ctx, RT_ERR_STATE, "render: no scene (rt_scene_generate / rt_scene_upload first)");
     if (a->use_octree && !ctx->octree->built) return fail(ctx, RT_ERR_STATE, "render: USE_OCTREE set but no octree built");
-    if (a->seed_mode != RT_SEED_HEAD)
-        return fail(ctx, RT_ERR_UNSUPPORTED, "render: only the HEAD seeding curand_init(1984+pixel_index,0,0) is implemented");
+    if (a->seed_mode != RT_SEED_HEAD && a->seed_mode != RT_SEED_UPSTREAM) return fail(ctx, RT_ERR_INVALID, "render: unknown seed_mode");
     CK(cudaSetDevice(ctx->device));
     if (!ctx->have_camera || ctx->cam_nx != a->nx || ctx->cam_ny != a->ny) {
         const int rc = rt_camera_set(ctx, nullptr, a->nx, a->ny);
@@ -391,7 +401,28 @@ static int do_render(rt_context *ctx, const rt_render_args *a, float *out_dev, b
     p.counters = ctx->counters;
     CK(cudaMemsetAsync(ctx->counters, 0, 32 * 8, ctx->stream));
     int blocks = 0;
+    int launches = 1;
+    if (a->seed_mode == RT_SEED_UPSTREAM) {
+        const size_t npix = (size_t)a->nx * a->ny;
+        if (!ctx->skip_tables) {
+            const std::vector<uint32_t> &t = host_skip_tables();
+            CK(cudaMalloc(&ctx->skip_tables, t.size() * 4));
+            CK(cudaMemcpyAsync(ctx->skip_tables, t.data(), t.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+        }
+        if (ctx->seed_states_words < npix * 6) {
+            cudaFree(ctx->seed_states);
+            ctx->seed_states = nullptr; ctx->seed_states_words = 0;
+            CK(cudaMalloc(&ctx->seed_states, npix * 6 * 4));
+            ctx->seed_states_words = npix * 6;
+        }
+        p.seed_states = ctx->seed_states;
+    }
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    if (p.seed_states) {   // render_init (main.cu:424): inside the timed region, as in the reference
+        // spp shard g draws from subsequences pixel_index + g * num_pixels (g = 0: the reference's streams)
+        CK(launch_seed_upstream(ctx->seed_states, (size_t)a->nx * a->ny, 1984ull, p.seed_offset, ctx->skip_tables, ctx->stream));
+        launches = 2;
+    }
     CK(launch_render(p, a->use_octree != 0, ctx->prop.multiProcessorCount, ctx->prop.sharedMemPerBlockOptin, ctx->stream, &blocks));
     CK(cudaEventRecord(ctx->ev1, ctx->stream));
     if (stats) {
@@ -409,8 +440,17 @@ static int do_render(rt_context *ctx, const rt_render_args *a, float *out_dev, b
         float ms = 0;
         cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
         stats->kernel_ms = ms;
-        stats->launches = 1;
+        stats->launches = launches;
     }
+    return RT_OK;
+}
+
+// curand_init(seed, subsequence, 0) -> {d, v0..v4}: host-side evaluation with the library's own skip matrices (no GPU needed)
+extern "C" int rt_xorwow_state(unsigned long long seed, unsigned long long subsequence, uint32_t out6[6]) {
+    if (!out6 || (subsequence >> kSkipBits)) return RT_ERR_INVALID;
+    xorwow s;
+    xorwow_seed_subsequence(s, seed, subsequence, host_skip_tables().data());
+    out6[0] = s.d; out6[1] = s.v0; out6[2] = s.v1; out6[3] = s.v2; out6[4] = s.v3; out6[5] = s.v4;
     return RT_OK;
 }
 

@@ -438,7 +438,7 @@ __global__ void __launch_bounds__(kRenderThreads, MINB) k_render_pool(const __gr
                         c.su(F_SD, 0u);
                         c.sv3(F_CX, mk(0, 0, 0));
                         xorwow rng;
-                        xorwow_seed(rng, (unsigned long long)(long long)(1984 + pix) + p.seed_offset);   // main.cu:93
+                        pixel_stream(p, pix, rng);
                         gen_sample<NC>(c, p, pix, rng, nrays, npaths);
                         c.store_rng(rng);
                     }                                   // else: a tile position outside the image; claim again

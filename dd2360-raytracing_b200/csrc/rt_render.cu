@@ -19,6 +19,7 @@
 
 #include "rt_render.h"
 #include "rt_trace.cuh"
+#include "rt_xorwow_skip.h"
 
 namespace rt {
 
@@ -67,6 +68,35 @@ __device__ __forceinline__ void stage_bulk(void *dst, const void *src, uint32_t 
         const uint32_t n = bytes - off < kChunk ? bytes - off : kChunk;
         bulk_g2s(static_cast<char *>(dst) + off, static_cast<const char *>(src) + off, n, bar);
     }
+}
+
+// render_init (main.cu:84-94): the pixel's XORWOW stream.  HEAD seeding curand_init(1984 + pixel_index, 0, 0) is a dozen
+// integer operations and happens right here; the upstream form curand_init(1984, pixel_index, 0) needs the skip-ahead
+// and is precomputed per pixel by k_seed_upstream.
+__device__ __forceinline__ void pixel_stream(const RenderLaunch &p, const int pix, xorwow &rng) {
+    if (p.seed_states) {
+        const uint2 *s = reinterpret_cast<const uint2 *>(p.seed_states + (size_t)pix * 6);
+        const uint2 a = __ldg(s), b = __ldg(s + 1), c = __ldg(s + 2);
+        rng.d = a.x; rng.v0 = a.y; rng.v1 = b.x; rng.v2 = b.y; rng.v3 = c.x; rng.v4 = c.y;
+    } else {
+        xorwow_seed(rng, (unsigned long long)(long long)(1984 + pix) + p.seed_offset);   // main.cu:93
+    }
+}
+
+__global__ void k_seed_upstream(uint32_t *__restrict__ states, size_t npix, unsigned long long seed, unsigned long long base,
+                                const uint32_t *__restrict__ tables) {
+    const size_t pix = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pix >= npix) return;
+    xorwow s;
+    xorwow_seed_subsequence(s, seed, base + pix, tables);
+    uint2 *o = reinterpret_cast<uint2 *>(states + pix * 6);
+    o[0] = make_uint2(s.d, s.v0); o[1] = make_uint2(s.v1, s.v2); o[2] = make_uint2(s.v3, s.v4);
+}
+
+cudaError_t launch_seed_upstream(uint32_t *states, size_t npix, unsigned long long seed, unsigned long long subsequence_base,
+                                 const uint32_t *tables, cudaStream_t st) {
+    k_seed_upstream<<<(unsigned)((npix + 127) / 128), 128, 0, st>>>(states, npix, seed, subsequence_base, tables);
+    return cudaGetLastError();
 }
 
 // item -> pixel.  Items enumerate 8x4 tiles row-major, 32 pixels per tile; `tile_stride/tile_first` select the
@@ -142,7 +172,7 @@ __global__ void __launch_bounds__(kRenderThreads, 4) k_render(const __grid_const
                     pix = pj * p.nx + pi;
                     s = 0; depth = 0;
                     col = mk(0, 0, 0);
-                    xorwow_seed(rng, (unsigned long long)(long long)(1984 + pix) + p.seed_offset);   // main.cu:93
+                    pixel_stream(p, pix, rng);
                 }
             }
             first = false;
@@ -293,7 +323,13 @@ cudaError_t launch_render(const RenderLaunch &p, bool octree, int sm_count, size
             case 12: return pool::launch_pool<128, 3>(p, sm_count, st, blocks_out);
             case 13: return pool::launch_pool<32, 8>(p, sm_count, st, blocks_out);
             case 14: return pool::launch_pool<64, 4>(p, sm_count, st, blocks_out);
-            default: return launch_variant<true, false>(p, 0, sm_count, st, blocks_out);
+            case 1: return launch_variant<true, false>(p, 0, sm_count, st, blocks_out);
+            default:
+                // measured on B200 (profiles/README.md r01m): the pooled kernel wins once candidate lists are long
+                // (+28 % at 100 k spheres 4K, +34 % at 1 M); short lists (< ~50 k spheres) leave its scheduling rounds
+                // too little work to amortise, there the pixel-per-lane kernel is ~30 % faster
+                if (p.scene.n >= kPoolMinSpheres) return pool::launch_pool<64, 6>(p, sm_count, st, blocks_out);
+                return launch_variant<true, false>(p, 0, sm_count, st, blocks_out);
         }
     }
     const size_t geom_bytes = (size_t)p.scene.n * sizeof(float4);

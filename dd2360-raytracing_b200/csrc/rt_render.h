@@ -8,6 +8,7 @@
 namespace rt {
 
 constexpr int kRenderThreads = 128;
+constexpr int kPoolMinSpheres = 50000;   // octree mode: scenes at least this large use the pooled kernel (rt_pool.cuh)
 
 struct RenderLaunch {
     SceneView scene;
@@ -20,6 +21,7 @@ struct RenderLaunch {
     int tile_first, tile_stride;   // this shard owns tiles tile_first + k*tile_stride
     uint32_t total_items;    // owned tiles * 32
     unsigned long long seed_offset;   // added to the per-pixel seed 1984 + pixel_index (spp shards)
+    const uint32_t *seed_states;      // RT_SEED_UPSTREAM: 6 words {d, v0..v4} per pixel from k_seed_upstream; else nullptr
     uint32_t max_rounds;     // pool kernel watchdog: scheduling rounds per warp before it gives up (host reports an error)
     int tune_sticky, tune_sticky_min;   // pool kernel: TEST chunks per scheduling round, and the lane count that keeps it going
     int variant;             // kernel variant for A/B measurements (rt_render_args.reserved[1]); 0 = default
@@ -35,6 +37,9 @@ cudaError_t launch_render(const RenderLaunch &p, bool octree, int sm_count, size
                           int *blocks_out);
 cudaError_t launch_trace_rays(const RenderLaunch &p, bool octree, const float *org, const float *dir, int n, int *out_idx,
                               float *out_t, cudaStream_t st);
+// render_init with the upstream seeding curand_init(1984, pixel_index + subsequence_base, 0) (main.cu:90)
+cudaError_t launch_seed_upstream(uint32_t *states, size_t npix, unsigned long long seed, unsigned long long subsequence_base,
+                                 const uint32_t *tables, cudaStream_t st);
 cudaError_t launch_finalize(const float *accum, float *fb, int nx, int ny, int ns, cudaStream_t st);
 
 }  // namespace rt

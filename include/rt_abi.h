@@ -114,6 +114,11 @@ int rt_octree_export_reference(rt_context *ctx, void *host_blob, size_t bytes);
  * (host == NULL) or bytes copied. */
 size_t rt_octree_debug_read(rt_context *ctx, int which, void *host, size_t cap);
 
+/* cuRAND XORWOW state {d, v0..v4} after curand_init(seed, subsequence, 0) (curand_kernel.h:772-797), evaluated on the host
+ * with the skip-ahead matrices this library derives itself; subsequence < 2^40.  What RT_SEED_UPSTREAM gives pixel
+ * `subsequence` (seed 1984, main.cu:90).  Needs no GPU. */
+int rt_xorwow_state(unsigned long long seed, unsigned long long subsequence, uint32_t out6[6]);
+
 /* test hook: raw device counters of the last render call.  [0] rays, [1] paths; RT_COUNTERS builds add [2] sphere tests,
  * [3] visibility line tests, [4] voxel steps and, for the pooled kernel, [8+s] scheduling rounds and [18+s] contexts
  * processed per state s. */

@@ -53,10 +53,13 @@ class RenderParams(C.Structure):
                                        "i0", "i1", "istep", "j0", "j1", "jstep", "threads")]
 
 
+SEED_HEAD, SEED_UPSTREAM = 0, 1
+
+
 def make_params(nx, ny, ns, use_octree, spl=30, arith=ARITH_DEVICE, window=None, step=(1, 1), threads=0,
-                max_depth=50) -> RenderParams:
+                max_depth=50, seed_mode=SEED_HEAD) -> RenderParams:
     i0, i1, j0, j1 = window if window else (0, nx, 0, ny)
-    return RenderParams(nx, ny, ns, int(use_octree), spl, arith, 0, max_depth, i0, i1, step[0], j0, j1, step[1], threads)
+    return RenderParams(nx, ny, ns, int(use_octree), spl, arith, seed_mode, max_depth, i0, i1, step[0], j0, j1, step[1], threads)
 
 
 def build(force: bool = False) -> str:
@@ -90,6 +93,8 @@ def lib() -> C.CDLL:
         L.rto_write_ppm.restype = C.c_size_t
         L.rto_write_ppm.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t]
         L.rto_xorwow_stream.argtypes = [C.c_uint64, C.c_int, C.c_void_p, C.c_void_p]
+        L.rto_xorwow_state.argtypes = [C.c_uint64, C.c_uint64, C.c_void_p]
+        L.rto_xorwow_skip_tables.argtypes = [C.c_void_p, C.c_int]
         L.rto_closest_hit.restype = C.c_int
         L.rto_closest_hit.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                       C.c_void_p, C.c_void_p, C.POINTER(C.c_float)]
@@ -169,6 +174,20 @@ def xorwow_stream(seed: int, count: int):
     return u, f
 
 
+def xorwow_state(seed: int, subsequence: int) -> np.ndarray:
+    """{d, v0..v4} after curand_init(seed, subsequence, 0), from the restatement."""
+    out = np.zeros(6, dtype=np.uint32)
+    lib().rto_xorwow_state(C.c_uint64(seed), C.c_uint64(subsequence), _p(out))
+    return out
+
+
+def xorwow_skip_tables(bits: int = 40) -> np.ndarray:
+    """The GF(2) skip matrices T^(2^(67+k)): [bits, 160, 5] uint32."""
+    out = np.zeros((bits, 160, 5), dtype=np.uint32)
+    n = lib().rto_xorwow_skip_tables(_p(out), bits)
+    return out[:n]
+
+
 def closest_hit(spheres, o, d, blob=None, spl=30, use_octree=False, arith=ARITH_DEVICE):
     o = np.asarray(o, dtype=np.float32)
     d = np.asarray(d, dtype=np.float32)
@@ -197,6 +216,8 @@ class RefHost:
         L.refh_closest_hit.restype = C.c_int
         L.refh_closest_hit.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_float)]
         L.refh_destroy.argtypes = [C.c_void_p]
+        if hasattr(L, "refh_curand_state"):
+            L.refh_curand_state.argtypes = [C.c_uint64, C.c_uint64, C.c_void_p]
         self.L = L
         self.spl = L.refh_spl()
         self.use_octree = bool(L.refh_use_octree())
@@ -233,6 +254,12 @@ class RefHost:
         ctr = Counters()
         self.L.refh_render(self.world, C.byref(params), _p(fb), _p(lin), C.byref(ctr))
         return fb, lin, ctr.as_dict()
+
+    def curand_state(self, seed: int, subsequence: int) -> np.ndarray:
+        """cuRAND's own curand_init(seed, subsequence, 0) (toolkit header compiled for the host)."""
+        out = np.zeros(6, dtype=np.uint32)
+        self.L.refh_curand_state(seed, subsequence, _p(out))
+        return out
 
     def closest_hit(self, o, d):
         o = np.asarray(o, dtype=np.float32)

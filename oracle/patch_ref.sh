@@ -29,6 +29,15 @@ sed -i -E 's/^#define USE_OCTREE.*/#ifdef RTO_USE_OCTREE\n#define USE_OCTREE\n#e
 must "$OUT/acceleration_structure.h" '^#define SPHERES_PER_LEAF 30'
 sed -i -E 's/^#define SPHERES_PER_LEAF 30.*/#define SPHERES_PER_LEAF RTO_SPL/' "$OUT/acceleration_structure.h"
 
+# optional (variant suffix _upseed): the upstream per-pixel seeding curand_init(1984, pixel_index, 0) that HEAD keeps
+# as a comment on main.cu:90 replaces the HEAD form on main.cu:93
+if [ "${RTO_UPSEED:-0}" = 1 ]; then
+  must "$OUT/main.cu" '^[[:space:]]*// curand_init\(1984, pixel_index, 0, &rand_state\[pixel_index\]\);'
+  must "$OUT/main.cu" '^[[:space:]]*curand_init\(1984 \+ pixel_index, 0, 0, &rand_state\[pixel_index\]\);'
+  sed -i -E 's|^([[:space:]]*)// curand_init\(1984, pixel_index, 0, &rand_state\[pixel_index\]\);|\1curand_init(1984, pixel_index, 0, \&rand_state[pixel_index]);|' "$OUT/main.cu"
+  sed -i -E 's|^([[:space:]]*)curand_init\(1984 \+ pixel_index, 0, 0, &rand_state\[pixel_index\]\);|\1// (HEAD form disabled for this variant)|' "$OUT/main.cu"
+fi
+
 if [ "$KIND" = host ]; then
   must "$OUT/material.h" '^#define RANDVEC3 vec3\(curand_uniform'
   sed -i -E 's/^#define RANDVEC3 vec3\(curand_uniform.*/static inline __host__ __device__ vec3 rto_randvec3(curandState *s_) { real_t a_ = curand_uniform(s_); real_t b_ = curand_uniform(s_); real_t c_ = curand_uniform(s_); return vec3(a_, b_, c_); }\n#define RANDVEC3 rto_randvec3(local_rand_state)/' "$OUT/material.h"

@@ -218,7 +218,8 @@ int refh_render(refh_world *w, const refh_params *p, float *fb_gamma, float *fb_
             for (int i = p->i0; i < p->i1; i += p->istep) {
                 const int pixel_index = j * p->nx + i;
                 curandState local_rand_state;
-                curand_init(1984 + pixel_index, 0, 0, &local_rand_state);          /* main.cu:93 */
+                if (p->seed_mode == 1) curand_init(1984, pixel_index, 0, &local_rand_state);   /* main.cu:90, the upstream form */
+                else curand_init(1984 + pixel_index, 0, 0, &local_rand_state);                 /* main.cu:93, HEAD */
                 vec3 col(0, 0, 0);
                 for (int s = 0; s < p->ns; s++) {
                     real_t u = real_t(i + curand_uniform(&local_rand_state)) / real_t(p->nx);
@@ -250,6 +251,14 @@ int refh_render(refh_world *w, const refh_params *p, float *fb_gamma, float *fb_
 }
 
 /* one ray through the reference's own closest-hit code; returns sphere index or -1 */
+/* cuRAND itself (the toolkit header, host-compiled): state words {d, v0..v4} after curand_init(seed, subsequence, 0) */
+void refh_curand_state(unsigned long long seed, unsigned long long subsequence, unsigned int out6[6]) {
+    curandState s;
+    curand_init(seed, subsequence, 0, &s);
+    out6[0] = s.d;
+    for (int k = 0; k < 5; k++) out6[1 + k] = s.v[k];
+}
+
 int refh_closest_hit(refh_world *w, const float *o, const float *d, float *t_out) {
     ray r(vec3(o[0], o[1], o[2]), vec3(d[0], d[1], d[2]));
     hit_record rec;

@@ -60,6 +60,71 @@ static inline float xorwow_uniform(xorwow *s) {
     return (float)xorwow_next(s) * 2.3283064e-10f + (2.3283064e-10f / 2.0f);
 }
 
+/* ---- cuRAND XORWOW subsequences: curand_init(seed, subsequence, 0) (curand_kernel.h:772-797) --------------------------
+ * Subsequence s starts 2^67 * s draws into the stream of the seed (XORWOW_SEQUENCE_SPACING 67, curand_precalc.h:54).
+ * The five xorshift words advance LINEARLY over GF(2) (the Weyl counter d does not move: 362437 * 2^67 = 0 mod 2^32,
+ * curand_kernel.h:697), so "skip 2^67 * s draws" is the 160x160 bit matrix T^(2^67 * s) applied to the words.  cuRAND
+ * ships T^(2^67 * 4^k) as 218 KB of precalculated tables; this restatement derives them from the step function
+ * itself: T by stepping the 160 unit vectors (as curand_kernel.h:569-586 does), S = T^(2^67) by 67 squarings, then
+ * B[k] = S^(2^k), and applies B[k] for every set bit k of the subsequence number.  Powers of T commute, so this is
+ * the same product cuRAND forms from its base-4 digits. */
+#define RTO_SKIP_BITS 40
+typedef struct { uint32_t row[160][5]; } gf2_mat;          /* row[i] = image of unit vector i (bit i%32 of word i/32) */
+static gf2_mat g_skip[RTO_SKIP_BITS];
+static int g_skip_ready = 0;
+
+static void gf2_apply(const gf2_mat *m, const uint32_t in[5], uint32_t out[5]) {
+    uint32_t r[5] = {0, 0, 0, 0, 0};
+    for (int i = 0; i < 5; i++)
+        for (int j = 0; j < 32; j++)
+            if (in[i] >> j & 1u)
+                for (int k = 0; k < 5; k++) r[k] ^= m->row[i * 32 + j][k];
+    for (int k = 0; k < 5; k++) out[k] = r[k];
+}
+static void gf2_square(const gf2_mat *m, gf2_mat *out) {     /* out = m o m */
+    gf2_mat t;
+    for (int i = 0; i < 160; i++) gf2_apply(m, m->row[i], t.row[i]);
+    *out = t;
+}
+static void skip_tables_init(void) {
+#pragma omp critical(rto_skip_tables)
+    if (!g_skip_ready) {
+        gf2_mat t;
+        for (int i = 0; i < 160; i++) {
+            xorwow s;
+            memset(&s, 0, sizeof s);
+            s.v[i / 32] = 1u << (i & 31);
+            xorwow_next(&s);
+            for (int k = 0; k < 5; k++) t.row[i][k] = s.v[k];
+        }
+        for (int q = 0; q < 67; q++) gf2_square(&t, &t);
+        g_skip[0] = t;
+        for (int k = 1; k < RTO_SKIP_BITS; k++) gf2_square(&g_skip[k - 1], &g_skip[k]);
+        g_skip_ready = 1;
+    }
+}
+static void xorwow_init_subseq(xorwow *s, uint64_t seed, uint64_t subsequence) {
+    xorwow_init(s, seed);
+    if (!subsequence) return;
+    if (!g_skip_ready) skip_tables_init();
+    for (int k = 0; k < RTO_SKIP_BITS && subsequence >> k; k++)
+        if (subsequence >> k & 1u) gf2_apply(&g_skip[k], s->v, s->v);
+}
+/* state words {d, v0..v4} after curand_init(seed, subsequence, 0) */
+void rto_xorwow_state(uint64_t seed, uint64_t subsequence, uint32_t out6[6]) {
+    xorwow s;
+    xorwow_init_subseq(&s, seed, subsequence);
+    out6[0] = s.d;
+    for (int k = 0; k < 5; k++) out6[1 + k] = s.v[k];
+}
+/* the skip tables themselves (RTO_SKIP_BITS x 160 x 5 words), for checking the product's own copy */
+int rto_xorwow_skip_tables(uint32_t *out, int max_bits) {
+    if (!g_skip_ready) skip_tables_init();
+    int nb = max_bits < RTO_SKIP_BITS ? max_bits : RTO_SKIP_BITS;
+    if (out) memcpy(out, g_skip, (size_t)nb * sizeof(gf2_mat));
+    return nb;
+}
+
 void rto_xorwow_stream(uint64_t seed, int count, uint32_t *out_u32, float *out_uniform) {
     xorwow a, b;
     xorwow_init(&a, seed);
@@ -263,7 +328,8 @@ int rto_build_octree(const rto_sphere *sph, int n, int spl, void *blob, rto_octr
 
 int rto_render(const rto_sphere *sph, int n, const rto_camera *cam, const void *blob, const rto_render_params *p,
                float *fb_gamma, float *fb_linear, rto_counters *ctr_out) {
-    if (p->seed_mode != RTO_SEED_HEAD) return -2;     /* upstream seeding needs cuRAND skip-ahead tables */
+    if (p->seed_mode != RTO_SEED_HEAD && p->seed_mode != RTO_SEED_UPSTREAM) return -2;
+    if (p->seed_mode == RTO_SEED_UPSTREAM && !g_skip_ready) skip_tables_init();
     if (p->use_octree && !blob) return -1;
     oct_view ov;
     memset(&ov, 0, sizeof ov);

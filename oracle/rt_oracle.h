@@ -97,6 +97,10 @@ void rto_quantise(const float *fb_gamma, int nx, int ny, uint8_t *out_rgb);
 
 /* cuRAND XORWOW known-answer helper: first `count` outputs of curand() after curand_init(seed,0,0). */
 void rto_xorwow_stream(uint64_t seed, int count, uint32_t *out_u32, float *out_uniform);
+/* {d, v0..v4} after curand_init(seed, subsequence, 0): subsequence s starts 2^67 * s draws into the seed's stream. */
+void rto_xorwow_state(uint64_t seed, uint64_t subsequence, uint32_t out6[6]);
+/* the GF(2) skip matrices T^(2^(67+k)), k < max_bits (each 160 rows x 5 words); returns the number written */
+int rto_xorwow_skip_tables(uint32_t *out, int max_bits);
 
 /* Single-ray closest hit (for per-ray parity tests): returns sphere index or -1; t/normal out. */
 int rto_closest_hit(const rto_sphere *spheres, int n, const void *octree_blob, int spl, int use_octree,

@@ -272,7 +272,8 @@ static void SUF(render_pixel)(const rto_sphere *sph, int n, const rto_camera *ca
                               rto_counters *ctr) {
     int pixel_index = j * p->nx + i;
     xorwow rng;
-    xorwow_init(&rng, (uint64_t)(int64_t)(1984 + pixel_index));     /* main.cu:93 */
+    if (p->seed_mode == RTO_SEED_UPSTREAM) xorwow_init_subseq(&rng, 1984, (uint64_t)pixel_index);   /* main.cu:90 (commented out at HEAD) */
+    else xorwow_init(&rng, (uint64_t)(int64_t)(1984 + pixel_index));                                /* main.cu:93 */
     v3 col = V3(0, 0, 0);
     for (int s = 0; s < p->ns; s++) {
         float u = ((float)i + xorwow_uniform(&rng)) / (float)p->nx;   /* main.cu:104 */

@@ -4,7 +4,7 @@
 # /root/reference, recompiled for sm_100) on the GPU box and dumps float framebuffers, sphere lists, cameras
 # and Octree blobs into gpurun_out/golden_ref_cuda/.  tests/golden/pack_ref_cuda.py then packs them into the
 # fixtures committed under tests/golden/ref_cuda/.
-#   usage (from the repo root, on a B200):  bash tests/golden/gen_ref_cuda.sh [small|timing|all]
+#   usage (from the repo root, on a B200):  bash tests/golden/gen_ref_cuda.sh [small|upseed|timing|all]
 set -uo pipefail
 MODE="${1:-all}"
 R=oracle/_ref
@@ -31,6 +31,11 @@ if [ "$MODE" = small ] || [ "$MODE" = all ]; then
   # big dumps are only checksummed (they are reproducible from the oracle)
   sha256sum "$O"/*.spheres "$O"/*.octree > "$O/sha256.txt"
   rm -f "$O/n100000.spheres" "$O/n100000_spl300.octree" "$O/n8000.spheres"
+fi
+if [ "$MODE" = upseed ] || [ "$MODE" = all ]; then
+  # the upstream per-pixel seeding curand_init(1984, pixel_index, 0) (main.cu:90 swapped in for :93 by patch_ref.sh)
+  run n488_oct_spl30_upseed upseed 240 160 4 --fb "$O/n488_oct_upseed_240x160x4.fb"
+  run n488_oct_spl30_upseed upseed_timing 1200 800 10 --reps 3
 fi
 if [ "$MODE" = timing ] || [ "$MODE" = all ]; then
   run n488_brute_spl30 C1 1200 800 10 --reps 3 --fb "$O/C1_1200x800x10.fb"

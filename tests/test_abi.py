@@ -76,3 +76,13 @@ def test_product_never_touches_the_oracle():
                 txt = open(os.path.join(dirpath, f), errors="ignore").read()
                 for banned in ("rto_", "librt_oracle", "oracle_py", "rt_oracle.h", "load_oracle", "_ref/"):
                     assert banned not in txt, (f, banned)
+
+
+def test_library_skip_ahead_matches_curand(pkg, golden_dir):
+    """rt_xorwow_state (host side, no GPU): the product's own skip-ahead matrices against cuRAND's answers."""
+    import json
+    kat = json.load(open(os.path.join(golden_dir, "curand_subsequence_kat.json")))
+    for c in kat["cases"]:
+        assert [int(x) for x in pkg.xorwow_state(c["seed"], c["subsequence"])] == c["state"], c
+    with pytest.raises(pkg.RtError):
+        pkg.xorwow_state(1984, 2 ** 40)

@@ -146,6 +146,44 @@ def test_render_matches_reference_cuda_goldens(rt, pkg, golden_dir):
     assert ppm.startswith(b"P3\n1200 800\n255\n") and ppm.count(b"\n") == 3 + 1200 * 800
 
 
+@pytest.mark.parametrize("n,spl,octree,nx,ny,ns", [
+    (488, 30, True, 240, 160, 4),
+    (488, 30, False, 96, 64, 2),
+    (100000, 300, True, 192, 108, 2),    # pooled kernel
+])
+def test_upstream_seeding_matches_oracle(rt, pkg, O, golden_dir, n, spl, octree, nx, ny, ns):
+    """RT_SEED_UPSTREAM = curand_init(1984, pixel_index, 0) (main.cu:90): per-pixel states from the library's own
+    skip-ahead kernel; frames bit-identical to the oracle, and to the reference's CUDA build patched to that line."""
+    rt.create_world(n, 0.1)
+    sph, _ = O.create_world(n)
+    blob = None
+    if octree:
+        rt.build_octree(spl)
+        blob, _ = O.build_octree(sph, spl)
+    fb, s = rt.render(nx, ny, ns, use_octree=octree, seed_mode=pkg.SEED_UPSTREAM)
+    ref, _, ctr = O.render(sph, O.camera(nx, ny, O.ARITH_DEVICE),
+                           O.make_params(nx, ny, ns, octree, spl, O.ARITH_DEVICE, seed_mode=O.SEED_UPSTREAM), blob)
+    assert _frac_identical(fb, ref) >= 1 - POWF_ALLOWANCE and s["launches"] == 2
+    assert abs(int(s["rays"]) - ctr["rays"]) <= max(2, int(POWF_ALLOWANCE * ctr["rays"]))
+    gold = os.path.join(golden_dir, "ref_cuda", f"n{n}_oct_upseed_{nx}x{ny}x{ns}.npz")
+    if octree and os.path.exists(gold):
+        assert _frac_identical(fb, np.load(gold)["fb"]) == 1.0
+
+
+def test_upstream_seeding_spp_shards_use_disjoint_subsequences(rt, pkg):
+    import torch
+    nx, ny = 64, 48
+    rt.create_world(488, 0.1)
+    rt.build_octree(30)
+    a = torch.zeros((ny, nx, 3), dtype=torch.float32, device="cuda")
+    b = torch.zeros_like(a)
+    c = torch.zeros_like(a)
+    rt.render_accumulate(rt.args(nx, ny, 2, True, seed_mode=pkg.SEED_UPSTREAM), a.data_ptr())
+    rt.render_accumulate(rt.args(nx, ny, 4, True, seed_mode=pkg.SEED_UPSTREAM, shard_mode=pkg.SHARD_SPP, shard_rank=0, shard_count=2), b.data_ptr())
+    rt.render_accumulate(rt.args(nx, ny, 4, True, seed_mode=pkg.SEED_UPSTREAM, shard_mode=pkg.SHARD_SPP, shard_rank=1, shard_count=2), c.data_ptr())
+    assert torch.equal(a, b) and not torch.equal(b, c)
+
+
 def test_metal_fuzz_is_clamped_like_the_reference_constructor(rt, pkg):
     sph = np.zeros(8, dtype=pkg.SPHERE_DTYPE)
     sph[0] = (0, -1000, -1, 1000, 0, 0.5, 0.5, 0.5, 0)
@@ -247,6 +285,6 @@ def test_error_behaviour(rt, pkg):
         fresh.render(8, 8, 1, use_octree=True)
     with pytest.raises(pkg.RtError):
         fresh.create_world(3, 0.1)
-    with pytest.raises(pkg.RtError, match="HEAD"):
-        fresh.render(8, 8, 1, use_octree=False, seed_mode=pkg.SEED_UPSTREAM)
+    with pytest.raises(pkg.RtError, match="seed_mode"):
+        fresh.render(8, 8, 1, use_octree=False, seed_mode=7)
     fresh.close()
