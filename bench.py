@@ -28,8 +28,10 @@ CONFIGS = {
     "C1": (488, 30, 0, 1200, 800, 10, "C1: RTIOW scene, 488 spheres, flat hitable_list, 1200x800, 10 spp, FP32"),
     "C2": (488, 30, 1, 1200, 800, 10, "C2: 488 spheres, octree SPHERES_PER_LEAF=30, 1200x800, 10 spp, FP32"),
     "C3": (100000, 300, 1, 3840, 2160, 64, "C3: 100k random spheres, octree SPHERES_PER_LEAF=300, 3840x2160, 64 spp, FP32"),
+    "C4": (100000, 300, 1, 3840, 2160, 64, "C4: 100k random spheres, octree SPHERES_PER_LEAF=300, 3840x2160, 64 spp, USE_FP16"),
     "C5": (1000000, 3000, 1, 7680, 4320, 256, "C5: 1M random spheres, octree SPHERES_PER_LEAF=3000, 7680x4320, 256 spp, FP32"),
 }
+FP16_CONFIGS = {"C4"}
 # CPU sample of the workload: every CPU_STRIDE-th pixel in x and y of the full frame, all ns samples
 CPU_STRIDE = {"C1": (4, 4), "C2": (2, 2), "C3": (16, 16), "C5": (96, 96)}
 # reference CUDA build on the same B200 (oracle/_ref/ref_cuda_*, measured with tests/golden/gen_ref_cuda.sh);

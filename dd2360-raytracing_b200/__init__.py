@@ -27,6 +27,7 @@ INCLUDE_DIR = os.path.normpath(os.path.join(HERE, "..", "include"))
 MAT_NONE, MAT_LAMBERTIAN, MAT_METAL, MAT_DIELECTRIC = -1, 0, 1, 2
 SEED_HEAD, SEED_UPSTREAM = 0, 1
 SHARD_NONE, SHARD_TILES, SHARD_SPP = 0, 1, 2
+PREC_FP32, PREC_FP16 = 0, 1
 
 SPHERE_DTYPE = np.dtype(
     [("cx", "<f4"), ("cy", "<f4"), ("cz", "<f4"), ("radius", "<f4"), ("mat", "<i4"),
@@ -36,8 +37,8 @@ SPHERE_DTYPE = np.dtype(
 # every symbol include/rt_abi.h declares (tests check the library exports exactly these)
 ABI_SYMBOLS = [
     "rt_abi_version", "rt_create", "rt_destroy", "rt_last_error", "rt_set_stream", "rt_device_info",
-    "rt_scene_generate", "rt_scene_upload", "rt_scene_download", "rt_scene_size", "rt_camera_set", "rt_camera_get",
-    "rt_octree_build", "rt_octree_reference_bytes", "rt_octree_export_reference", "rt_octree_debug_read", "rt_xorwow_state", "rt_debug_counters", "rt_trace_rays",
+    "rt_scene_generate", "rt_scene_generate_ex", "rt_scene_upload", "rt_scene_download", "rt_scene_size", "rt_camera_set", "rt_camera_get", "rt_camera_get_half",
+    "rt_octree_build", "rt_octree_build_ex", "rt_octree_reference_bytes", "rt_octree_export_reference", "rt_octree_debug_read", "rt_xorwow_state", "rt_debug_counters", "rt_trace_rays",
     "rt_render_accumulate", "rt_finalize", "rt_render", "rt_render_to_host", "rt_format_ppm",
     "rt_ffma_peak", "rt_malloc", "rt_free", "rt_memcpy_to_host", "rt_synchronize",
 ]
@@ -55,7 +56,7 @@ class OctreeStats(C.Structure):
 class RenderArgs(C.Structure):
     _fields_ = [("nx", C.c_int32), ("ny", C.c_int32), ("ns", C.c_int32), ("max_depth", C.c_int32),
                 ("use_octree", C.c_int32), ("seed_mode", C.c_int32), ("shard_mode", C.c_int32),
-                ("shard_rank", C.c_int32), ("shard_count", C.c_int32), ("reserved", C.c_int32 * 7)]
+                ("shard_rank", C.c_int32), ("shard_count", C.c_int32), ("precision", C.c_int32), ("tune", C.c_int32 * 6)]
 
 
 class RenderStats(C.Structure):
@@ -97,12 +98,15 @@ def load_library(path: str | None = None) -> C.CDLL:
         "rt_set_stream": (i32, [vp, vp]),
         "rt_device_info": (i32, [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(sz)]),
         "rt_scene_generate": (i32, [vp, i32, f32]),
+        "rt_scene_generate_ex": (i32, [vp, i32, f32, i32]),
         "rt_scene_upload": (i32, [vp, vp, i32]),
         "rt_scene_download": (i32, [vp, vp, i32]),
         "rt_scene_size": (i32, [vp]),
         "rt_camera_set": (i32, [vp, C.POINTER(CameraDesc), i32, i32]),
         "rt_camera_get": (i32, [vp, vp]),
+        "rt_camera_get_half": (i32, [vp, i32, i32, vp]),
         "rt_octree_build": (i32, [vp, i32, C.POINTER(OctreeStats)]),
+        "rt_octree_build_ex": (i32, [vp, i32, i32, C.POINTER(OctreeStats)]),
         "rt_octree_reference_bytes": (sz, [i32]),
         "rt_octree_export_reference": (i32, [vp, vp, sz]),
         "rt_octree_debug_read": (sz, [vp, i32, vp, sz]),
@@ -195,8 +199,8 @@ class RayTracer:
         return {"sm_count": sm.value, "clock_khz": clk.value, "mem_bytes": mem.value}
 
     # -- scene (main.cu:388-401) --
-    def create_world(self, n: int, radius: float = 0.1):
-        self._ck(self.L.rt_scene_generate(self._ctx, n, radius), "rt_scene_generate")
+    def create_world(self, n: int, radius: float = 0.1, precision: int = PREC_FP32):
+        self._ck(self.L.rt_scene_generate_ex(self._ctx, n, radius, precision), "rt_scene_generate_ex")
         self.n = n
         return self
 
@@ -219,10 +223,16 @@ class RayTracer:
         self._ck(self.L.rt_camera_get(self._ctx, out.ctypes.data), "rt_camera_get")
         return out
 
+    def camera_half(self, nx: int, ny: int) -> np.ndarray:
+        """The camera of the USE_FP16 build for an nx x ny frame (half values widened to float)."""
+        out = np.zeros(22, dtype=np.float32)
+        self._ck(self.L.rt_camera_get_half(self._ctx, nx, ny, out.ctypes.data), "rt_camera_get_half")
+        return out
+
     # -- octree (main.cu:405-415) --
-    def build_octree(self, spheres_per_leaf: int = 30) -> dict:
+    def build_octree(self, spheres_per_leaf: int = 30, precision: int = PREC_FP32) -> dict:
         st = OctreeStats()
-        self._ck(self.L.rt_octree_build(self._ctx, spheres_per_leaf, C.byref(st)), "rt_octree_build")
+        self._ck(self.L.rt_octree_build_ex(self._ctx, spheres_per_leaf, precision, C.byref(st)), "rt_octree_build_ex")
         self.spl = spheres_per_leaf
         return st.as_dict()
 
@@ -234,7 +244,7 @@ class RayTracer:
 
     def debug_tree(self) -> dict:
         """Test hook: the internal traversal arrays as raw bytes."""
-        names = ["grid", "vox", "refs", "ent_off", "ent_cell", "big_refs", "sph_flag"]
+        names = ["grid", "vox", "refs", "ent_off", "ent_cell", "big_refs", "sph_flag", "cell_start", "cell_list"]
         out = {}
         for k, name in enumerate(names):
             n = self.L.rt_octree_debug_read(self._ctx, k, None, 0)
@@ -265,11 +275,10 @@ class RayTracer:
     # -- render (main.cu:424-429) --
     @staticmethod
     def args(nx, ny, ns, use_octree, max_depth=50, shard_mode=SHARD_NONE, shard_rank=0, shard_count=1,
-             seed_mode=SEED_HEAD, variant=0, max_rounds=0, tune=(0, 0)) -> RenderArgs:
-        a = RenderArgs(nx, ny, ns, max_depth, int(bool(use_octree)), seed_mode, shard_mode, shard_rank, shard_count)
-        a.reserved[3], a.reserved[4] = tune  # pool-kernel tuning knobs (0 = default)
-        a.reserved[2] = max_rounds           # pool-kernel watchdog (scheduling rounds per warp; 0 = off)
-        a.reserved[1] = variant              # kernel A/B knob (0 = default); every variant renders the same image
+             seed_mode=SEED_HEAD, precision=PREC_FP32, variant=0, max_rounds=0, tune=(0, 0)) -> RenderArgs:
+        a = RenderArgs(nx, ny, ns, max_depth, int(bool(use_octree)), seed_mode, shard_mode, shard_rank, shard_count, precision)
+        # kernel A/B and tuning knobs (0 = defaults); they never change the image
+        a.tune[1], a.tune[2], a.tune[3], a.tune[4] = variant, max_rounds, tune[0], tune[1]
         return a
 
     def render(self, nx, ny, ns, use_octree=True, **kw):

@@ -1,5 +1,6 @@
 // rt_abi.cu — implementation of the C ABI in include/rt_abi.h (context, scene, camera, build, render, output).
 // There is no CPU fallback anywhere in this library: every compute entry point launches CUDA kernels.
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdarg.h>
@@ -47,6 +48,14 @@ struct rt_context {
     size_t pinned_bytes = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     // RT_SEED_UPSTREAM: skip-ahead matrices (device copy) and the per-pixel stream states
+    // RT_PREC_FP16: the scene rounded to half (8 B geometry + 8 B material per sphere) and the half camera
+    uint2 *geom_h = nullptr, *matl_h = nullptr;
+    size_t half_cap = 0;
+    bool half_valid = false;
+    __half *cam_h = nullptr;
+    int cam_h_nx = 0, cam_h_ny = 0;
+    rt_camera_desc cam_desc{};
+    bool cam_desc_custom = false;
     uint32_t *skip_tables = nullptr;
     uint32_t *seed_states = nullptr;
     size_t seed_states_words = 0;
@@ -112,6 +121,7 @@ extern "C" void rt_destroy(rt_context *ctx) {
     cudaFree(ctx->geom); cudaFree(ctx->matl); cudaFree(ctx->tag); cudaFree(ctx->cam_dev);
     cudaFree(ctx->work_counter); cudaFree(ctx->counters); cudaFree(ctx->scratch_fb);
     cudaFree(ctx->skip_tables); cudaFree(ctx->seed_states);
+    cudaFree(ctx->geom_h); cudaFree(ctx->matl_h); cudaFree(ctx->cam_h);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -139,7 +149,13 @@ extern "C" int rt_device_info(const rt_context *ctx, int *sm_count, int *clock_k
 // main.cu:146-181.  The generator is one sequential XORWOW stream (seed 1984, curand_init(1984,0,0), main.cu:80),
 // so it runs on the host and the result is uploaded as SoA; arguments are drawn left to right as the device
 // evaluates them.  No device heap, no per-sphere `new`.
-static void generate_world(int n, float radius, std::vector<rt_sphere_desc> &out) {
+static inline float round_half(float x) { return __half2float(__float2half_rn(x)); }
+
+// fp16: the USE_FP16 build of create_world.  Every stored value goes through real_t(float|double), i.e. is rounded to
+// half; the one place where that changes the CONTROL flow is `const real_t choose_mat = RND` compared with
+// real_t(0.8f) / real_t(0.95f) (main.cu:165,168,172): a draw within half an ulp of a threshold picks another material,
+// which consumes a different number of draws and shifts every later sphere.
+static void generate_world(int n, float radius, bool fp16, std::vector<rt_sphere_desc> &out) {
     out.assign((size_t)n, rt_sphere_desc{0, 0, 0, 0, RT_MAT_NONE, 0, 0, 0, 0});
     if (n < 4) return;
     xorwow rng;
@@ -154,17 +170,18 @@ static void generate_world(int n, float radius, std::vector<rt_sphere_desc> &out
     const double spacing = 20. / spheres_per_dim;              // main.cu:161
     for (double a = -10; a < 10; a += spacing) {
         for (double b = -10; b < 10 && i < n; b += spacing) {
-            const float choose_mat = RND();
+            const float choose_mat = fp16 ? round_half(RND()) : RND();
+            const float th_lambert = fp16 ? round_half(0.8f) : 0.8f, th_metal = fp16 ? round_half(0.95f) : 0.95f;
             rt_sphere_desc s{};
             s.cx = (float)(a + (double)RND());
             s.cy = radius;
             s.cz = (float)(b + (double)RND());
             s.radius = radius;
-            if (choose_mat < 0.8f) {
+            if (choose_mat < th_lambert) {
                 s.mat = RT_MAT_LAMBERTIAN;
                 const float q0 = RND(), q1 = RND(), q2 = RND(), q3 = RND(), q4 = RND(), q5 = RND();
                 s.ax = q0 * q1; s.ay = q2 * q3; s.az = q4 * q5;
-            } else if (choose_mat < 0.95f) {
+            } else if (choose_mat < th_metal) {
                 s.mat = RT_MAT_METAL;
                 const float q0 = RND(), q1 = RND(), q2 = RND(), q3 = RND();
                 s.ax = 0.5f * (1.0f + q0); s.ay = 0.5f * (1.0f + q1); s.az = 0.5f * (1.0f + q2);
@@ -177,6 +194,11 @@ static void generate_world(int n, float radius, std::vector<rt_sphere_desc> &out
             out[i++] = s;
         }
     }
+    if (fp16)
+        for (auto &s : out) {
+            s.cx = round_half(s.cx); s.cy = round_half(s.cy); s.cz = round_half(s.cz); s.radius = round_half(s.radius);
+            s.ax = round_half(s.ax); s.ay = round_half(s.ay); s.az = round_half(s.az); s.param = round_half(s.param);
+        }
 }
 
 static int upload_scene(rt_context *ctx) {
@@ -205,11 +227,15 @@ static int upload_scene(rt_context *ctx) {
     return RT_OK;
 }
 
-extern "C" int rt_scene_generate(rt_context *ctx, int n, float radius) {
+extern "C" int rt_scene_generate(rt_context *ctx, int n, float radius) { return rt_scene_generate_ex(ctx, n, radius, RT_PREC_FP32); }
+
+extern "C" int rt_scene_generate_ex(rt_context *ctx, int n, float radius, int precision) {
     if (!ctx || n < 4) return fail(ctx, RT_ERR_INVALID, "rt_scene_generate: n must be >= 4");
+    if (precision != RT_PREC_FP32 && precision != RT_PREC_FP16) return fail(ctx, RT_ERR_INVALID, "rt_scene_generate: unknown precision");
     CK(cudaSetDevice(ctx->device));
     ctx->n = n;
-    generate_world(n, radius, ctx->host_scene);
+    ctx->half_valid = false;          // the half copy of the scene (USE_FP16 path) is derived on demand
+    generate_world(n, radius, precision == RT_PREC_FP16, ctx->host_scene);
     return upload_scene(ctx);
 }
 
@@ -217,6 +243,7 @@ extern "C" int rt_scene_upload(rt_context *ctx, const rt_sphere_desc *spheres, i
     if (!ctx || !spheres || n < 1) return fail(ctx, RT_ERR_INVALID, "rt_scene_upload: bad arguments");
     CK(cudaSetDevice(ctx->device));
     ctx->n = n;
+    ctx->half_valid = false;          // the half copy of the scene (USE_FP16 path) is derived on demand
     ctx->host_scene.assign(spheres, spheres + n);
     for (auto &s : ctx->host_scene)
         if (s.mat == RT_MAT_METAL && !(s.param < 1.0f)) s.param = 1.0f;   // metal::metal clamps fuzz (material.h:67)
@@ -286,6 +313,9 @@ extern "C" int rt_camera_set(rt_context *ctx, const rt_camera_desc *desc, int nx
         c.aperture = 0.1f;
         c.focus_dist = 10.0f;
     }
+    ctx->cam_desc = c;
+    ctx->cam_desc_custom = desc != nullptr;
+    ctx->cam_h_nx = ctx->cam_h_ny = 0;          // the half camera is derived on demand
     k_camera_setup<<<1, 1, 0, ctx->stream>>>(c, ctx->cam_dev);
     CK(cudaGetLastError());
     CK(upload_camera_from_device(ctx->cam_dev, ctx->stream));
@@ -302,13 +332,43 @@ extern "C" int rt_camera_get(rt_context *ctx, float out22[22]) {
     return RT_OK;
 }
 
+static int ensure_half_camera(rt_context *ctx, int nx, int ny) {
+    if (!ctx->have_camera) {
+        const int rc = rt_camera_set(ctx, nullptr, nx, ny);
+        if (rc) return rc;
+    }
+    if (!ctx->cam_h) CK(cudaMalloc(&ctx->cam_h, 22 * sizeof(__half)));
+    if (ctx->cam_h_nx != nx || ctx->cam_h_ny != ny) {
+        const rt_camera_desc &c = ctx->cam_desc;
+        CK(launch_camera_setup_half(c.lookfrom, c.lookat, c.vup, c.vfov, nx, ny, ctx->cam_desc_custom ? c.aspect : 0.f, c.aperture,
+                                    c.focus_dist, ctx->cam_h, ctx->stream));
+        ctx->cam_h_nx = nx; ctx->cam_h_ny = ny;
+    }
+    return RT_OK;
+}
+
+extern "C" int rt_camera_get_half(rt_context *ctx, int nx, int ny, float out22[22]) {
+    if (!ctx || !out22 || nx < 1 || ny < 1) return fail(ctx, RT_ERR_INVALID, "rt_camera_get_half: bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    const int rc = ensure_half_camera(ctx, nx, ny);
+    if (rc) return rc;
+    __half h[22];
+    CK(cudaMemcpyAsync(h, ctx->cam_h, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (int k = 0; k < 22; k++) out22[k] = __half2float(h[k]);
+    return RT_OK;
+}
+
 // ---- octree -----------------------------------------------------------------------------------------------------
-extern "C" int rt_octree_build(rt_context *ctx, int spl, rt_octree_stats *stats) {
+extern "C" int rt_octree_build(rt_context *ctx, int spl, rt_octree_stats *stats) { return rt_octree_build_ex(ctx, spl, RT_PREC_FP32, stats); }
+
+extern "C" int rt_octree_build_ex(rt_context *ctx, int spl, int precision, rt_octree_stats *stats) {
     if (!ctx || spl < 1) return fail(ctx, RT_ERR_INVALID, "rt_octree_build: SPHERES_PER_LEAF must be >= 1");
+    if (precision != RT_PREC_FP32 && precision != RT_PREC_FP16) return fail(ctx, RT_ERR_INVALID, "rt_octree_build: unknown precision");
     if (ctx->n < 1) return fail(ctx, RT_ERR_STATE, "rt_octree_build: no scene");
     CK(cudaSetDevice(ctx->device));
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
-    CK(ctx->octree->build(ctx->stream, ctx->geom, ctx->tag, ctx->n, spl, ctx->grid_density));
+    CK(ctx->octree->build(ctx->stream, ctx->geom, ctx->tag, ctx->n, spl, ctx->grid_density, precision == RT_PREC_FP16));
     CK(cudaEventRecord(ctx->ev1, ctx->stream));
     CK(cudaEventSynchronize(ctx->ev1));
     if (stats) {
@@ -332,6 +392,8 @@ extern "C" size_t rt_octree_reference_bytes(int spl) { return OctreeBuilder::ref
 extern "C" int rt_octree_export_reference(rt_context *ctx, void *host_blob, size_t bytes) {
     if (!ctx || !host_blob) return RT_ERR_INVALID;
     if (!ctx->octree->built) return fail(ctx, RT_ERR_STATE, "rt_octree_export_reference: build the octree first");
+    if (ctx->octree->fp16)
+        return fail(ctx, RT_ERR_UNSUPPORTED, "rt_octree_export_reference: the USE_FP16 Octree layout (48-byte nodes) is not exported");
     CK(cudaSetDevice(ctx->device));
     CK(ctx->octree->export_reference(ctx->stream, host_blob, bytes));
     return RT_OK;
@@ -350,6 +412,12 @@ static int do_render(rt_context *ctx, const rt_render_args *a, float *out_dev, b
     if (ctx->n < 1) return fail(ctx, RT_ERR_STATE, "render: no scene (rt_scene_generate / rt_scene_upload first)");
     if (a->use_octree && !ctx->octree->built) return fail(ctx, RT_ERR_STATE, "render: USE_OCTREE set but no octree built");
     if (a->seed_mode != RT_SEED_HEAD && a->seed_mode != RT_SEED_UPSTREAM) return fail(ctx, RT_ERR_INVALID, "render: unknown seed_mode");
+    if (a->precision != RT_PREC_FP32 && a->precision != RT_PREC_FP16) return fail(ctx, RT_ERR_INVALID, "render: unknown precision");
+    const bool fp16 = a->precision == RT_PREC_FP16;
+    if (fp16 && a->shard_mode != RT_SHARD_NONE)
+        return fail(ctx, RT_ERR_UNSUPPORTED, "render: USE_FP16 frames are rendered whole (RT_SHARD_NONE): the half accumulator does not split");
+    if (a->use_octree && ctx->octree->built && ctx->octree->fp16 != fp16)
+        return fail(ctx, RT_ERR_STATE, "render: the octree was built for the other precision (rt_octree_build_ex)");
     CK(cudaSetDevice(ctx->device));
     if (!ctx->have_camera || ctx->cam_nx != a->nx || ctx->cam_ny != a->ny) {
         const int rc = rt_camera_set(ctx, nullptr, a->nx, a->ny);
@@ -392,10 +460,10 @@ static int do_render(rt_context *ctx, const rt_render_args *a, float *out_dev, b
     if (owned * 32 > 0xfffffff0ll) return fail(ctx, RT_ERR_INVALID, "render: image too large for the 32-bit work queue");
     p.total_items = (uint32_t)(owned * 32);
     p.finalize = finalize ? 1 : 0;
-    p.variant = a->reserved[1] ? a->reserved[1] : ctx->default_variant;
-    p.tune_sticky = a->reserved[3] > 0 ? a->reserved[3] : 4;
-    p.tune_sticky_min = a->reserved[4] > 0 ? a->reserved[4] : 8;
-    p.max_rounds = a->reserved[2] > 0 ? (uint32_t)a->reserved[2] : 0x7fffffffu;            // A/B measurement knob; every variant renders the same image
+    p.variant = a->tune[1] ? a->tune[1] : ctx->default_variant;
+    p.tune_sticky = a->tune[3] > 0 ? a->tune[3] : 4;
+    p.tune_sticky_min = a->tune[4] > 0 ? a->tune[4] : 8;
+    p.max_rounds = a->tune[2] > 0 ? (uint32_t)a->tune[2] : 0x7fffffffu;            // A/B measurement knob; every variant renders the same image
     p.out = out_dev;
     p.work_counter = ctx->work_counter;
     p.counters = ctx->counters;
@@ -423,7 +491,27 @@ static int do_render(rt_context *ctx, const rt_render_args *a, float *out_dev, b
         CK(launch_seed_upstream(ctx->seed_states, (size_t)a->nx * a->ny, 1984ull, p.seed_offset, ctx->skip_tables, ctx->stream));
         launches = 2;
     }
-    CK(launch_render(p, a->use_octree != 0, ctx->prop.multiProcessorCount, ctx->prop.sharedMemPerBlockOptin, ctx->stream, &blocks));
+    if (fp16) {
+        if (ctx->half_cap < (size_t)ctx->n) {
+            cudaFree(ctx->geom_h); cudaFree(ctx->matl_h);
+            ctx->geom_h = ctx->matl_h = nullptr; ctx->half_cap = 0;
+            CK(cudaMalloc(&ctx->geom_h, (size_t)ctx->n * sizeof(uint2)));
+            CK(cudaMalloc(&ctx->matl_h, (size_t)ctx->n * sizeof(uint2)));
+            ctx->half_cap = (size_t)ctx->n;
+            ctx->half_valid = false;
+        }
+        if (!ctx->half_valid) {
+            CK(launch_scene_to_half(ctx->geom, ctx->matl, ctx->n, ctx->geom_h, ctx->matl_h, ctx->stream));
+            ctx->half_valid = true;
+        }
+        {
+            const int rc = ensure_half_camera(ctx, a->nx, a->ny);
+            if (rc) return rc;
+        }
+        CK(launch_render_half(p, a->use_octree != 0, ctx->geom_h, ctx->matl_h, ctx->cam_h, ctx->prop.multiProcessorCount, ctx->stream, &blocks));
+    } else {
+        CK(launch_render(p, a->use_octree != 0, ctx->prop.multiProcessorCount, ctx->prop.sharedMemPerBlockOptin, ctx->stream, &blocks));
+    }
     CK(cudaEventRecord(ctx->ev1, ctx->stream));
     if (stats) {
         unsigned long long c[8] = {0, 0, 0, 0, 0, 0, 0, 0};

@@ -1,0 +1,314 @@
+// rt_half.cuh — the USE_FP16 build of the reference (precision_types.h:8), per-lane device code.
+//
+// With USE_FP16 the reference's real_t is a struct around __half (precision_types.h:16-163): every vec3 / ray / sphere /
+// material operation rounds to half, EXCEPT where C++ overload resolution quietly falls back to float — unary minus,
+// `sqrt(x)` (float sqrtf), `pow`, `1.0/t`, float-literal-on-the-left expressions — and where the CUDA half intrinsics are
+// themselves approximate (__hdiv = rcp.approx * x with a fix-up for tiny quotients, hsqrt / hrsqrt = MUFU on float).
+// This file states that arithmetic explicitly, operation by operation.  Where each expression lands (half or float,
+// fused or not) was read off the SASS of the reference headers compiled with -DUSE_FP16 for sm_100 (small probe kernels
+// around sphere::hit, reflect, refract, scatter, get_ray, color's sky branch, render's pixel arithmetic):
+//   * half multiply-adds are contracted exactly like the float ones: a*b+c*d -> fma(a,b,c*d),
+//     x-a*b -> fma(-a,b,x), dot -> fma(z,z',fma(x,x',y*y'));
+//   * sphere::hit's two roots are FLOAT expressions of half inputs: (-b - hsqrt(disc)) / a and (-b + sqrtf(disc)) / a
+//     with IEEE float division, rounded to half on assignment (sphere.h:25,36);
+//   * length() = half(sqrtf(float(dot))) (vec3.h:34), v / length() uses __hdiv (vec3.h:146);
+//   * the ground sphere (radius 1000) overflows: r*r = 1e6 > 65504 -> c = inf -> discriminant -inf/NaN -> never hit
+//     (SURVEY D9): the FP16 image has no ground, by construction, here as there.
+// The same intrinsics are used as in the reference build (__hdiv, hsqrt, hrsqrt, hsin, hcos), so their approximation
+// errors are reproduced rather than modelled.  Vector operations are packed: (x, y) in one __half2, z separate —
+// per-lane rounding of the packed instructions is identical to the scalar ones.
+#pragma once
+#include <cuda_fp16.h>
+
+#include "rt_math.cuh"
+#include "rt_types.h"
+
+namespace rt {
+namespace h16 {
+
+typedef __half hf;
+
+__device__ __forceinline__ hf f2h(float f) { return __float2half_rn(f); }
+__device__ __forceinline__ float h2f(hf h) { return __half2float(h); }
+__device__ __forceinline__ hf hfma_(hf a, hf b, hf c) { return __hfma(a, b, c); }
+__device__ __forceinline__ hf hmul_(hf a, hf b) { return __hmul_rn(a, b); }
+__device__ __forceinline__ hf hadd_(hf a, hf b) { return __hadd_rn(a, b); }
+__device__ __forceinline__ hf hsub_(hf a, hf b) { return __hsub_rn(a, b); }
+__device__ __forceinline__ hf hdiv_(hf a, hf b) { return __hdiv(a, b); }                 // real_t::operator/ (precision_types.h:56-63)
+__device__ __forceinline__ hf hsqrtf_(hf a) { return f2h(__fsqrt_rn(h2f(a))); }          // sqrt(real_t) -> float sqrtf -> real_t
+__device__ __forceinline__ hf hneg_(hf a) { return __hneg(a); }
+
+struct vec3h {
+    __half2 xy;
+    hf z;
+};
+__device__ __forceinline__ vec3h mkh(hf x, hf y, hf z) { vec3h v; v.xy = __halves2half2(x, y); v.z = z; return v; }
+__device__ __forceinline__ vec3h mkh_f(float x, float y, float z) { return mkh(f2h(x), f2h(y), f2h(z)); }
+__device__ __forceinline__ hf vx(const vec3h v) { return __low2half(v.xy); }
+__device__ __forceinline__ hf vy(const vec3h v) { return __high2half(v.xy); }
+__device__ __forceinline__ vec3h vsub(const vec3h a, const vec3h b) { vec3h r; r.xy = __hsub2_rn(a.xy, b.xy); r.z = hsub_(a.z, b.z); return r; }
+__device__ __forceinline__ vec3h vadd(const vec3h a, const vec3h b) { vec3h r; r.xy = __hadd2_rn(a.xy, b.xy); r.z = hadd_(a.z, b.z); return r; }
+__device__ __forceinline__ vec3h vmul(const vec3h a, const vec3h b) { vec3h r; r.xy = __hmul2_rn(a.xy, b.xy); r.z = hmul_(a.z, b.z); return r; }
+__device__ __forceinline__ vec3h vscale(const hf t, const vec3h a) { vec3h r; r.xy = __hmul2_rn(__half2half2(t), a.xy); r.z = hmul_(t, a.z); return r; }
+// a * t + c per component
+__device__ __forceinline__ vec3h vfma(const vec3h a, const hf t, const vec3h c) { vec3h r; r.xy = __hfma2(a.xy, __half2half2(t), c.xy); r.z = hfma_(a.z, t, c.z); return r; }
+__device__ __forceinline__ vec3h vneg(const vec3h a) { vec3h r; r.xy = __hneg2(a.xy); r.z = hneg_(a.z); return r; }
+
+// vec3.h:91-93 dot(): fma(z,z', fma(x,x', y*y'))
+__device__ __forceinline__ hf dot3h(const vec3h a, const vec3h b) { return hfma_(a.z, b.z, hfma_(vx(a), vx(b), hmul_(vy(a), vy(b)))); }
+// vec3.h:34 length(): the squares in half, the root in float
+__device__ __forceinline__ hf lengthh(const vec3h v) { return hsqrtf_(dot3h(v, v)); }
+// vec3.h:146-148 unit_vector(): v / v.length(), three __hdiv
+__device__ __forceinline__ vec3h unit_vectorh(const vec3h v) {
+    const hf len = lengthh(v);
+    return mkh(hdiv_(vx(v), len), hdiv_(vy(v), len), hdiv_(v.z, len));
+}
+
+__device__ __forceinline__ hf uniform_h(xorwow &s) { return f2h(xorwow_uniform(s)); }   // curand_uniform() is float; real_t(float) rounds
+
+struct SphereH {            // one sphere in half: what the FP16 create_world stores (the FP32 scene rounded once)
+    vec3h c;
+    hf r;
+};
+__device__ __forceinline__ SphereH load_sphere_h(const uint2 *geom_h, int i) {
+    const uint2 u = __ldg(geom_h + i);
+    SphereH s;
+    s.c.xy = *reinterpret_cast<const __half2 *>(&u.x);
+    const __half2 zr = *reinterpret_cast<const __half2 *>(&u.y);
+    s.c.z = __low2half(zr);
+    s.r = __high2half(zr);
+    return s;
+}
+
+// sphere.h:17-46 under USE_FP16.  t_min = real_t(0.001f); returns true and the accepted root when t_min < t < t_max.
+__device__ __forceinline__ bool sphere_test_h(const SphereH s, const vec3h o, const vec3h d, const hf a, const hf t_max, hf &t_out) {
+    const vec3h oc = vsub(o, s.c);                                        // sphere.h:18
+    const hf b = dot3h(oc, d);                                            // :20
+    const hf c = hfma_(hneg_(s.r), s.r, dot3h(oc, oc));                   // :21
+    const hf disc = hfma_(b, b, hneg_(hmul_(a, c)));                      // :22
+    if (__hgt(disc, f2h(0.0f))) {
+        const float fb = h2f(b), fa = h2f(a);
+        const hf t_min = f2h(0.001f);
+        hf temp = f2h(__fdiv_rn(__fsub_rn(-fb, h2f(hsqrt(disc))), fa));   // :25  (-b - real_t::sqrt(disc)) / a  in float
+        if (__hlt(temp, t_max) && __hgt(temp, t_min)) { t_out = temp; return true; }
+        temp = f2h(__fdiv_rn(__fadd_rn(-fb, __fsqrt_rn(h2f(disc))), fa));  // :36  (-b + sqrt(disc)) / a        in float
+        if (__hlt(temp, t_max) && __hgt(temp, t_min)) { t_out = temp; return true; }
+    }
+    return false;
+}
+
+// sphere.h:30-33: p = A + t*B (fused), normal = (p - center) / radius (__hdiv)
+__device__ __forceinline__ void hit_point_h(const SphereH s, const vec3h o, const vec3h d, const hf t, vec3h &p, vec3h &n) {
+    p = vfma(d, t, o);
+    const vec3h pc = vsub(p, s.c);
+    n = mkh(hdiv_(vx(pc), s.r), hdiv_(vy(pc), s.r), hdiv_(pc.z, s.r));
+}
+
+// material.h:33-41: p = real_t(2)*RANDVEC3 - vec3(1,1,1) until squared_length() < 1
+__device__ __forceinline__ vec3h random_in_unit_sphere_h(xorwow &rng) {
+    vec3h p;
+    const hf two = f2h(2.0f), m1 = f2h(-1.0f);
+    do {
+        const hf u0 = uniform_h(rng), u1 = uniform_h(rng), u2 = uniform_h(rng);
+        p = mkh(hfma_(u0, two, m1), hfma_(u1, two, m1), hfma_(u2, two, m1));
+    } while (__hge(dot3h(p, p), f2h(1.0f)));
+    return p;
+}
+
+// material.h:43-45 reflect: v - real_t(2)*dot(v,n)*n
+__device__ __forceinline__ vec3h reflect_h(const vec3h v, const vec3h n) {
+    const hf d2 = hmul_(dot3h(v, n), f2h(2.0f));
+    return vfma(n, hneg_(d2), v);
+}
+
+// material.h:17-31 refract
+__device__ __forceinline__ bool refract_h(const vec3h v, const vec3h n, const hf ni_over_nt, vec3h &refracted) {
+    const vec3h uv = unit_vectorh(v);
+    const hf dt = dot3h(uv, n);
+    const hf one = f2h(1.0f);
+    const hf disc = hfma_(hneg_(hmul_(ni_over_nt, ni_over_nt)), hfma_(hneg_(dt), dt, one), one);
+    if (__hgt(disc, f2h(0.0f))) {
+        const hf sq = hsqrt(disc);                                           // real_t::sqrt -> hsqrt (:24)
+        const vec3h inner = vfma(n, hneg_(dt), uv);                          // uv - n*dt
+        // ni*(uv - n*dt) - n*sq: here ptxas fuses the LEFT product, fma(inner, ni, -(sq*n)) (FP32 fuses the right one)
+        const vec3h nsq = vscale(sq, n);
+        refracted = vfma(inner, ni_over_nt, vneg(nsq));
+        return true;
+    }
+    return false;
+}
+
+// material.h:11-15 schlick: (1 -/+ ref_idx) and pow() are float, the rest half
+__device__ __forceinline__ hf schlick_h(const hf cosine, const hf ref_idx) {
+    hf r0 = hdiv_(f2h(1.0f - h2f(ref_idx)), f2h(1.0f + h2f(ref_idx)));
+    r0 = hmul_(r0, r0);
+    return hfma_(f2h(1.0f - h2f(r0)), f2h(powf(1.0f - h2f(cosine), 5.0f)), r0);
+}
+
+struct MatH {
+    vec3h albedo;
+    hf param;       // metal: fuzz (clamped to <= 1 by metal::metal, material.h:66); dielectric: ref_idx
+};
+__device__ __forceinline__ MatH load_mat_h(const uint2 *matl_h, int i) {
+    const uint2 u = __ldg(matl_h + i);
+    MatH m;
+    m.albedo.xy = *reinterpret_cast<const __half2 *>(&u.x);
+    const __half2 zp = *reinterpret_cast<const __half2 *>(&u.y);
+    m.albedo.z = __low2half(zp);
+    m.param = __high2half(zp);
+    return m;
+}
+
+// material.h:55-60 / :68-73 / :81-113 under USE_FP16; returns false when the ray is absorbed (metal only)
+__device__ __forceinline__ bool scatter_h(const int tag, const MatH m, const vec3h d_in, const vec3h p, const vec3h n, vec3h &atten,
+                                          vec3h &d_out, xorwow &rng) {
+    if (tag == 0) {
+        const vec3h r = random_in_unit_sphere_h(rng);
+        const vec3h target = vadd(vadd(p, n), r);
+        d_out = vsub(target, p);
+        atten = m.albedo;
+        return true;
+    }
+    if (tag == 1) {
+        const vec3h refl = reflect_h(unit_vectorh(d_in), n);
+        const vec3h r = random_in_unit_sphere_h(rng);
+        d_out = vfma(r, m.param, refl);                                      // reflected + fuzz*r
+        atten = m.albedo;
+        return __hgt(dot3h(d_out, n), f2h(0.0f));
+    }
+    const hf ref_idx = m.param, one = f2h(1.0f);
+    const vec3h reflected = reflect_h(d_in, n);
+    vec3h outward, refracted = mkh_f(0.f, 0.f, 0.f);
+    hf ni_over_nt, cosine, reflect_prob;
+    atten = mkh(one, one, one);
+    const hf ddn = dot3h(d_in, n);
+    if (__hgt(ddn, f2h(0.0f))) {
+        outward = vneg(n);
+        ni_over_nt = ref_idx;
+        cosine = hdiv_(ddn, lengthh(d_in));                                                       // real_t / real_t (:92)
+        cosine = hsqrtf_(hfma_(hneg_(hmul_(ref_idx, ref_idx)), hfma_(hneg_(cosine), cosine, one), one));   // :93 sqrt() is float
+    } else {
+        outward = n;
+        ni_over_nt = hdiv_(one, ref_idx);
+        cosine = f2h(__fdiv_rn(-h2f(ddn), h2f(lengthh(d_in))));                                    // -dot is float, float / real_t is float (:98)
+    }
+    if (refract_h(d_in, outward, ni_over_nt, refracted)) reflect_prob = schlick_h(cosine, ref_idx);
+    else reflect_prob = one;
+    d_out = (xorwow_uniform(rng) < h2f(reflect_prob)) ? reflected : refracted;                    // float < real_t compares as float
+    return true;
+}
+
+struct CameraH {
+    vec3h origin, lower_left_corner, horizontal, vertical, u, v, w;
+    hf lens_radius;
+};
+
+// camera.h:12-18 + :45-49 under USE_FP16
+__device__ __forceinline__ void camera_ray_h(const CameraH &c, const hf s, const hf t, xorwow &rng, vec3h &o, vec3h &d) {
+    hf px, py;
+    const hf two = f2h(2.0f), m1 = f2h(-1.0f);
+    do {
+        const hf u0 = uniform_h(rng), u1 = uniform_h(rng);
+        px = hfma_(u0, two, m1);
+        py = hfma_(u1, two, m1);
+    } while (__hge(hfma_(px, px, hmul_(py, py)), f2h(1.0f)));       // dot(p,p) with p.z = 0: the z term adds an exact zero
+    const hf rdx = hmul_(c.lens_radius, px), rdy = hmul_(c.lens_radius, py);
+    const vec3h off = vfma(c.u, rdx, vscale(rdy, c.v));            // u*rd.x + v*rd.y
+    o = vadd(c.origin, off);
+    d = vsub(vsub(vfma(c.vertical, t, vfma(c.horizontal, s, c.lower_left_corner)), c.origin), off);
+}
+
+// main.cu:68-71 under USE_FP16: (1.0f - t) is a float subtraction rounded to half
+__device__ __forceinline__ vec3h sky_h(const vec3h d) {
+    const vec3h ud = unit_vectorh(d);
+    const hf t = hmul_(hadd_(vy(ud), f2h(1.0f)), f2h(0.5f));
+    const hf omt = f2h(1.0f - h2f(t));
+    return mkh(hfma_(t, f2h(0.5f), omt), hfma_(t, f2h(0.7f), omt), hadd_(omt, t));
+}
+
+// acceleration_structure.h:226-244 under USE_FP16: AABB members, ray origin and direction are real_t, so every slab
+// parameter is (half - half) / half with __hdiv, widened to float only for the comparisons
+__device__ __forceinline__ bool ref_line_test_h(const vec3h o, const vec3h d, const hf xl, const hf yl, const hf zl, const hf xh,
+                                                const hf yh, const hf zh) {
+    float tmin = h2f(hdiv_(hsub_(xl, vx(o)), vx(d))), tmax = h2f(hdiv_(hsub_(xh, vx(o)), vx(d)));
+    if (tmin > tmax) { const float t = tmin; tmin = tmax; tmax = t; }
+    float tymin = h2f(hdiv_(hsub_(yl, vy(o)), vy(d))), tymax = h2f(hdiv_(hsub_(yh, vy(o)), vy(d)));
+    if (tymin > tymax) { const float t = tymin; tymin = tymax; tymax = t; }
+    if ((tmin > tymax) || (tymin > tmax)) return false;
+    if (tymin > tmin) tmin = tymin;
+    if (tymax < tmax) tmax = tymax;
+    float tzmin = h2f(hdiv_(hsub_(zl, o.z), d.z)), tzmax = h2f(hdiv_(hsub_(zh, o.z), d.z));
+    if (tzmin > tzmax) { const float t = tzmin; tzmin = tzmax; tzmax = t; }
+    if ((tmin > tzmax) || (tzmin > tmax)) return false;
+    return true;
+}
+
+struct HitH {
+    hf t;
+    int idx;
+};
+
+// hitable_list.h:16-31 under USE_FP16.  Exact ties between different spheres are COMMON in half (11 significant bits),
+// so the test order is part of the result: ascending index, strict '<', as in the reference.
+__device__ __forceinline__ HitH trace_list_h(const uint2 *geom_h, const int *tag, const int n, const vec3h o, const vec3h d) {
+    HitH h;
+    h.t = f2h(3.402823466e+38f);          // real_t(FLT_MAX) = +inf
+    h.idx = -1;
+    const hf a = dot3h(d, d);
+    for (int i = 0; i < n; i++) {
+        hf t;
+        if (sphere_test_h(load_sphere_h(geom_h, i), o, d, a, h.t, t) && __ldg(tag + i) >= 0) { h.t = t; h.idx = i; }
+    }
+    return h;
+}
+
+// acceleration_structure.h:276-342 under USE_FP16: ground sphere first, then the tree in the reference's own order —
+// children by octant index at every level (= ascending Morton code), the stored list of each level-3 cell in
+// insertion (= ascending sphere index) order — with the half-precision line test at EVERY level (approximate __hdiv is
+// not monotone, so a child's pass does not imply its parent's).  No sub-grid here: in half arithmetic a sphere can
+// "hit" far from where it is, so every sphere of a passing cell is a real candidate, exactly as in the reference.
+__device__ __forceinline__ HitH trace_tree_h(const uint2 *geom_h, const int *tag, const TreeView &tv, const vec3h o, const vec3h d) {
+    HitH h;
+    h.t = f2h(3.402823466e+38f);
+    h.idx = -1;
+    const hf a = dot3h(d, d);
+    {
+        hf t;
+        if (sphere_test_h(load_sphere_h(geom_h, 0), o, d, a, h.t, t)) { h.t = t; h.idx = 0; }     // :322-332
+    }
+    const float *P = &tv.planes[0][0];
+    auto box_pass = [&](int level, int ix, int iy, int iz) {
+        const int sh = 3 - level;
+        return ref_line_test_h(o, d, f2h(P[ix << sh]), f2h(P[kPlanes + (iy << sh)]), f2h(P[2 * kPlanes + (iz << sh)]),
+                               f2h(P[(ix + 1) << sh]), f2h(P[kPlanes + ((iy + 1) << sh)]), f2h(P[2 * kPlanes + ((iz + 1) << sh)]));
+    };
+    const uint32_t *cs = tv.cell_start;
+    if (__ldg(cs + kCells) == 0u || !box_pass(0, 0, 0, 0)) return h;
+    for (int c1 = 0; c1 < 8; c1++) {
+        if (__ldg(cs + c1 * 64 + 64) == __ldg(cs + c1 * 64)) continue;                  // child node never created
+        const int x1 = c1 >> 2, y1 = (c1 >> 1) & 1, z1 = c1 & 1;
+        if (!box_pass(1, x1, y1, z1)) continue;
+        for (int c2 = 0; c2 < 8; c2++) {
+            const int m2 = c1 * 8 + c2;
+            if (__ldg(cs + m2 * 8 + 8) == __ldg(cs + m2 * 8)) continue;
+            const int x2 = x1 * 2 + (c2 >> 2), y2 = y1 * 2 + ((c2 >> 1) & 1), z2 = z1 * 2 + (c2 & 1);
+            if (!box_pass(2, x2, y2, z2)) continue;
+            for (int c3 = 0; c3 < 8; c3++) {
+                const int m3 = m2 * 8 + c3;
+                const uint32_t b = __ldg(cs + m3), e_all = __ldg(cs + m3 + 1);
+                if (e_all == b) continue;
+                if (!box_pass(3, x2 * 2 + (c3 >> 2), y2 * 2 + ((c3 >> 1) & 1), z2 * 2 + (c3 & 1))) continue;
+                const uint32_t e = min(e_all, b + (uint32_t)tv.cell_cap);                 // entries beyond 8*SPL were dropped (:135)
+                for (uint32_t k = b; k < e; k++) {
+                    const int idx = (int)__ldg(tv.cell_list + k);
+                    hf t;
+                    if (sphere_test_h(load_sphere_h(geom_h, idx), o, d, a, h.t, t) && __ldg(tag + idx) >= 0) { h.t = t; h.idx = idx; }
+                }
+            }
+        }
+    }
+    return h;
+}
+
+}  // namespace h16
+}  // namespace rt

@@ -16,6 +16,7 @@
 // CUB (shipped inside the CUDA toolkit, header-only) provides the device-wide scan and radix sort; everything
 // else is hand-written.
 #include <cub/cub.cuh>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <limits.h>
 #include <stdio.h>
@@ -34,8 +35,22 @@ namespace rt {
         if (e_ != cudaSuccess) return e_;   \
     } while (0)
 
+// acceleration_structure.h:82-93 along one axis under USE_FP16: centre, radius and box are halves, the grown bounds round to half
+__device__ __forceinline__ AxisRange axis_range_h(const float *P, float c, float r, bool open_low) {
+    AxisRange a;
+    a.lo = 8; a.hi = -1;
+    const __half ch = __float2half_rn(c), rh = __float2half_rn(r);
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const __half low = __hsub_rn(__float2half_rn(P[i]), rh), high = __hadd_rn(__float2half_rn(P[i + 1]), rh);
+        const bool in = (open_low ? __hgt(ch, low) : __hge(ch, low)) && __hle(ch, high);
+        if (in) { a.lo = imin(a.lo, i); a.hi = imax(a.hi, i); }
+    }
+    return a;
+}
+
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void k_classify(const float4 *__restrict__ geom, int n, BuildPlanes P, uint32_t *__restrict__ ranges,
+__global__ void k_classify(const float4 *__restrict__ geom, int n, BuildPlanes P, int fp16, uint32_t *__restrict__ ranges,
                            uint32_t *__restrict__ ent_count, uint32_t *__restrict__ cell_count,
                            unsigned long long *__restrict__ dropped_outside) {
     __shared__ uint32_t hist[kCells];
@@ -46,9 +61,11 @@ __global__ void k_classify(const float4 *__restrict__ geom, int n, BuildPlanes P
         uint32_t packed = 0, cnt = 0;
         if (i >= 1) {   // ground sphere (index 0) is never inserted (acceleration_structure.h:208)
             const float4 s = geom[i];
-            const AxisRange rx = axis_range(P.p[0], s.x, s.w, true);
-            const AxisRange ry = axis_range(P.p[1], s.y, s.w, false);
-            const AxisRange rz = axis_range(P.p[2], s.z, s.w, false);
+            // USE_FP16: AABB, centre and radius are real_t, so `low - radius` / `high + radius` round to half
+            // (acceleration_structure.h:83-88); the planes themselves are exact in half
+            const AxisRange rx = fp16 ? axis_range_h(P.p[0], s.x, s.w, true) : axis_range(P.p[0], s.x, s.w, true);
+            const AxisRange ry = fp16 ? axis_range_h(P.p[1], s.y, s.w, false) : axis_range(P.p[1], s.y, s.w, false);
+            const AxisRange rz = fp16 ? axis_range_h(P.p[2], s.z, s.w, false) : axis_range(P.p[2], s.z, s.w, false);
             if (rx.lo <= rx.hi && ry.lo <= ry.hi && rz.lo <= rz.hi) {
                 cnt = (uint32_t)((rx.hi - rx.lo + 1) * (ry.hi - ry.lo + 1) * (rz.hi - rz.lo + 1));
                 packed = 1u << 31 | rx.lo | rx.hi << 4 | ry.lo << 8 | ry.hi << 12 | rz.lo << 16 | rz.hi << 20;
@@ -367,8 +384,9 @@ OctreeBuilder::~OctreeBuilder() {
     for (void *p : ptrs) if (p) cudaFree(p);
 }
 
-cudaError_t OctreeBuilder::build(cudaStream_t st, const float4 *geom, const int *tag, int n, int spl_, float density) {
+cudaError_t OctreeBuilder::build(cudaStream_t st, const float4 *geom, const int *tag, int n, int spl_, float density, bool fp16_) {
     spl = spl_;
+    fp16 = fp16_;
     built = false;
     blob_valid = false;
     RT_CUDA(ensure(d.ranges, cap.ranges, (size_t)n + 1));
@@ -390,7 +408,7 @@ cudaError_t OctreeBuilder::build(cudaStream_t st, const float4 *geom, const int 
     RT_CUDA(cudaMemsetAsync(d.ent_count + n, 0, 4, st));
     RT_CUDA(cudaMemsetAsync(d.sph_flag, 0, (size_t)n + 1, st));
     const int tb = 256;
-    k_classify<<<(n + tb - 1) / tb, tb, 0, st>>>(geom, n, planes, d.ranges, d.ent_count, d.cell_count, d.stats + 2);
+    k_classify<<<(n + tb - 1) / tb, tb, 0, st>>>(geom, n, planes, fp16 ? 1 : 0, d.ranges, d.ent_count, d.cell_count, d.stats + 2);
     size_t tmp = 0;
     cub::DeviceScan::ExclusiveSum(nullptr, tmp, d.ent_count, d.ent_off, n + 1, st);
     RT_CUDA(ensure(d.cub_tmp, cap.cub, tmp));
@@ -513,6 +531,8 @@ size_t OctreeBuilder::debug_read(cudaStream_t st, int which, void *host, size_t 
         case 4: src = d.ent_cell; bytes = (size_t)E * 2; break;
         case 5: src = d.big_refs + 1; bytes = (size_t)nbig * 4; break;
         case 6: src = d.sph_flag; bytes = (size_t)n_spheres; break;
+        case 7: src = d.cell_start; bytes = (size_t)(kCells + 1) * 4; break;
+        case 8: src = d.vals_sorted; bytes = (size_t)E * 4; break;
         default: return 0;
     }
     if (!host) return bytes;
@@ -528,6 +548,9 @@ TreeView OctreeBuilder::view() const {
     v.grid = grid;
     v.vis.ent_off = d.ent_off;
     v.vis.ent_cell = d.ent_cell;
+    v.cell_list = d.vals_sorted;
+    v.cell_start = d.cell_start;
+    v.cell_cap = 8 * spl;
     v.prolog = d.big_refs;
     v.nprolog = 1 + nbig;
     for (int a = 0; a < 3; a++) for (int i = 0; i < kPlanes; i++) v.planes[a][i] = planes.p[a][i];

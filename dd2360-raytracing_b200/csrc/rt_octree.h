@@ -28,7 +28,8 @@ public:
     OctreeBuilder &operator=(const OctreeBuilder &) = delete;
 
     // replaces D2H(spheres) + buildOctree + H2D(Octree), main.cu:405-415
-    cudaError_t build(cudaStream_t st, const float4 *geom, const int *tag, int n, int spl, float density);
+    // fp16: the USE_FP16 build of the reference (half-rounded scene, half arithmetic in `intersects`)
+    cudaError_t build(cudaStream_t st, const float4 *geom, const int *tag, int n, int spl, float density, bool fp16 = false);
     static size_t reference_bytes(int spl);
     // the tree in the reference's own layout (acceleration_structure.h:23-61), assembled on the GPU on demand
     cudaError_t export_reference(cudaStream_t st, void *host_blob, size_t bytes);
@@ -38,7 +39,7 @@ public:
     // host == nullptr
     size_t debug_read(cudaStream_t st, int which, void *host, size_t cap) const;
 
-    bool built = false, blob_valid = false;
+    bool built = false, blob_valid = false, fp16 = false;
     int spl = 0, n_spheres = 0, leaf_count_h = 0;
     int nbig = 0;
     uint32_t prolog_h[kMaxBig + 1];   // staging for the async upload (must outlive build())

@@ -18,6 +18,7 @@
 #include <stdint.h>
 
 #include "rt_render.h"
+#include "rt_half.cuh"
 #include "rt_trace.cuh"
 #include "rt_xorwow_skip.h"
 
@@ -258,6 +259,24 @@ namespace rt {
 #include "rt_pool.cuh"
 }  // namespace rt
 namespace rt {
+
+#include "rt_render_half.cuh"
+
+cudaError_t launch_scene_to_half(const float4 *geom, const float4 *matl, int n, uint2 *geom_h, uint2 *matl_h, cudaStream_t st) {
+    h16::k_scene_to_half<<<(n + 255) / 256, 256, 0, st>>>(geom, matl, n, geom_h, matl_h);
+    return cudaGetLastError();
+}
+cudaError_t launch_camera_setup_half(const float lookfrom[3], const float lookat[3], const float vup[3], float vfov, int nx, int ny,
+                                     float aspect_override, float aperture, float focus_dist, __half *cam_h, cudaStream_t st) {
+    h16::k_camera_setup_h<<<1, 1, 0, st>>>(lookfrom[0], lookfrom[1], lookfrom[2], lookat[0], lookat[1], lookat[2], vup[0], vup[1], vup[2],
+                                           vfov, nx, ny, aspect_override, aperture, focus_dist, cam_h);
+    return cudaGetLastError();
+}
+cudaError_t launch_render_half(const RenderLaunch &p, bool octree, const uint2 *geom_h, const uint2 *matl_h, const __half *cam_h,
+                               int sm_count, cudaStream_t st, int *blocks_out) {
+    return octree ? h16::launch_half<true>(p, geom_h, matl_h, cam_h, sm_count, st, blocks_out)
+                  : h16::launch_half<false>(p, geom_h, matl_h, cam_h, sm_count, st, blocks_out);
+}
 
 // Closest hit for caller-supplied rays (test hook: per-ray parity against the oracle's hitTree / hitable_list::hit)
 __global__ void k_trace_rays(const __grid_constant__ RenderLaunch p, int octree, const float *__restrict__ org,

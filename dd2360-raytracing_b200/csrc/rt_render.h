@@ -1,5 +1,6 @@
 // rt_render.h — launch interface of the persistent render kernel (rt_render.cu).
 #pragma once
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -40,6 +41,12 @@ cudaError_t launch_trace_rays(const RenderLaunch &p, bool octree, const float *o
 // render_init with the upstream seeding curand_init(1984, pixel_index + subsequence_base, 0) (main.cu:90)
 cudaError_t launch_seed_upstream(uint32_t *states, size_t npix, unsigned long long seed, unsigned long long subsequence_base,
                                  const uint32_t *tables, cudaStream_t st);
+// ---- USE_FP16 path (rt_render_half.cuh) ----
+cudaError_t launch_scene_to_half(const float4 *geom, const float4 *matl, int n, uint2 *geom_h, uint2 *matl_h, cudaStream_t st);
+cudaError_t launch_camera_setup_half(const float lookfrom[3], const float lookat[3], const float vup[3], float vfov, int nx, int ny,
+                                     float aspect_override, float aperture, float focus_dist, __half *cam_h, cudaStream_t st);
+cudaError_t launch_render_half(const RenderLaunch &p, bool octree, const uint2 *geom_h, const uint2 *matl_h, const __half *cam_h,
+                               int sm_count, cudaStream_t st, int *blocks_out);
 cudaError_t launch_finalize(const float *accum, float *fb, int nx, int ny, int ns, cudaStream_t st);
 
 }  // namespace rt

@@ -1,0 +1,190 @@
+// rt_render_half.cuh — the USE_FP16 render path (BASELINE config 4): render_init + render + color in half precision.
+// (included by rt_render.cu; arithmetic in rt_half.cuh)
+//
+// Same persistent, queue-fed kernel shape as k_render (one pixel chain per lane, ballot/popc-compacted claims), with the
+// per-lane state in half: ray, attenuation and — as in the reference, whose `vec3 col` is three halves (main.cu:101) —
+// the pixel accumulator.  Octree mode walks the reference's own cells (rt_half.cuh trace_tree_h): the sub-grid of the
+// FP32 path is built on float error bounds that half arithmetic does not honour.
+#pragma once
+// (rt_half.cuh is included by rt_render.cu at file scope)
+
+namespace h16 {
+
+// the FP16 create_world stores every centre, radius, albedo and parameter through real_t(float|double): the FP32 scene
+// rounded once to half (main.cu:160-181).  8 bytes per sphere for geometry, 8 for the material.
+__global__ void k_scene_to_half(const float4 *__restrict__ geom, const float4 *__restrict__ matl, int n, uint2 *__restrict__ geom_h,
+                                uint2 *__restrict__ matl_h) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 g = geom[i], m = matl[i];
+    __half2 a = __floats2half2_rn(g.x, g.y), b = __floats2half2_rn(g.z, g.w);
+    geom_h[i] = make_uint2(*reinterpret_cast<uint32_t *>(&a), *reinterpret_cast<uint32_t *>(&b));
+    a = __floats2half2_rn(m.x, m.y);
+    b = __floats2half2_rn(m.z, m.w);
+    matl_h[i] = make_uint2(*reinterpret_cast<uint32_t *>(&a), *reinterpret_cast<uint32_t *>(&b));
+}
+
+// vec3.h:95-99 cross(): a*b - c*d -> fma(a,b,-(c*d)); the middle component's unary minus goes through float
+__device__ __forceinline__ vec3h cross_h(const vec3h a, const vec3h b) {
+    const hf cx = hfma_(vy(a), b.z, hneg_(hmul_(a.z, vy(b))));
+    const hf cy = f2h(-h2f(hfma_(vx(a), b.z, hneg_(hmul_(a.z, vx(b))))));
+    const hf cz = hfma_(vx(a), vy(b), hneg_(hmul_(vy(a), vx(b))));
+    return mkh(cx, cy, cz);
+}
+
+// camera.h:22-44 under USE_FP16, evaluated on the device with the reference's own intrinsics (hsin / hcos / __hdiv);
+// nvcc does not fold half intrinsics, so unlike the FP32 camera nothing here is a compile-time constant.
+// out: 22 halves in CameraData order (origin, llc, horizontal, vertical, u, v, w, lens_radius).
+__global__ void k_camera_setup_h(const float lfx, const float lfy, const float lfz, const float lax, const float lay, const float laz,
+                                 const float upx, const float upy, const float upz, const float vfov_f, const int nx, const int ny,
+                                 const float aspect_override, const float aperture_f, const float focus_f, __half *__restrict__ out) {
+    const hf aperture = f2h(aperture_f), focus = f2h(focus_f), vfov = f2h(vfov_f);
+    const hf aspect = aspect_override > 0.f ? f2h(aspect_override) : hdiv_(f2h((float)nx), f2h((float)ny));   // real_t(nx) / real_t(ny), main.cu:199
+    const hf lens_radius = hdiv_(aperture, f2h(2.0f));
+    const hf theta = hdiv_(hmul_(vfov, f2h(3.14159265358979323846f)), f2h(180.0f));
+    const hf arg = hdiv_(theta, f2h(2.0f));
+    const hf half_height = hdiv_(hsin(arg), hcos(arg));
+    const hf half_width = hmul_(aspect, half_height);
+    const vec3h lookfrom = mkh_f(lfx, lfy, lfz), lookat = mkh_f(lax, lay, laz), vup = mkh_f(upx, upy, upz);
+    const vec3h w = unit_vectorh(vsub(lookfrom, lookat));
+    const vec3h u = unit_vectorh(cross_h(vup, w));
+    const vec3h v = cross_h(w, u);
+    const hf hwf = hmul_(half_width, focus), hhf = hmul_(half_height, focus);
+    const vec3h llc = vfma(w, hneg_(focus), vfma(v, hneg_(hhf), vfma(u, hneg_(hwf), lookfrom)));
+    const vec3h horizontal = vscale(hmul_(hmul_(f2h(2.0f), half_width), focus), u);
+    const vec3h vertical = vscale(hmul_(hmul_(f2h(2.0f), half_height), focus), v);
+    const vec3h all[7] = {lookfrom, llc, horizontal, vertical, u, v, w};
+    for (int k = 0; k < 7; k++) { out[3 * k] = vx(all[k]); out[3 * k + 1] = vy(all[k]); out[3 * k + 2] = all[k].z; }
+    out[21] = lens_radius;
+}
+
+template <bool OCTREE>
+__global__ void __launch_bounds__(kRenderThreads, 4)
+k_render_h(const __grid_constant__ RenderLaunch p, const uint2 *__restrict__ geom_h, const uint2 *__restrict__ matl_h,
+           const __half *__restrict__ cam_h) {
+    CameraH cam;
+    {
+        vec3h *v[7] = {&cam.origin, &cam.lower_left_corner, &cam.horizontal, &cam.vertical, &cam.u, &cam.v, &cam.w};
+        for (int k = 0; k < 7; k++) *v[k] = mkh(cam_h[3 * k], cam_h[3 * k + 1], cam_h[3 * k + 2]);
+        cam.lens_radius = cam_h[21];
+    }
+    const unsigned lane = threadIdx.x & 31u;
+    const uint32_t gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int pix = -1, pi = 0, pj = 0, s = 0, depth = 0;
+    xorwow rng;
+    rng.d = rng.v0 = rng.v1 = rng.v2 = rng.v3 = rng.v4 = 0;
+    const hf zero = f2h(0.0f), one = f2h(1.0f);
+    vec3h o = mkh(zero, zero, zero), d = mkh(zero, zero, one), att = mkh(one, one, one), col = mkh(zero, zero, zero);
+    uint32_t nrays = 0, npaths = 0;
+    bool exhausted = false, first = true;
+    const uint32_t first_item = gwarp * 32u + lane;
+    const hf nxh = f2h((float)p.nx), nyh = f2h((float)p.ny);
+    // col /= real_t(ns): k = 1.0 / t in double, stored as real_t (vec3.h:137-144)
+    const hf inv_ns = f2h((float)(1.0 / (double)h2f(f2h((float)p.ns_total))));
+
+    while (true) {
+        while (true) {          // claim pixels for idle lanes (as k_render)
+            const bool need = pix < 0 && !exhausted;
+            const unsigned m = __ballot_sync(0xffffffffu, need);
+            if (!m) break;
+            uint32_t item;
+            if (first) {
+                item = first_item;
+            } else {
+                uint32_t base = 0;
+                const int leader = __ffs(m) - 1;
+                if ((int)lane == leader) base = atomicAdd(p.work_counter, (uint32_t)__popc(m));
+                base = __shfl_sync(0xffffffffu, base, leader);
+                item = base + (uint32_t)__popc(m & ((1u << lane) - 1u));
+            }
+            if (need) {
+                if (item >= p.total_items) {
+                    exhausted = true;
+                } else if (item_to_pixel(p, item, pi, pj)) {
+                    pix = pj * p.nx + pi;
+                    s = 0; depth = 0;
+                    col = mkh(zero, zero, zero);
+                    pixel_stream(p, pix, rng);
+                }
+            }
+            first = false;
+        }
+        if (!__ballot_sync(0xffffffffu, pix >= 0)) break;
+
+        if (pix >= 0) {
+            if (depth == 0) {   // main.cu:104-106: real_t(i + U) / real_t(max_x) — the sum is float, the quotient __hdiv
+                const hf u = hdiv_(f2h(__fadd_rn((float)pi, xorwow_uniform(rng))), nxh);
+                const hf v = hdiv_(f2h(__fadd_rn((float)pj, xorwow_uniform(rng))), nyh);
+                camera_ray_h(cam, u, v, rng, o, d);
+                att = mkh(one, one, one);
+                npaths++;
+            }
+            nrays++;
+            const HitH h = OCTREE ? trace_tree_h(geom_h, p.scene.tag, p.tree, o, d) : trace_list_h(geom_h, p.scene.tag, p.scene.n, o, d);
+            bool sample_done = false;
+            vec3h contrib = mkh(zero, zero, zero);
+            if (h.idx >= 0) {
+                vec3h hp, hn, a, dn;
+                hit_point_h(load_sphere_h(geom_h, h.idx), o, d, h.t, hp, hn);
+                if (scatter_h(__ldg(p.scene.tag + h.idx), load_mat_h(matl_h, h.idx), d, hp, hn, a, dn, rng)) {
+                    att = vmul(att, a);                                   // main.cu:61
+                    o = hp; d = dn;
+                    depth++;
+                    if (depth >= p.max_depth) sample_done = true;         // main.cu:74
+                } else {
+                    sample_done = true;                                    // main.cu:64
+                }
+            } else {
+                contrib = vmul(att, sky_h(d));                             // main.cu:68-71
+                sample_done = true;
+            }
+            if (sample_done) {
+                col = vadd(col, contrib);                                  // main.cu:107, accumulated in half
+                depth = 0;
+                s++;
+                if (s >= p.ns_local) {
+                    float *out = p.out + (size_t)pix * 3;
+                    if (p.finalize) {   // main.cu:111-115: col /= real_t(ns); sqrt() is the float one
+                        out[0] = h2f(hsqrtf_(hmul_(vx(col), inv_ns)));
+                        out[1] = h2f(hsqrtf_(hmul_(vy(col), inv_ns)));
+                        out[2] = h2f(hsqrtf_(hmul_(col.z, inv_ns)));
+                    } else {
+                        out[0] = h2f(vx(col)); out[1] = h2f(vy(col)); out[2] = h2f(col.z);
+                    }
+                    pix = -1;
+                }
+            }
+        }
+        __syncwarp();
+    }
+    unsigned long long r64 = nrays, p64 = npaths;
+    for (int off = 16; off > 0; off >>= 1) {
+        r64 += __shfl_xor_sync(0xffffffffu, r64, off);
+        p64 += __shfl_xor_sync(0xffffffffu, p64, off);
+    }
+    if (lane == 0) {
+        atomicAdd(p.counters + 0, r64);
+        atomicAdd(p.counters + 1, p64);
+    }
+}
+
+template <bool OCTREE>
+static cudaError_t launch_half(const RenderLaunch &p, const uint2 *geom_h, const uint2 *matl_h, const __half *cam_h, int sm_count,
+                               cudaStream_t st, int *blocks_out) {
+    auto kern = k_render_h<OCTREE>;
+    int per_sm = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kRenderThreads, 0);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+    long long blocks = (long long)per_sm * sm_count;
+    const long long need = ((long long)p.total_items + kRenderThreads - 1) / kRenderThreads;
+    if (blocks > need) blocks = need < 1 ? 1 : need;
+    const uint32_t head = (uint32_t)(blocks * kRenderThreads);
+    e = cudaMemcpyAsync(p.work_counter, &head, 4, cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) return e;
+    kern<<<(unsigned)blocks, kRenderThreads, 0, st>>>(p, geom_h, matl_h, cam_h);
+    if (blocks_out) *blocks_out = (int)blocks;
+    return cudaGetLastError();
+}
+
+}  // namespace h16

@@ -57,6 +57,11 @@ struct TreeView {
     const uint32_t *prolog;     // first candidate list of every ray: the ground sphere (index 0, tested unconditionally by
     int nprolog;                // hitTree :322-332), then the big spheres in ascending order; nprolog = 1 + nbig
     float planes[3][kPlanes];   // slab plane coordinates per axis (exact floats of the reference subdivision)
+    // the reference's own cell lists (USE_FP16 path walks these): cell m (9-bit Morton id) was offered
+    // cell_list[cell_start[m] .. cell_start[m+1]) in ascending sphere order and stored the first cell_cap = 8*SPL of them
+    const uint32_t *cell_list;
+    const uint32_t *cell_start;
+    int cell_cap;
 };
 
 }  // namespace rt

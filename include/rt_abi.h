@@ -37,6 +37,10 @@ enum { RT_SEED_HEAD = 0, RT_SEED_UPSTREAM = 1 };
 /* how a frame is split over ranks: whole frame, interleaved pixel tiles (bit-identical to the
  * 1-GPU image after the sum), or samples-per-pixel shards (statistically equivalent, not bit-identical) */
 enum { RT_SHARD_NONE = 0, RT_SHARD_TILES = 1, RT_SHARD_SPP = 2 };
+/* arithmetic: RT_PREC_FP32 = the default build (real_t = float, precision_types.h:179); RT_PREC_FP16 = the reference
+ * compiled with USE_FP16 (precision_types.h:8): real_t is a __half wrapper, the scene is the FP32 scene rounded to half,
+ * frames are half values widened to float */
+enum { RT_PREC_FP32 = 0, RT_PREC_FP16 = 1 };
 
 /* One sphere and its material, flattened: what `sphere(center, radius, new <material>(...))` carries
  * (sphere.h:10, material.h:54,64,78).  36 bytes, same layout the oracle uses. */
@@ -70,7 +74,8 @@ typedef struct rt_render_args {
     int32_t seed_mode;       /* RT_SEED_* */
     int32_t shard_mode;      /* RT_SHARD_* */
     int32_t shard_rank, shard_count;
-    int32_t reserved[7];
+    int32_t precision;       /* RT_PREC_* (USE_FP16, precision_types.h:8); FP16 renders whole frames only (RT_SHARD_NONE) */
+    int32_t tune[6];         /* kernel A/B and tuning knobs for measurements; 0 = defaults; never change the image */
 } rt_render_args;
 
 typedef struct rt_render_stats {
@@ -95,6 +100,9 @@ int rt_device_info(const rt_context *ctx, int *sm_count, int *clock_khz, size_t 
 /* ---- scene: replaces rand_init + create_world (main.cu:388,399) ------------------------------------------ */
 /* The reference's generator: world seed 1984, NUM_SPHERES = n, SPHERE_RADIUS = radius (main.cu:22-23,146-181). */
 int rt_scene_generate(rt_context *ctx, int n, float sphere_radius);
+/* same under a given arithmetic: with RT_PREC_FP16 every value is stored through real_t (rounded to half) and the material
+ * choice compares a half-rounded draw with half-rounded thresholds, which changes the draw sequence (main.cu:165-172) */
+int rt_scene_generate_ex(rt_context *ctx, int n, float sphere_radius, int precision);
 /* A caller-built world (the drop-in headers flatten hitable_list into this). */
 int rt_scene_upload(rt_context *ctx, const rt_sphere_desc *spheres, int n);
 int rt_scene_download(rt_context *ctx, rt_sphere_desc *out, int n);
@@ -102,15 +110,21 @@ int rt_scene_size(const rt_context *ctx);
 /* camera: main.cu:192-202 constants with aspect = nx/ny when desc == NULL */
 int rt_camera_set(rt_context *ctx, const rt_camera_desc *desc, int nx, int ny);
 int rt_camera_get(rt_context *ctx, float out22[22]);         /* origin,llc,horizontal,vertical,u,v,w,lens_radius */
+/* the camera the USE_FP16 build constructs for an nx x ny frame (half values widened to float) */
+int rt_camera_get_half(rt_context *ctx, int nx, int ny, float out22[22]);
 
 /* ---- octree: replaces D2H(spheres) + buildOctree + H2D(Octree) (main.cu:405-415) -------------------------- */
 int rt_octree_build(rt_context *ctx, int spheres_per_leaf, rt_octree_stats *stats);
+/* same for a given arithmetic: with RT_PREC_FP16 `intersects` (acceleration_structure.h:82-93) compares half-rounded
+ * centres against half-rounded grown bounds, which moves spheres between cells */
+int rt_octree_build_ex(rt_context *ctx, int spheres_per_leaf, int precision, rt_octree_stats *stats);
 size_t rt_octree_reference_bytes(int spheres_per_leaf);      /* sizeof(Octree) for that SPHERES_PER_LEAF */
 /* the tree in the reference's own memory layout (acceleration_structure.h:23-61), for the bit-exact check */
 int rt_octree_export_reference(rt_context *ctx, void *host_blob, size_t bytes);
 
 /* test hook: read one internal traversal array back (0 grid descriptor, 1 voxel records, 2 voxel references,
- * 3 per-sphere entry offsets, 4 per-sphere cell lists, 5 big-sphere list, 6 sphere flags).  Returns the byte size
+ * 3 per-sphere entry offsets, 4 per-sphere cell lists, 5 big-sphere list, 6 sphere flags, 7 per-cell list offsets (513),
+ * 8 per-cell sphere lists in Morton cell order).  Returns the byte size
  * (host == NULL) or bytes copied. */
 size_t rt_octree_debug_read(rt_context *ctx, int which, void *host, size_t cap);
 

@@ -4,7 +4,7 @@
 # /root/reference, recompiled for sm_100) on the GPU box and dumps float framebuffers, sphere lists, cameras
 # and Octree blobs into gpurun_out/golden_ref_cuda/.  tests/golden/pack_ref_cuda.py then packs them into the
 # fixtures committed under tests/golden/ref_cuda/.
-#   usage (from the repo root, on a B200):  bash tests/golden/gen_ref_cuda.sh [small|upseed|timing|all]
+#   usage (from the repo root, on a B200):  bash tests/golden/gen_ref_cuda.sh [small|upseed|fp16|timing|all]
 set -uo pipefail
 MODE="${1:-all}"
 R=oracle/_ref
@@ -36,6 +36,17 @@ if [ "$MODE" = upseed ] || [ "$MODE" = all ]; then
   # the upstream per-pixel seeding curand_init(1984, pixel_index, 0) (main.cu:90 swapped in for :93 by patch_ref.sh)
   run n488_oct_spl30_upseed upseed 240 160 4 --fb "$O/n488_oct_upseed_240x160x4.fb"
   run n488_oct_spl30_upseed upseed_timing 1200 800 10 --reps 3
+fi
+if [ "$MODE" = fp16 ] || [ "$MODE" = all ]; then
+  # the reference built with -DUSE_FP16 (precision_types.h:8): frames are 3 halves per pixel
+  run n488_brute_spl30_fp16 fp16 240 160 4 --fb "$O/n488_brute_fp16_240x160x4.fb" --spheres "$O/n488_fp16.spheres" --camera "$O/cam_fp16_240x160.bin"
+  run n488_oct_spl30_fp16   fp16 240 160 4 --fb "$O/n488_oct_fp16_240x160x4.fb" --octree "$O/n488_spl30_fp16.octree"
+  run n8000_oct_spl30_fp16  fp16 240 160 4 --fb "$O/n8000_oct_fp16_240x160x4.fb" --octree "$O/n8000_spl30_fp16.octree"
+  run n100000_oct_spl300_fp16 fp16 192 108 2 --fb "$O/n100000_oct_fp16_192x108x2.fb"
+  run n488_brute_spl30_fp16 C1_fp16 1200 800 10 --reps 3 --fb "$O/C1_fp16_1200x800x10.fb"
+  run n488_oct_spl30_fp16   C2_fp16 1200 800 10 --reps 3
+  run n100000_oct_spl300_fp16 C4_4spp 3840 2160 4
+  sha256sum "$O"/*fp16*.octree > "$O/sha256_fp16.txt"
 fi
 if [ "$MODE" = timing ] || [ "$MODE" = all ]; then
   run n488_brute_spl30 C1 1200 800 10 --reps 3 --fb "$O/C1_1200x800x10.fb"
