@@ -33,10 +33,11 @@ CONFIGS = {
 }
 FP16_CONFIGS = {"C4"}
 # CPU sample of the workload: every CPU_STRIDE-th pixel in x and y of the full frame, all ns samples
-CPU_STRIDE = {"C1": (4, 4), "C2": (2, 2), "C3": (16, 16), "C5": (96, 96)}
+CPU_STRIDE = {"C1": (4, 4), "C2": (2, 2), "C3": (16, 16), "C4": (96, 96), "C5": (96, 96)}
 # reference CUDA build on the same B200 (oracle/_ref/ref_cuda_*, measured with tests/golden/gen_ref_cuda.sh);
 # kept next to the number for context — the driver computes its own ratios
-REF_CUDA_MS = {"C1": 42.19, "C2": 325.12, "C3": 177654.47}
+REF_CUDA_MS = {"C1": 42.19, "C2": 325.12, "C3": 177654.47,
+               "C4": 16 * 3489.82}        # C4: measured at 4 spp (3 489.8 ms), scaled to 64 spp
 
 
 class ClockSampler(threading.Thread):
@@ -82,7 +83,7 @@ def cpu_reference_sample(cfg: str, threads: int = 0):
     cores = threads or os.cpu_count() or 1
     params = O.make_params(nx, ny, ns, octree, spl, O.ARITH_HOST, step=(sx, sy), threads=cores)
     sample = f"pixels (i%{sx}==0, j%{sy}==0) of the {nx}x{ny} frame, all {ns} spp"
-    variant = f"{'oct' if octree else 'brute'}_spl{spl}"
+    variant = f"{'oct' if octree else 'brute'}_spl{spl}" + ("_fp16" if cfg in FP16_CONFIGS else "")
     if O.RefHost.available(variant):
         rh = O.RefHost(variant).create_world(n, 0.1, nx, ny)
         saved, devnull = os.dup(1), os.open(os.devnull, os.O_WRONLY)
@@ -136,6 +137,48 @@ def run_reference_arm(args):
     return 0
 
 
+def measure_e2e(pkg, mg, rt, torch, dist, dev, rank, world, mode, prec, n, spl, octree, nx, ny, ns, accum, fb, steps):
+    """The same metric through the public API with HOST buffers, all N ranks taking part: host->device copy of the sphere
+    descriptors, GPU octree build, (sharded) render, the reduce, device->host copy of the frame into pinned memory on
+    rank 0.  Wall clock around barriers; max over ranks by construction (rank 0 waits for the reduce)."""
+    import ctypes as C
+    spheres = rt.spheres()
+    host_fb = torch.empty((ny, nx, 3), dtype=torch.float32).pin_memory() if rank == 0 else None
+    rays, secs = 0.0, 0.0
+    for k in range(steps + 1):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        rt.upload_world(spheres)
+        if octree:
+            rt.build_octree(spl, prec)
+        if world == 1:
+            a = rt.args(nx, ny, ns, octree, precision=prec)
+            stt = pkg.RenderStats()
+            rt._ck(rt.L.rt_render_to_host(rt._ctx, C.byref(a), C.c_void_p(host_fb.data_ptr()), C.byref(stt)), "rt_render_to_host")
+            r = float(stt.rays)
+        else:
+            st = mg.render_sharded(rt, accum, fb, nx, ny, ns, bool(octree), rank, world, mode, dist, want_stats=True)
+            if rank == 0:
+                host_fb.copy_(fb, non_blocking=False)
+            r = float(st["rays"])
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([r], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            r = float(t[0])
+        if k > 0:                      # the first pass warms the allocations
+            rays += r
+            secs += dt
+    return {"value": rays / secs / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": int(n * 36) * world,
+            "d2h_bytes_per_step": int(nx * ny * 12 + 40), "ms_per_step": 1e3 * secs / steps,
+            "includes": "per rank: scene upload + GPU octree build + render of its shard; one reduce; frame copy to pinned host memory on rank 0"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -143,7 +186,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="C3", choices=sorted(CONFIGS))
-    ap.add_argument("--shard", default="tiles", choices=["tiles", "spp"])
+    ap.add_argument("--shard", default="spp", choices=["tiles", "spp"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -169,11 +212,14 @@ def main():
     dev = torch.device("cuda", local_rank)
 
     n, spl, octree, nx, ny, ns, desc = CONFIGS[args.config]
+    prec = pkg.PREC_FP16 if args.config in FP16_CONFIGS else pkg.PREC_FP32
+    if prec == pkg.PREC_FP16 and world > 1:
+        raise SystemExit("the USE_FP16 config renders whole frames on one GPU (the half accumulator does not split); use --gpus 1")
     rt = pkg.RayTracer(local_rank)
     stream = torch.cuda.current_stream()
     rt.set_stream(stream.cuda_stream)
-    rt.create_world(n, 0.1)
-    bst = rt.build_octree(spl) if octree else None
+    rt.create_world(n, 0.1, prec)
+    bst = rt.build_octree(spl, prec) if octree else None
     rt.set_camera(nx, ny)
     accum = torch.empty((ny, nx, 3), dtype=torch.float32, device=dev)
     fb = torch.empty_like(accum) if rank == 0 else accum
@@ -182,7 +228,7 @@ def main():
 
     def step(want_stats):
         if world == 1:
-            return rt.render_device(rt.args(nx, ny, ns, octree), fb.data_ptr(), want_stats=want_stats)
+            return rt.render_device(rt.args(nx, ny, ns, octree, precision=prec), fb.data_ptr(), want_stats=want_stats)
         return mg.render_sharded(rt, accum, fb, nx, ny, ns, bool(octree), rank, world, mode, dist, want_stats=want_stats)
 
     def barrier():
@@ -218,6 +264,7 @@ def main():
         total_ms, total_rays = float(tmax[0]), float(tsum[1])
     else:
         total_ms, total_rays = float(t[0]), float(t[1])
+    e2e_result = measure_e2e(pkg, mg, rt, torch, dist, dev, rank, world, mode, prec, n, spl, octree, nx, ny, ns, accum, fb, args.steps)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -227,9 +274,13 @@ def main():
     launches_per_step = 1 if world == 1 else 2          # render (+ finalize on rank 0); the reduce is NCCL's kernel
     line = {"metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
+            "dtype": "f16" if prec == pkg.PREC_FP16 else "f32", "data": "synthetic",
             "config": {"workload": desc, "n_spheres": n, "spheres_per_leaf": spl, "use_octree": octree, "nx": nx, "ny": ny, "ns": ns,
                        "max_depth": 50, "seed": "curand_init(1984+pixel_index,0,0)", "sharding": "none" if world == 1 else args.shard,
+                       "sharding_note": None if world == 1 else (
+                           "spp: rank g traces ns/N samples of every pixel from its own XORWOW streams (g = 0: the reference's); a valid "
+                           "frame of the same quality, not bit-identical to the 1-GPU frame.  --shard tiles is bit-identical (tests) but "
+                           "keeps every pixel's whole sample chain on one GPU, so the longest chain bounds the frame time"),
                        "collective": None if world == 1 else "one NCCL reduce-sum of the linear radiance buffer per frame",
                        "l2": "flushed between timed steps (256 MiB memset, untimed); each step times one whole frame",
                        "rays_per_frame": total_rays / args.steps, "octree_build_ms": bst["build_ms"] if bst else None},
@@ -239,33 +290,13 @@ def main():
         line["ref_cuda_build_same_b200"] = {"ms_per_frame": REF_CUDA_MS[args.config],
                                             "source": "tests/golden/ref_cuda/manifest.json (oracle/_ref/ref_cuda_*, sm_100 recompile)"}
 
-    # ---- end to end through the public API with HOST buffers (N = world ranks; rank 0 measures its own share) ----
-    spheres = rt.spheres()
-    host_fb = torch.empty((ny, nx, 3), dtype=torch.float32).pin_memory()
-    e2e_rays, e2e_t = 0, 0.0
-    if world == 1:
-        import ctypes as C
-        for k in range(args.steps + 1):
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            rt.upload_world(spheres)                           # host -> device: sphere descriptors (SoA split on the way)
-            if octree:
-                rt.build_octree(spl)
-            a = rt.args(nx, ny, ns, octree)
-            stt = pkg.RenderStats()
-            rt._ck(rt.L.rt_render_to_host(rt._ctx, C.byref(a), C.c_void_p(host_fb.data_ptr()), C.byref(stt)), "rt_render_to_host")
-            dt = time.perf_counter() - t0
-            if k > 0:                                          # first pass warms the allocations
-                e2e_rays += stt.rays
-                e2e_t += dt
-        line["e2e"] = {"value": e2e_rays / e2e_t / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": int(n * 36),
-                       "d2h_bytes_per_step": int(nx * ny * 12 + 40), "ms_per_step": 1e3 * e2e_t / args.steps,
-                       "includes": "scene upload, GPU octree build, render, frame copy to pinned host memory"}
-    else:
-        line["e2e"] = None
-
+    # ---- end to end through the public API with HOST buffers: every rank uploads the sphere descriptors and rebuilds the
+    #      octree, renders its shard, the shards are reduced, rank 0 copies the frame to pinned host memory ----
+    line["e2e"] = e2e_result
     # ---- roofline of the dominant kernel (k_render): FP32 issue, SURVEY §8(d) formula with measured S, B ----
     try:
+        if prec == pkg.PREC_FP16:
+            raise RuntimeError("no work counters in the USE_FP16 kernel; see profiles/ for its ncu summary")
         peak = rt.ffma_peak_tflops()
         rti = pkg.RayTracer(local_rank, instrumented=True)
         rti.create_world(n, 0.1)
