@@ -3,7 +3,8 @@
 //   mode 0 = P3 PPM to stdout (default), 1 = no output, 3 = output.ppm; 2 (OpenGL preview) is accepted and ignored.
 // Same banner on stderr, same "took X seconds." line, same exit(99) on a CUDA error.  The reference's knobs keep
 // their names; they are #ifndef-guarded so -D works, and can be overridden at run time without touching the
-// positional argument: RT_NUM_SPHERES, RT_SPHERES_PER_LEAF, RT_USE_OCTREE, RT_NX, RT_NY, RT_NS.
+// positional argument: RT_NUM_SPHERES, RT_SPHERES_PER_LEAF, RT_USE_OCTREE, RT_USE_FP16, RT_NX, RT_NY, RT_NS
+// (and RT_SEED_MODE=1 for the upstream per-pixel seeding curand_init(1984, pixel_index, 0), main.cu:90).
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -57,19 +58,26 @@ int main(int argc, char **argv) {
     std::cerr << "Number of spheres: " << n << "\n";
     std::cerr << "Sphere radius: " << SPHERE_RADIUS << "\n";
     std::cerr << (use_octree ? "Use octree: ON\n" : "Use octree: OFF\n");
+#ifdef USE_FP16                   // precision_types.h:8
+    const int precision = env_int("RT_USE_FP16", 1) ? RT_PREC_FP16 : RT_PREC_FP32;
+#else
+    const int precision = env_int("RT_USE_FP16", 0) ? RT_PREC_FP16 : RT_PREC_FP32;
+#endif
     int output_mode = 0;
     if (argc > 1) output_mode = std::stoi(argv[1]);      // throws on garbage, as the reference does
     std::cerr << "Output mode: " << output_mode << "\n";
 
     rt_context *ctx = nullptr;
     CHECK(rt_create(0, &ctx));
-    CHECK(rt_scene_generate(ctx, n, SPHERE_RADIUS));
-    if (use_octree) CHECK(rt_octree_build(ctx, spl, nullptr));
+    CHECK(rt_scene_generate_ex(ctx, n, SPHERE_RADIUS, precision));
+    if (use_octree) CHECK(rt_octree_build_ex(ctx, spl, precision, nullptr));
     CHECK(rt_camera_set(ctx, nullptr, nx, ny));
 
     std::vector<float> fb((size_t)nx * ny * 3);
     rt_render_args a{};
     a.nx = nx; a.ny = ny; a.ns = ns; a.max_depth = 50; a.use_octree = use_octree;
+    a.precision = precision;
+    a.seed_mode = env_int("RT_SEED_MODE", RT_SEED_HEAD);
     rt_render_stats st{};
     const auto t0 = std::chrono::steady_clock::now();
     CHECK(rt_render_to_host(ctx, &a, fb.data(), &st));
