@@ -52,6 +52,7 @@ struct rt_context {
     uint2 *geom_h = nullptr, *matl_h = nullptr;
     size_t half_cap = 0;
     bool half_valid = false;
+    HalfPairs half_pairs;
     __half *cam_h = nullptr;
     int cam_h_nx = 0, cam_h_ny = 0;
     rt_camera_desc cam_desc{};
@@ -122,6 +123,7 @@ extern "C" void rt_destroy(rt_context *ctx) {
     cudaFree(ctx->work_counter); cudaFree(ctx->counters); cudaFree(ctx->scratch_fb);
     cudaFree(ctx->skip_tables); cudaFree(ctx->seed_states);
     cudaFree(ctx->geom_h); cudaFree(ctx->matl_h); cudaFree(ctx->cam_h);
+    cudaFree(ctx->half_pairs.geom); cudaFree(ctx->half_pairs.idx); cudaFree(ctx->half_pairs.start); cudaFree(ctx->half_pairs.count);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -369,6 +371,7 @@ extern "C" int rt_octree_build_ex(rt_context *ctx, int spl, int precision, rt_oc
     CK(cudaSetDevice(ctx->device));
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
     CK(ctx->octree->build(ctx->stream, ctx->geom, ctx->tag, ctx->n, spl, ctx->grid_density, precision == RT_PREC_FP16));
+    ctx->half_pairs.valid = false;
     CK(cudaEventRecord(ctx->ev1, ctx->stream));
     CK(cudaEventSynchronize(ctx->ev1));
     if (stats) {
@@ -503,12 +506,16 @@ static int do_render(rt_context *ctx, const rt_render_args *a, float *out_dev, b
         if (!ctx->half_valid) {
             CK(launch_scene_to_half(ctx->geom, ctx->matl, ctx->n, ctx->geom_h, ctx->matl_h, ctx->stream));
             ctx->half_valid = true;
+            ctx->half_pairs.valid = false;
         }
+        if (!ctx->half_pairs.valid || ctx->half_pairs.octree != (a->use_octree != 0))
+            CK(build_half_pairs(ctx->half_pairs, ctx->geom_h, ctx->tag, ctx->n, a->use_octree != 0, p.tree, ctx->stream));
         {
             const int rc = ensure_half_camera(ctx, a->nx, a->ny);
             if (rc) return rc;
         }
-        CK(launch_render_half(p, a->use_octree != 0, ctx->geom_h, ctx->matl_h, ctx->cam_h, ctx->prop.multiProcessorCount, ctx->stream, &blocks));
+        CK(launch_render_half(p, a->use_octree != 0, ctx->geom_h, ctx->matl_h, ctx->cam_h, ctx->half_pairs, ctx->prop.multiProcessorCount,
+                              ctx->stream, &blocks));
     } else {
         CK(launch_render(p, a->use_octree != 0, ctx->prop.multiProcessorCount, ctx->prop.sharedMemPerBlockOptin, ctx->stream, &blocks));
     }

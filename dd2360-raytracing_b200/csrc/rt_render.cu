@@ -273,9 +273,38 @@ cudaError_t launch_camera_setup_half(const float lookfrom[3], const float lookat
     return cudaGetLastError();
 }
 cudaError_t launch_render_half(const RenderLaunch &p, bool octree, const uint2 *geom_h, const uint2 *matl_h, const __half *cam_h,
-                               int sm_count, cudaStream_t st, int *blocks_out) {
-    return octree ? h16::launch_half<true>(p, geom_h, matl_h, cam_h, sm_count, st, blocks_out)
-                  : h16::launch_half<false>(p, geom_h, matl_h, cam_h, sm_count, st, blocks_out);
+                               const HalfPairs &hp, int sm_count, cudaStream_t st, int *blocks_out) {
+    h16::PairView pv;
+    pv.geom = hp.geom; pv.idx = hp.idx; pv.start = hp.start;
+    return octree ? h16::launch_half<true>(p, geom_h, matl_h, cam_h, pv, sm_count, st, blocks_out)
+                  : h16::launch_half<false>(p, geom_h, matl_h, cam_h, pv, sm_count, st, blocks_out);
+}
+
+// (re)build the pair lists of the USE_FP16 path: lists = 1 (flat mode) or kCells (octree mode)
+cudaError_t build_half_pairs(HalfPairs &hp, const uint2 *geom_h, const int *tag, int n, bool octree, const TreeView &tv, cudaStream_t st) {
+    const int lists = octree ? kCells : 1;
+    cudaError_t e;
+    if (!hp.count) {
+        if ((e = cudaMalloc(&hp.count, (kCells + 1) * 4)) != cudaSuccess) return e;
+        if ((e = cudaMalloc(&hp.start, (kCells + 2) * 4)) != cudaSuccess) return e;
+    }
+    h16::k_pairs_count<<<(lists + 127) / 128, 128, 0, st>>>(tag, n, lists, tv.cell_start, tv.cell_list, tv.cell_cap, hp.count);
+    h16::k_pairs_scan<<<1, 32, 0, st>>>(hp.count, lists, hp.start);
+    uint32_t total = 0;
+    if ((e = cudaMemcpyAsync(&total, hp.start + lists, 4, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return e;
+    if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return e;
+    if (total + 1 > hp.cap) {
+        cudaFree(hp.geom); cudaFree(hp.idx);
+        hp.geom = nullptr; hp.idx = nullptr; hp.cap = 0;
+        if ((e = cudaMalloc(&hp.geom, ((size_t)total + 1) * sizeof(uint4))) != cudaSuccess) return e;
+        if ((e = cudaMalloc(&hp.idx, ((size_t)total + 1) * sizeof(int2))) != cudaSuccess) return e;
+        hp.cap = (size_t)total + 1;
+    }
+    h16::k_pairs_fill<<<(lists + 127) / 128, 128, 0, st>>>(geom_h, tag, n, lists, tv.cell_start, tv.cell_list, tv.cell_cap, hp.start, hp.geom, hp.idx);
+    hp.pairs = total;
+    hp.octree = octree;
+    hp.valid = true;
+    return cudaGetLastError();
 }
 
 // Closest hit for caller-supplied rays (test hook: per-ray parity against the oracle's hitTree / hitable_list::hit)

@@ -45,8 +45,17 @@ cudaError_t launch_seed_upstream(uint32_t *states, size_t npix, unsigned long lo
 cudaError_t launch_scene_to_half(const float4 *geom, const float4 *matl, int n, uint2 *geom_h, uint2 *matl_h, cudaStream_t st);
 cudaError_t launch_camera_setup_half(const float lookfrom[3], const float lookat[3], const float vup[3], float vfov, int nx, int ny,
                                      float aspect_override, float aperture, float focus_dist, __half *cam_h, cudaStream_t st);
+struct HalfPairs {            // candidate lists as transposed sphere pairs (rt_half.cuh PairView), owned by the context
+    uint4 *geom = nullptr;
+    int2 *idx = nullptr;
+    uint32_t *start = nullptr, *count = nullptr;
+    size_t cap = 0;
+    uint32_t pairs = 0;
+    bool valid = false, octree = false;
+};
+cudaError_t build_half_pairs(HalfPairs &hp, const uint2 *geom_h, const int *tag, int n, bool octree, const TreeView &tv, cudaStream_t st);
 cudaError_t launch_render_half(const RenderLaunch &p, bool octree, const uint2 *geom_h, const uint2 *matl_h, const __half *cam_h,
-                               int sm_count, cudaStream_t st, int *blocks_out);
+                               const HalfPairs &hp, int sm_count, cudaStream_t st, int *blocks_out);
 cudaError_t launch_finalize(const float *accum, float *fb, int nx, int ny, int ns, cudaStream_t st);
 
 }  // namespace rt

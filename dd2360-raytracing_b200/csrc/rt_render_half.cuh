@@ -24,6 +24,62 @@ __global__ void k_scene_to_half(const float4 *__restrict__ geom, const float4 *_
     matl_h[i] = make_uint2(*reinterpret_cast<uint32_t *>(&a), *reinterpret_cast<uint32_t *>(&b));
 }
 
+// Pair lists (rt_half.cuh PairView).  lists == 1: the flat mode, one list of all n spheres in index order;
+// lists == kCells: the stored list of every level-3 cell (first cell_cap entries in ascending sphere order).
+// Pass 1 (count) sizes the lists, a 513-thread scan makes the offsets, pass 2 writes the pairs.
+__global__ void k_pairs_count(const int *__restrict__ tag, int n, int lists, const uint32_t *__restrict__ cell_start,
+                              const uint32_t *__restrict__ cell_list, int cell_cap, uint32_t *__restrict__ pair_count) {
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= lists) return;
+    uint32_t valid = 0;
+    if (lists == 1) {
+        for (int i = 0; i < n; i++) valid += tag[i] >= 0;
+    } else {
+        const uint32_t b = cell_start[m], e = min(cell_start[m + 1], b + (uint32_t)cell_cap);
+        for (uint32_t k = b; k < e; k++) valid += tag[cell_list[k]] >= 0;
+    }
+    pair_count[m] = (valid + 1u) / 2u;
+}
+__global__ void k_pairs_scan(const uint32_t *__restrict__ pair_count, int lists, uint32_t *__restrict__ pair_start) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        uint32_t acc = 0;
+        for (int m = 0; m < lists; m++) { pair_start[m] = acc; acc += pair_count[m]; }
+        pair_start[lists] = acc;
+    }
+}
+__global__ void k_pairs_fill(const uint2 *__restrict__ geom_h, const int *__restrict__ tag, int n, int lists,
+                             const uint32_t *__restrict__ cell_start, const uint32_t *__restrict__ cell_list, int cell_cap,
+                             const uint32_t *__restrict__ pair_start, uint4 *__restrict__ pair_geom, int2 *__restrict__ pair_idx) {
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= lists) return;
+    uint32_t out = pair_start[m];
+    int pend = -1;
+    const unsigned short nan16 = 0x7e00u;
+    auto emit = [&](int i0, int i1) {
+        const uint2 g0 = geom_h[i0];
+        uint2 g1 = make_uint2(0x7e007e00u, 0x7e007e00u);           // NaN sphere: the padding of an odd list
+        if (i1 >= 0) g1 = geom_h[i1];
+        (void)nan16;
+        // g = {cx | cy << 16, cz | r << 16}; transpose to {cx0|cx1<<16, cy0|cy1<<16, cz0|cz1<<16, r0|r1<<16}
+        pair_geom[out] = make_uint4((g0.x & 0xffffu) | (g1.x << 16), (g0.x >> 16) | (g1.x & 0xffff0000u),
+                                    (g0.y & 0xffffu) | (g1.y << 16), (g0.y >> 16) | (g1.y & 0xffff0000u));
+        pair_idx[out] = make_int2(i0, i1);
+        out++;
+    };
+    auto feed = [&](int i) {
+        if (tag[i] < 0) return;
+        if (pend < 0) pend = i;
+        else { emit(pend, i); pend = -1; }
+    };
+    if (lists == 1) {
+        for (int i = 0; i < n; i++) feed(i);
+    } else {
+        const uint32_t b = cell_start[m], e = min(cell_start[m + 1], b + (uint32_t)cell_cap);
+        for (uint32_t k = b; k < e; k++) feed((int)cell_list[k]);
+    }
+    if (pend >= 0) emit(pend, -1);
+}
+
 // vec3.h:95-99 cross(): a*b - c*d -> fma(a,b,-(c*d)); the middle component's unary minus goes through float
 __device__ __forceinline__ vec3h cross_h(const vec3h a, const vec3h b) {
     const hf cx = hfma_(vy(a), b.z, hneg_(hmul_(a.z, vy(b))));
@@ -61,7 +117,7 @@ __global__ void k_camera_setup_h(const float lfx, const float lfy, const float l
 template <bool OCTREE>
 __global__ void __launch_bounds__(kRenderThreads, 4)
 k_render_h(const __grid_constant__ RenderLaunch p, const uint2 *__restrict__ geom_h, const uint2 *__restrict__ matl_h,
-           const __half *__restrict__ cam_h) {
+           const __half *__restrict__ cam_h, const PairView pv) {
     CameraH cam;
     {
         vec3h *v[7] = {&cam.origin, &cam.lower_left_corner, &cam.horizontal, &cam.vertical, &cam.u, &cam.v, &cam.w};
@@ -120,7 +176,7 @@ k_render_h(const __grid_constant__ RenderLaunch p, const uint2 *__restrict__ geo
                 npaths++;
             }
             nrays++;
-            const HitH h = OCTREE ? trace_tree_h(geom_h, p.scene.tag, p.tree, o, d) : trace_list_h(geom_h, p.scene.tag, p.scene.n, o, d);
+            const HitH h = OCTREE ? trace_tree_h(pv, geom_h, p.tree, o, d) : trace_list_h(pv, geom_h, o, d);
             bool sample_done = false;
             vec3h contrib = mkh(zero, zero, zero);
             if (h.idx >= 0) {
@@ -169,8 +225,8 @@ k_render_h(const __grid_constant__ RenderLaunch p, const uint2 *__restrict__ geo
 }
 
 template <bool OCTREE>
-static cudaError_t launch_half(const RenderLaunch &p, const uint2 *geom_h, const uint2 *matl_h, const __half *cam_h, int sm_count,
-                               cudaStream_t st, int *blocks_out) {
+static cudaError_t launch_half(const RenderLaunch &p, const uint2 *geom_h, const uint2 *matl_h, const __half *cam_h, const PairView pv,
+                               int sm_count, cudaStream_t st, int *blocks_out) {
     auto kern = k_render_h<OCTREE>;
     int per_sm = 0;
     cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kRenderThreads, 0);
@@ -182,7 +238,7 @@ static cudaError_t launch_half(const RenderLaunch &p, const uint2 *geom_h, const
     const uint32_t head = (uint32_t)(blocks * kRenderThreads);
     e = cudaMemcpyAsync(p.work_counter, &head, 4, cudaMemcpyHostToDevice, st);
     if (e != cudaSuccess) return e;
-    kern<<<(unsigned)blocks, kRenderThreads, 0, st>>>(p, geom_h, matl_h, cam_h);
+    kern<<<(unsigned)blocks, kRenderThreads, 0, st>>>(p, geom_h, matl_h, cam_h, pv);
     if (blocks_out) *blocks_out = (int)blocks;
     return cudaGetLastError();
 }
