@@ -124,6 +124,7 @@ extern "C" void rt_destroy(rt_context *ctx) {
     cudaFree(ctx->skip_tables); cudaFree(ctx->seed_states);
     cudaFree(ctx->geom_h); cudaFree(ctx->matl_h); cudaFree(ctx->cam_h);
     cudaFree(ctx->half_pairs.geom); cudaFree(ctx->half_pairs.idx); cudaFree(ctx->half_pairs.start); cudaFree(ctx->half_pairs.count);
+    cudaFree(ctx->half_pairs.nodes); cudaFree(ctx->half_pairs.node_count);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);

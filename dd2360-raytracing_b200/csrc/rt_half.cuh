@@ -337,5 +337,143 @@ __device__ __forceinline__ HitH trace_tree_h(const PairView pv, const uint2 *geo
     return h;
 }
 
+// ---- warp-cooperative closest hit ---------------------------------------------------------------------------------------------
+// The USE_FP16 closest hit is an exhaustive scan (every sphere of every passing cell: ~2 000 candidates per ray at 100 k
+// spheres), so instead of 32 lanes each crawling through their own lists, the WARP takes the rays of its lanes one at a
+// time: the ray is broadcast, the lanes test the existing octree nodes level by level (compact per-level tables, one
+// node per lane, parents gate children through ballot masks), then stride through the pair list of each passing cell
+// together — coalesced 16-byte loads, no divergence.  Equivalence with the reference's sequential scan: a candidate's
+// accepted root t_i does not depend on closest_so_far (if the near root is valid but not closer, the far root is not
+// closer either), so the sequential result is the lexicographic minimum of (t_i, position in scan order) — ties keep
+// the first, as strict '<' does — and that minimum is taken with two warp-wide REDUX mins.
+struct NodeTab {
+    const uint2 *ent;         // [8 | 64 | 512] compact per level: x = ix | iy << 8 | iz << 16, y = parent position | morton << 16
+    const uint32_t *count;    // n1, n2, n3
+};
+
+__device__ __forceinline__ bool node_pass_h(const float *P, const uint2 e, const int level, const vec3h o, const vec3h d) {
+    const int ix = e.x & 255, iy = (e.x >> 8) & 255, iz = (e.x >> 16) & 255, sh = 3 - level;
+    return ref_line_test_h(o, d, f2h(P[ix << sh]), f2h(P[kPlanes + (iy << sh)]), f2h(P[2 * kPlanes + (iz << sh)]),
+                           f2h(P[(ix + 1) << sh]), f2h(P[kPlanes + ((iy + 1) << sh)]), f2h(P[2 * kPlanes + ((iz + 1) << sh)]));
+}
+
+struct BestH {                // lane-local lexicographic minimum of (t bits, scan position)
+    uint32_t t, order;
+};
+__device__ __forceinline__ void best_update(BestH &b, const hf t, const uint32_t order) {
+    const uint32_t tb = __half_as_ushort(t);          // accepted roots are > 0.001: positive halves order like their bits
+    if (tb < b.t || (tb == b.t && order < b.order)) { b.t = tb; b.order = order; }
+}
+
+// all 32 lanes stride through pairs [pb, pe) of one list for the broadcast ray (o, d)
+__device__ __forceinline__ void coop_scan_h(const PairView pv, const uint2 *geom_h, const uint32_t pb, const uint32_t pe, const unsigned lane,
+                                            const vec3h o, const vec3h d, const hf a, BestH &best) {
+    const __half2 ox = __half2half2(vx(o)), oy = __half2half2(vy(o)), oz = __half2half2(o.z);
+    const __half2 dx = __half2half2(vx(d)), dy = __half2half2(vy(d)), dz = __half2half2(d.z);
+    const __half2 a2 = __half2half2(a), zero2 = __float2half2_rn(0.0f);
+    const hf inf = f2h(3.402823466e+38f);
+    for (uint32_t k = pb + lane; k < pe; k += 32u) {
+        const uint4 g = __ldg(pv.geom + k);
+        const __half2 cx = *reinterpret_cast<const __half2 *>(&g.x), cy = *reinterpret_cast<const __half2 *>(&g.y);
+        const __half2 cz = *reinterpret_cast<const __half2 *>(&g.z), r = *reinterpret_cast<const __half2 *>(&g.w);
+        const __half2 ocx = __hsub2_rn(ox, cx), ocy = __hsub2_rn(oy, cy), ocz = __hsub2_rn(oz, cz);
+        const __half2 b = __hfma2(ocz, dz, __hfma2(ocx, dx, __hmul2_rn(ocy, dy)));
+        const __half2 c = __hfma2(__hneg2(r), r, __hfma2(ocz, ocz, __hfma2(ocx, ocx, __hmul2_rn(ocy, ocy))));
+        const __half2 disc = __hfma2(b, b, __hneg2(__hmul2_rn(a2, c)));
+        const __half2 pos = __hgt2(disc, zero2);
+        if (*reinterpret_cast<const uint32_t *>(&pos) != 0u) {
+            const int2 id = __ldg(pv.idx + k);
+            hf t;
+            if (__hgt(__low2half(disc), f2h(0.0f)) && sphere_test_h(load_sphere_h(geom_h, id.x), o, d, a, inf, t)) best_update(best, t, 2u * k + 1u);
+            if (__hgt(__high2half(disc), f2h(0.0f)) && id.y >= 0 && sphere_test_h(load_sphere_h(geom_h, id.y), o, d, a, inf, t))
+                best_update(best, t, 2u * k + 2u);
+        }
+    }
+}
+
+template <bool OCTREE>
+__device__ __forceinline__ HitH coop_trace_h(const PairView pv, const NodeTab nt, const uint2 *geom_h, const TreeView &tv, const bool have_ray,
+                                             const vec3h o, const vec3h d) {
+    const unsigned full = 0xffffffffu;
+    const unsigned lane = threadIdx.x & 31u;
+    const hf inf = f2h(3.402823466e+38f);
+    HitH mine;
+    mine.t = inf;
+    mine.idx = -1;
+    const float *P = &tv.planes[0][0];
+    uint32_t n1 = 0, n2 = 0, n3 = 0;
+    if (OCTREE) { n1 = __ldg(nt.count); n2 = __ldg(nt.count + 1); n3 = __ldg(nt.count + 2); }
+    unsigned todo = __ballot_sync(full, have_ray);
+    while (todo) {
+        const int r = __ffs(todo) - 1;
+        todo &= todo - 1u;
+        // broadcast the ray of lane r
+        vec3h ro, rd;
+        {
+            const uint32_t oxy = __shfl_sync(full, *reinterpret_cast<const uint32_t *>(&o.xy), r);
+            const uint32_t dxy = __shfl_sync(full, *reinterpret_cast<const uint32_t *>(&d.xy), r);
+            const __half2 zz = __halves2half2(o.z, d.z);
+            const uint32_t ozdz = __shfl_sync(full, *reinterpret_cast<const uint32_t *>(&zz), r);
+            ro.xy = *reinterpret_cast<const __half2 *>(&oxy);
+            rd.xy = *reinterpret_cast<const __half2 *>(&dxy);
+            const __half2 z2 = *reinterpret_cast<const __half2 *>(&ozdz);
+            ro.z = __low2half(z2);
+            rd.z = __high2half(z2);
+        }
+        const hf a = dot3h(rd, rd);
+        BestH best;
+        best.t = 0xffffffffu;
+        best.order = 0xffffffffu;
+        if (!OCTREE) {
+            coop_scan_h(pv, geom_h, __ldg(pv.start), __ldg(pv.start + 1), lane, ro, rd, a, best);        // hitable_list.h:16-31
+        } else {
+            if (lane == 0) {                                                                                // ground sphere first (:322-332)
+                hf t;
+                if (sphere_test_h(load_sphere_h(geom_h, 0), ro, rd, a, inf, t)) best_update(best, t, 0u);
+            }
+            uint2 root;
+            root.x = 0; root.y = 0;
+            if (n1 > 0 && node_pass_h(P, root, 0, ro, rd)) {                                               // uniform: every lane, same ray
+                const uint2 e1 = lane < n1 ? __ldg(nt.ent + lane) : root;
+                const unsigned m1 = __ballot_sync(full, lane < n1 && node_pass_h(P, e1, 1, ro, rd));
+                unsigned m2[2];
+#pragma unroll
+                for (int i = 0; i < 2; i++) {
+                    const uint32_t j = lane + 32u * i;
+                    const uint2 e2 = j < n2 ? __ldg(nt.ent + 8 + j) : root;
+                    m2[i] = __ballot_sync(full, j < n2 && ((m1 >> (e2.y & 0xffffu)) & 1u) && node_pass_h(P, e2, 2, ro, rd));
+                }
+                for (uint32_t base = 0; base < n3; base += 32u) {
+                    const uint32_t j = base + lane;
+                    const uint2 e3 = j < n3 ? __ldg(nt.ent + 72 + j) : root;
+                    const uint32_t par = e3.y & 0xffffu;
+                    const bool par_ok = ((par < 32u ? m2[0] >> par : m2[1] >> (par - 32u)) & 1u) != 0u;
+                    unsigned m3 = __ballot_sync(full, j < n3 && par_ok && node_pass_h(P, e3, 3, ro, rd));
+                    while (m3) {                                   // passing cells of this group, in Morton order
+                        const int c = __ffs(m3) - 1;
+                        m3 &= m3 - 1u;
+                        const uint32_t cell = __shfl_sync(full, e3.y >> 16, c);
+                        coop_scan_h(pv, geom_h, __ldg(pv.start + cell), __ldg(pv.start + cell + 1), lane, ro, rd, a, best);
+                    }
+                }
+            }
+        }
+        const uint32_t tmin = __reduce_min_sync(full, best.t);
+        if (tmin != 0xffffffffu) {
+            const uint32_t omin = __reduce_min_sync(full, best.t == tmin ? best.order : 0xffffffffu);
+            if ((int)lane == r) {
+                mine.t = __ushort_as_half((unsigned short)tmin);
+                if (omin == 0u) {
+                    mine.idx = 0;
+                } else {
+                    const int2 id = __ldg(pv.idx + ((omin - 1u) >> 1));
+                    mine.idx = ((omin - 1u) & 1u) ? id.y : id.x;
+                }
+            }
+        }
+    }
+    return mine;
+}
+
 }  // namespace h16
 }  // namespace rt

@@ -18,6 +18,7 @@
 #include <stdint.h>
 
 #include "rt_render.h"
+#include "rt_build.cuh"
 #include "rt_half.cuh"
 #include "rt_trace.cuh"
 #include "rt_xorwow_skip.h"
@@ -276,8 +277,10 @@ cudaError_t launch_render_half(const RenderLaunch &p, bool octree, const uint2 *
                                const HalfPairs &hp, int sm_count, cudaStream_t st, int *blocks_out) {
     h16::PairView pv;
     pv.geom = hp.geom; pv.idx = hp.idx; pv.start = hp.start;
-    return octree ? h16::launch_half<true>(p, geom_h, matl_h, cam_h, pv, sm_count, st, blocks_out)
-                  : h16::launch_half<false>(p, geom_h, matl_h, cam_h, pv, sm_count, st, blocks_out);
+    h16::NodeTab nt;
+    nt.ent = hp.nodes; nt.count = hp.node_count;
+    return octree ? h16::launch_half<true>(p, geom_h, matl_h, cam_h, pv, nt, sm_count, st, blocks_out)
+                  : h16::launch_half<false>(p, geom_h, matl_h, cam_h, pv, nt, sm_count, st, blocks_out);
 }
 
 // (re)build the pair lists of the USE_FP16 path: lists = 1 (flat mode) or kCells (octree mode)
@@ -287,7 +290,10 @@ cudaError_t build_half_pairs(HalfPairs &hp, const uint2 *geom_h, const int *tag,
     if (!hp.count) {
         if ((e = cudaMalloc(&hp.count, (kCells + 1) * 4)) != cudaSuccess) return e;
         if ((e = cudaMalloc(&hp.start, (kCells + 2) * 4)) != cudaSuccess) return e;
+        if ((e = cudaMalloc(&hp.nodes, (8 + 64 + 512) * sizeof(uint2))) != cudaSuccess) return e;
+        if ((e = cudaMalloc(&hp.node_count, 4 * 4)) != cudaSuccess) return e;
     }
+    if (octree) h16::k_fp16_nodes<<<1, 1, 0, st>>>(tv.cell_start, hp.nodes, hp.node_count);
     h16::k_pairs_count<<<(lists + 127) / 128, 128, 0, st>>>(tag, n, lists, tv.cell_start, tv.cell_list, tv.cell_cap, hp.count);
     h16::k_pairs_scan<<<1, 32, 0, st>>>(hp.count, lists, hp.start);
     uint32_t total = 0;

@@ -49,6 +49,8 @@ struct HalfPairs {            // candidate lists as transposed sphere pairs (rt_
     uint4 *geom = nullptr;
     int2 *idx = nullptr;
     uint32_t *start = nullptr, *count = nullptr;
+    uint2 *nodes = nullptr;          // compact per-level tables of the existing octree nodes (rt_half.cuh NodeTab)
+    uint32_t *node_count = nullptr;
     size_t cap = 0;
     uint32_t pairs = 0;
     bool valid = false, octree = false;

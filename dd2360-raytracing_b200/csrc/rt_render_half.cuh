@@ -80,6 +80,35 @@ __global__ void k_pairs_fill(const uint2 *__restrict__ geom_h, const int *__rest
     if (pend >= 0) emit(pend, -1);
 }
 
+// compact per-level tables of the octree nodes that exist (a node was created iff its subtree received an entry):
+// ent[0..8) level 1, ent[8..72) level 2, ent[72..584) level 3; parents before children, each level in Morton order
+__global__ void k_fp16_nodes(const uint32_t *__restrict__ cell_start, uint2 *__restrict__ ent, uint32_t *__restrict__ count) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    int pos1[8], pos2[64];
+    uint32_t n1 = 0, n2 = 0, n3 = 0;
+    for (int c1 = 0; c1 < 8; c1++) {
+        pos1[c1] = -1;
+        if (cell_start[c1 * 64 + 64] == cell_start[c1 * 64]) continue;
+        pos1[c1] = (int)n1;
+        ent[n1++] = make_uint2((uint32_t)(c1 >> 2) | (uint32_t)((c1 >> 1) & 1) << 8 | (uint32_t)(c1 & 1) << 16, 0u | (uint32_t)c1 << 16);
+    }
+    for (int m2 = 0; m2 < 64; m2++) {
+        pos2[m2] = -1;
+        if (cell_start[m2 * 8 + 8] == cell_start[m2 * 8]) continue;
+        const int c1 = m2 >> 3, c2 = m2 & 7;
+        const int x = (c1 >> 2) * 2 + (c2 >> 2), y = ((c1 >> 1) & 1) * 2 + ((c2 >> 1) & 1), z = (c1 & 1) * 2 + (c2 & 1);
+        pos2[m2] = (int)n2;
+        ent[8 + n2++] = make_uint2((uint32_t)x | (uint32_t)y << 8 | (uint32_t)z << 16, (uint32_t)pos1[c1] | (uint32_t)m2 << 16);
+    }
+    for (int m3 = 0; m3 < 512; m3++) {
+        if (cell_start[m3 + 1] == cell_start[m3]) continue;
+        int x, y, z;
+        morton_to_xyz(m3, x, y, z);
+        ent[72 + n3++] = make_uint2((uint32_t)x | (uint32_t)y << 8 | (uint32_t)z << 16, (uint32_t)pos2[m3 >> 3] | (uint32_t)m3 << 16);
+    }
+    count[0] = n1; count[1] = n2; count[2] = n3;
+}
+
 // vec3.h:95-99 cross(): a*b - c*d -> fma(a,b,-(c*d)); the middle component's unary minus goes through float
 __device__ __forceinline__ vec3h cross_h(const vec3h a, const vec3h b) {
     const hf cx = hfma_(vy(a), b.z, hneg_(hmul_(a.z, vy(b))));
@@ -117,7 +146,7 @@ __global__ void k_camera_setup_h(const float lfx, const float lfy, const float l
 template <bool OCTREE>
 __global__ void __launch_bounds__(kRenderThreads, 4)
 k_render_h(const __grid_constant__ RenderLaunch p, const uint2 *__restrict__ geom_h, const uint2 *__restrict__ matl_h,
-           const __half *__restrict__ cam_h, const PairView pv) {
+           const __half *__restrict__ cam_h, const PairView pv, const NodeTab nt) {
     CameraH cam;
     {
         vec3h *v[7] = {&cam.origin, &cam.lower_left_corner, &cam.horizontal, &cam.vertical, &cam.u, &cam.v, &cam.w};
@@ -167,7 +196,8 @@ k_render_h(const __grid_constant__ RenderLaunch p, const uint2 *__restrict__ geo
         }
         if (!__ballot_sync(0xffffffffu, pix >= 0)) break;
 
-        if (pix >= 0) {
+        const bool have = pix >= 0;
+        if (have) {
             if (depth == 0) {   // main.cu:104-106: real_t(i + U) / real_t(max_x) — the sum is float, the quotient __hdiv
                 const hf u = hdiv_(f2h(__fadd_rn((float)pi, xorwow_uniform(rng))), nxh);
                 const hf v = hdiv_(f2h(__fadd_rn((float)pj, xorwow_uniform(rng))), nyh);
@@ -176,7 +206,10 @@ k_render_h(const __grid_constant__ RenderLaunch p, const uint2 *__restrict__ geo
                 npaths++;
             }
             nrays++;
-            const HitH h = OCTREE ? trace_tree_h(pv, geom_h, p.tree, o, d) : trace_list_h(pv, geom_h, o, d);
+        }
+        // closest hit of every lane's ray, one ray at a time by the whole warp (rt_half.cuh coop_trace_h)
+        const HitH h = coop_trace_h<OCTREE>(pv, nt, geom_h, p.tree, have, o, d);
+        if (have) {
             bool sample_done = false;
             vec3h contrib = mkh(zero, zero, zero);
             if (h.idx >= 0) {
@@ -226,7 +259,7 @@ k_render_h(const __grid_constant__ RenderLaunch p, const uint2 *__restrict__ geo
 
 template <bool OCTREE>
 static cudaError_t launch_half(const RenderLaunch &p, const uint2 *geom_h, const uint2 *matl_h, const __half *cam_h, const PairView pv,
-                               int sm_count, cudaStream_t st, int *blocks_out) {
+                               const NodeTab nt, int sm_count, cudaStream_t st, int *blocks_out) {
     auto kern = k_render_h<OCTREE>;
     int per_sm = 0;
     cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kRenderThreads, 0);
@@ -238,7 +271,7 @@ static cudaError_t launch_half(const RenderLaunch &p, const uint2 *geom_h, const
     const uint32_t head = (uint32_t)(blocks * kRenderThreads);
     e = cudaMemcpyAsync(p.work_counter, &head, 4, cudaMemcpyHostToDevice, st);
     if (e != cudaSuccess) return e;
-    kern<<<(unsigned)blocks, kRenderThreads, 0, st>>>(p, geom_h, matl_h, cam_h, pv);
+    kern<<<(unsigned)blocks, kRenderThreads, 0, st>>>(p, geom_h, matl_h, cam_h, pv, nt);
     if (blocks_out) *blocks_out = (int)blocks;
     return cudaGetLastError();
 }
