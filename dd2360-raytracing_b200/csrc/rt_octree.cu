@@ -273,6 +273,12 @@ __global__ void k_vox_finish(const uint32_t *__restrict__ vox_start, uint32_t to
     vox[v] = make_uint2(b, e - b);
 }
 
+// geometry in list order (TreeView::ref_geom / prolog_geom)
+__global__ void k_gather_geom(const float4 *__restrict__ geom, const uint32_t *__restrict__ refs, size_t count, float4 *__restrict__ out) {
+    const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < count) out[k] = geom[refs[k]];
+}
+
 // ---- reference-layout blob ------------------------------------------------------------------------------------
 // bucket (cell m, slot k) exists when k*spl < stored(m); its creator is the sphere with in-cell rank k*spl.
 __global__ void k_leaf_number(const uint32_t *__restrict__ vals, const uint32_t *__restrict__ cell_start, int spl,
@@ -380,7 +386,7 @@ OctreeBuilder::OctreeBuilder() { memset(&d, 0, sizeof d); memset(&cap, 0, sizeof
 OctreeBuilder::~OctreeBuilder() {
     void *ptrs[] = {d.ranges, d.ent_count, d.ent_off, d.keys, d.vals, d.keys_sorted, d.vals_sorted, d.cell_count,
                     d.cell_start, d.ent_cell, d.sph_flag, d.stats, d.node_of_potential, d.counts, d.prep, d.big_refs,
-                    d.vox_count, d.vox_start, d.vox_refs, d.vox, d.cub_tmp, d.leaf_index, d.blob};
+                    d.vox_count, d.vox_start, d.vox_refs, d.vox, d.cub_tmp, d.leaf_index, d.blob, d.ref_geom, d.prolog_geom};
     for (void *p : ptrs) if (p) cudaFree(p);
 }
 
@@ -475,10 +481,15 @@ cudaError_t OctreeBuilder::build(cudaStream_t st, const float4 *geom, const int 
         RT_CUDA(cudaMemsetAsync(d.vox_count, 0, ((size_t)V + 2) * 4, st));
         k_vox_pass<true><<<(n + tb - 1) / tb, tb, 0, st>>>(geom, d.sph_flag, n, grid, d.vox_count, d.vox_start, d.vox_refs);
         k_vox_finish<<<(V + tb - 1) / tb, tb, 0, st>>>(d.vox_start, V, d.vox_refs, d.vox);
+        RT_CUDA(ensure(d.ref_geom, cap.ref_geom, (size_t)total_refs + 1));
+        if (total_refs) k_gather_geom<<<(unsigned)(((size_t)total_refs + tb - 1) / tb), tb, 0, st>>>(geom, d.vox_refs, total_refs, d.ref_geom);
     }
+    if (!d.prolog_geom) RT_CUDA(cudaMalloc(&d.prolog_geom, (kMaxBig + 1) * sizeof(float4)));
+    k_gather_geom<<<1, kMaxBig + 1, 0, st>>>(geom, d.big_refs, (size_t)(1 + nbig), d.prolog_geom);
     RT_CUDA(cudaGetLastError());
     grid.vox = d.vox;
     grid.refs = d.vox_refs;
+    grid.ref_geom = d.ref_geom;
     built = true;
     n_spheres = n;
     return cudaSuccess;
@@ -552,6 +563,7 @@ TreeView OctreeBuilder::view() const {
     v.cell_start = d.cell_start;
     v.cell_cap = 8 * spl;
     v.prolog = d.big_refs;
+    v.prolog_geom = d.prolog_geom;
     v.nprolog = 1 + nbig;
     for (int a = 0; a < 3; a++) for (int i = 0; i < kPlanes; i++) v.planes[a][i] = planes.p[a][i];
     return v;

@@ -60,6 +60,7 @@ private:
         GridPrep *prep;
         uint32_t *big_refs;
         uint32_t *vox_count, *vox_start, *vox_refs;
+        float4 *ref_geom, *prolog_geom;
         uint2 *vox;
         uint8_t *cub_tmp;
         int *leaf_index;
@@ -67,7 +68,7 @@ private:
     } d;
     struct {
         size_t ranges, ent_count, ent_off, keys, vals, keys_sorted, vals_sorted, ent_cell, sph_flag, vox_count, vox_start,
-            vox_refs, vox, cub, blob;
+            vox_refs, vox, cub, blob, ref_geom;
     } cap;
 };
 

@@ -27,7 +27,7 @@
 
 namespace pool {
 
-enum : int { S_TEST = 0, S_CAND, S_ENTER, S_STEP, S_END, S_DIFF, S_DIEL, S_SAMPLE, S_CLAIM, S_DONE };
+enum : int { S_TEST = 0, S_CAND, S_ENTER, S_STEP, S_END, S_DIFF, S_DIEL, S_SAMPLE, S_DONE };
 enum : int {
     F_OX = 0, F_OY, F_OZ, F_DX, F_DY, F_DZ,          // current ray
     F_HT, F_HIDX,                                    // closest candidate so far (F_HIDX: -1 none, -2 "sample ended black")
@@ -37,7 +37,9 @@ enum : int {
     F_R0, F_R1, F_R2, F_R3, F_R4, F_R5,              // XORWOW state
     F_PIX, F_SD,                                     // pixel index; sample number (24 bits) | depth << 24
     F_CM,                                            // CAND: bits 0-3 = chunk positions still to evaluate exactly, bits 4-6 = chunk length
-    F_STATE, NF
+    F_CW0, F_CW1,                                    // the state, stored as its contribution to the warp's packed per-state byte
+                                                     // counters: states 0-3 -> 1 << 8*s in CW0, states 4-7 -> 1 << 8*(s-4) in CW1
+    NF
 };
 constexpr uint32_t kPrologBit = 0x80000000u;
 constexpr int kChunk = 4;
@@ -54,6 +56,11 @@ struct Ctx {
     __device__ __forceinline__ void su(int field, uint32_t v) const { w[field * NC] = v; }
     __device__ __forceinline__ vec3f v3(int field) const { return mk(f(field), f(field + 1), f(field + 2)); }
     __device__ __forceinline__ void sv3(int field, const vec3f v) const { sf(field, v.x); sf(field + 1, v.y); sf(field + 2, v.z); }
+    __device__ __forceinline__ void set_state(int s) const {
+        w[F_CW0 * NC] = s < 4 ? 1u << (8 * s) : 0u;
+        w[F_CW1 * NC] = (s >= 4 && s < 8) ? 1u << (8 * (s - 4)) : 0u;
+    }
+    __device__ __forceinline__ void set_state_walk(int s) const { w[F_CW0 * NC] = 1u << (8 * s); }   // among TEST..STEP (CW1 is already 0)
     __device__ __forceinline__ void load_rng(xorwow &r) const {
         r.d = u(F_R0); r.v0 = u(F_R1); r.v1 = u(F_R2); r.v2 = u(F_R3); r.v3 = u(F_R4); r.v4 = u(F_R5);
     }
@@ -94,9 +101,13 @@ template <int NC>
 __device__ __forceinline__ void begin_walk(const Ctx<NC> c, const RenderLaunch &p) {
     c.sf(F_HT, kTMax);
     c.su(F_HIDX, (uint32_t)-1);
-    c.su(F_K, 0u);
-    c.su(F_E, (uint32_t)p.tree.nprolog | kPrologBit);
-    c.su(F_STATE, S_TEST);
+    if (p.tree.nprolog == 1) {          // no big spheres: the ground test rides along with ENTER
+        c.set_state(S_ENTER);
+    } else {
+        c.su(F_K, 0u);
+        c.su(F_E, (uint32_t)p.tree.nprolog | kPrologBit);
+        c.set_state(S_TEST);
+    }
 }
 
 // ---- TEST: chunks of kChunk candidates of the current list -------------------------------------------------------
@@ -118,7 +129,7 @@ __device__ __forceinline__ void body_test(const Ctx<NC> c, const bool have, cons
         pro = (eraw & kPrologBit) != 0;
     }
     const float a = dot3(d, d), ia = rcp_fast(a);
-    const uint32_t *list = pro ? p.tree.prolog : p.tree.grid.refs;
+    const float4 *list = pro ? p.tree.prolog_geom : p.tree.grid.ref_geom;       // geometry in list order: one dependent load
     const uint32_t last = e - 1;
     bool act = have;
     uint32_t cm = 0;
@@ -126,12 +137,9 @@ __device__ __forceinline__ void body_test(const Ctx<NC> c, const bool have, cons
     for (int it = 0; it < p.tune_sticky; it++) {
         if (act) {
             const uint32_t n = min(e - k, (uint32_t)kChunk);
-            uint32_t idx[kChunk];
             float4 s[kChunk];
 #pragma unroll
-            for (int j = 0; j < kChunk; j++) idx[j] = __ldg(list + min(k + j, last));
-#pragma unroll
-            for (int j = 0; j < kChunk; j++) s[j] = __ldg(p.scene.geom + idx[j]);
+            for (int j = 0; j < kChunk; j++) s[j] = __ldg(list + min(k + j, last));
             uint32_t m = 0;
 #pragma unroll
             for (int j = 0; j < kChunk; j++) m |= (uint32_t)maybe_hit(s[j], o, d, a, ia, ht) << j;
@@ -147,7 +155,7 @@ __device__ __forceinline__ void body_test(const Ctx<NC> c, const bool have, cons
     if (have) {
         c.su(F_K, k);
         if (cm) c.su(F_CM, cm);
-        c.su(F_STATE, cm ? S_CAND : (k < e ? S_TEST : (pro ? S_ENTER : S_STEP)));
+        c.set_state_walk(cm ? S_CAND : (k < e ? S_TEST : (pro ? S_ENTER : S_STEP)));
     }
 }
 
@@ -170,7 +178,7 @@ __device__ __forceinline__ void body_cand(const Ctx<NC> c, const RenderLaunch &p
     if (cm & 15u) { c.su(F_CM, cm); return; }        // more flagged candidates in this chunk: stay in CAND
     k += cm >> 4;
     c.su(F_K, k);
-    c.su(F_STATE, k < e ? S_TEST : (pro ? S_ENTER : S_STEP));
+    c.set_state_walk(k < e ? S_TEST : (pro ? S_ENTER : S_STEP));
 }
 
 template <int NC>
@@ -179,19 +187,28 @@ __device__ __forceinline__ void load_voxel(const Ctx<NC> c, const GridView &g, i
     const uint2 v = __ldg(g.vox + ((size_t)(iz * g.ny + iy) * g.nx + ix));
     c.su(F_K, v.x);
     c.su(F_E, v.x + v.y);
-    c.su(F_STATE, v.y ? S_TEST : S_STEP);
+    c.set_state_walk(v.y ? S_TEST : S_STEP);
 }
 
 template <int NC>
-__device__ __forceinline__ void end_walk(const Ctx<NC> c) { c.su(F_STATE, c.i(F_HIDX) >= 0 ? S_END : S_SAMPLE); }
+__device__ __forceinline__ void end_walk(const Ctx<NC> c) {
+    const bool hit = c.i(F_HIDX) >= 0;
+    c.su(F_CW0, 0u);
+    c.su(F_CW1, hit ? 1u << (8 * (S_END - 4)) : 1u << (8 * (S_SAMPLE - 4)));
+}
 
 // ---- ENTER: clip the ray to the grid, set up the DDA (rt_trace.cuh trace_walk, same expressions) --------------------
 template <int NC>
 __device__ __forceinline__ void body_enter(const Ctx<NC> c, const RenderLaunch &p, TraceCounters &tc) {
     const GridView &g = p.tree.grid;
-    if (g.nx == 0) { end_walk(c); return; }
     const vec3f o = c.v3(F_OX), d = c.v3(F_DX);
-    const float ht = c.f(F_HT);
+    float ht = c.f(F_HT);
+    if (p.tree.nprolog == 1) {          // the ground sphere, unconditionally and first (hitTree :322-332)
+        float t;
+        RT_COUNT(sphere_tests);
+        if (sphere_test(__ldg(p.scene.geom), o, d, dot3(d, d), kTMax, t)) { ht = t; c.sf(F_HT, t); c.su(F_HIDX, 0u); }
+    }
+    if (g.nx == 0) { end_walk(c); return; }
     RayPre r;
     r.o = o; r.d = d; r.a = 0.f;
     r.inv = mk(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
@@ -247,7 +264,7 @@ __device__ __forceinline__ void body_end(const Ctx<NC> c, const RenderLaunch &p,
             hidx = h.idx;
         }
     }
-    c.su(F_STATE, hidx < 0 ? S_SAMPLE : (__ldg(p.scene.tag + hidx) == 2 /* RT_MAT_DIELECTRIC */ ? S_DIEL : S_DIFF));
+    c.set_state(hidx < 0 ? S_SAMPLE : (__ldg(p.scene.tag + hidx) == 2 /* RT_MAT_DIELECTRIC */ ? S_DIEL : S_DIFF));
 }
 
 // ---- DIFF / DIEL: material scatter (rt_shade.cuh scatter), then the next walk or the end of the sample ---------------
@@ -276,7 +293,7 @@ __device__ __forceinline__ void body_shade(const Ctx<NC> c, const RenderLaunch &
         begin_walk(c, p);
     } else {                                         // absorbed (main.cu:64) or depth exhausted (main.cu:74): black
         c.su(F_HIDX, (uint32_t)-2);
-        c.su(F_STATE, S_SAMPLE);
+        c.set_state(S_SAMPLE);
     }
 }
 
@@ -296,34 +313,75 @@ __device__ __forceinline__ void gen_sample(const Ctx<NC> c, const RenderLaunch &
     begin_walk(c, p);
 }
 
-// ---- SAMPLE: a sample ended (sky or black): accumulate, next sample or pixel write-out (main.cu:68-71,107-115) -------
+// ---- SAMPLE: a sample ended (sky or black): accumulate, next sample — or pixel write-out and the claim of the next pixel ----
+// (main.cu:68-71,107-115).  Entered by all 32 lanes (`have` = this lane was handed a context) because the queue pop is
+// compacted per warp with ballot/popc: one atomic for all lanes whose pixel just finished.  F_PIX < 0 marks a context
+// that has no pixel yet (start of the kernel, or a tile position outside the image).
 template <int NC>
-__device__ __forceinline__ void body_sample(const Ctx<NC> c, const RenderLaunch &p, const float inv_ns, uint32_t &nrays, uint32_t &npaths) {
-    vec3f contrib = mk(0, 0, 0);
-    if (c.i(F_HIDX) == -1) {
-        const vec3f att = c.v3(F_AX);
-        const vec3f k = sky(c.v3(F_DX));
-        contrib = mk(mul_(att.x, k.x), mul_(att.y, k.y), mul_(att.z, k.z));
-    }
-    vec3f col = c.v3(F_CX);
-    col = mk(add_(col.x, contrib.x), add_(col.y, contrib.y), add_(col.z, contrib.z));   // main.cu:107
-    const uint32_t s = (c.u(F_SD) & 0xffffffu) + 1u;
-    const int pix = c.i(F_PIX);
-    if (s >= (uint32_t)p.ns_local) {
-        float *out = p.out + (size_t)pix * 3;
-        if (p.finalize) {   // main.cu:111-115
-            out[0] = sqrt_(mul_(col.x, inv_ns));
-            out[1] = sqrt_(mul_(col.y, inv_ns));
-            out[2] = sqrt_(mul_(col.z, inv_ns));
-        } else {
-            out[0] = col.x; out[1] = col.y; out[2] = col.z;
+__device__ __forceinline__ void body_sample(const Ctx<NC> c, const bool have, const RenderLaunch &p, const float inv_ns, const unsigned lt,
+                                            uint32_t &nrays, uint32_t &npaths) {
+    int pix = -1;
+    bool need_pixel = false;
+    xorwow rng;
+    rng.d = rng.v0 = rng.v1 = rng.v2 = rng.v3 = rng.v4 = 0;
+    if (have) {
+        pix = c.i(F_PIX);
+        need_pixel = pix < 0;
+        if (!need_pixel) {
+            vec3f contrib = mk(0, 0, 0);
+            if (c.i(F_HIDX) == -1) {
+                const vec3f att = c.v3(F_AX);
+                const vec3f k = sky(c.v3(F_DX));
+                contrib = mk(mul_(att.x, k.x), mul_(att.y, k.y), mul_(att.z, k.z));
+            }
+            vec3f col = c.v3(F_CX);
+            col = mk(add_(col.x, contrib.x), add_(col.y, contrib.y), add_(col.z, contrib.z));   // main.cu:107
+            const uint32_t s = (c.u(F_SD) & 0xffffffu) + 1u;
+            if (s >= (uint32_t)p.ns_local) {
+                float *out = p.out + (size_t)pix * 3;
+                if (p.finalize) {   // main.cu:111-115
+                    out[0] = sqrt_(mul_(col.x, inv_ns));
+                    out[1] = sqrt_(mul_(col.y, inv_ns));
+                    out[2] = sqrt_(mul_(col.z, inv_ns));
+                } else {
+                    out[0] = col.x; out[1] = col.y; out[2] = col.z;
+                }
+                need_pixel = true;
+            } else {
+                c.sv3(F_CX, col);
+                c.su(F_SD, s);      // depth 0
+                c.load_rng(rng);
+            }
         }
-        c.su(F_STATE, S_CLAIM);
-    } else {
-        c.sv3(F_CX, col);
-        c.su(F_SD, s);      // depth 0
-        xorwow rng;
-        c.load_rng(rng);
+    }
+    // ---- queue pop for the lanes whose context needs a pixel ----
+    const unsigned m = __ballot_sync(0xffffffffu, need_pixel);
+    if (m) {
+        uint32_t qbase = 0;
+        const int leader = __ffs(m) - 1;
+        if ((int)(threadIdx.x & 31u) == leader) qbase = atomicAdd(p.work_counter, (uint32_t)__popc(m));
+        qbase = __shfl_sync(0xffffffffu, qbase, leader);
+        if (need_pixel) {
+            const uint32_t item = qbase + (uint32_t)__popc(m & lt);
+            int pi, pj;
+            pix = -1;
+            if (item >= p.total_items) {
+                c.su(F_CW0, 0u); c.su(F_CW1, 0u);                     // S_DONE
+                return;
+            }
+            if (!item_to_pixel(p, item, pi, pj)) {                   // a tile position outside the image: pop again next time
+                c.su(F_PIX, (uint32_t)-1);
+                c.set_state(S_SAMPLE);
+                return;
+            }
+            pix = pj * p.nx + pi;
+            c.su(F_PIX, (uint32_t)pix);
+            c.su(F_SD, 0u);
+            c.sv3(F_CX, mk(0, 0, 0));
+            pixel_stream(p, pix, rng);
+        }
+    }
+    if (have && pix >= 0) {
         gen_sample(c, p, pix, rng, nrays, npaths);
         c.store_rng(rng);
     }
@@ -343,7 +401,11 @@ __global__ void __launch_bounds__(kRenderThreads, MINB) k_render_pool(const __gr
     const float inv_ns = __fdiv_rn(1.0f, (float)p.ns_total);   // vec3.h:137-144: k = 1.0/t
 
 #pragma unroll
-    for (int j = 0; j < C; j++) W[F_STATE * NC + lane + 32 * j] = S_CLAIM;
+    for (int j = 0; j < C; j++) {       // every context starts in SAMPLE without a pixel: its first visit pops one
+        const Ctx<NC> c0{W + lane + 32 * j};
+        c0.su(F_PIX, (uint32_t)-1);
+        c0.set_state(S_SAMPLE);
+    }
     __syncwarp();
 
     uint32_t nrays = 0, npaths = 0;
@@ -355,36 +417,33 @@ __global__ void __launch_bounds__(kRenderThreads, MINB) k_render_pool(const __gr
     uint32_t sched_rounds[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, sched_ctx[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
 #endif
     while (true) {
-        // ---- 1. contexts per state: byte counters packed in three words, summed over the warp ----
-        uint32_t st[C];
-        uint32_t w0 = 0, w1 = 0, w2 = 0;
+        // ---- 1. contexts per state: each context stores its own contribution to two words of packed byte counters ----
+        uint32_t c0[C], c1[C];
+        uint32_t w0 = 0, w1 = 0;
 #pragma unroll
         for (int j = 0; j < C; j++) {
-            const uint32_t s = W[F_STATE * NC + lane + 32 * j];
-            st[j] = s;
-            const uint32_t one = 1u << ((s & 3u) * 8u);
-            if (s < 4u) w0 += one;
-            else if (s < 8u) w1 += one;
-            else if (s == (uint32_t)S_CLAIM) w2 += 1u;
+            c0[j] = W[F_CW0 * NC + lane + 32 * j];
+            c1[j] = W[F_CW1 * NC + lane + 32 * j];
+            w0 += c0[j];
+            w1 += c1[j];
         }
         w0 = __reduce_add_sync(full, w0);
         w1 = __reduce_add_sync(full, w1);
-        w2 = __reduce_add_sync(full, w2);
-        if (!(w0 | w1 | w2)) break;
+        if (!(w0 | w1)) break;
+
         // ---- 2. the state with the most waiting contexts (ties: the earlier, cheaper state): lane s holds the count
         //         of state s, one warp-wide max of (count << 4 | 15 - s) ----
         int best;
         {
-            const uint32_t word = lane < 4u ? w0 : (lane < 8u ? w1 : w2);
-            const uint32_t key = lane <= (uint32_t)S_CLAIM ? ((word >> ((lane & 3u) * 8u)) & 255u) << 4 | (15u - lane) : 0u;
+            const uint32_t word = lane < 4u ? w0 : w1;
+            const uint32_t key = lane < 8u ? ((word >> ((lane & 3u) * 8u)) & 255u) << 4 | (15u - lane) : 0u;
             best = 15 - (int)(__reduce_max_sync(full, key) & 15u);
         }
-
         if (++rounds > p.max_rounds) {          // watchdog: a scheduling bug must never hang the GPU; the host reports it
             if (lane == 0) {
                 atomicAdd(p.counters + 7, 1ull);
                 p.counters[5] = (unsigned long long)w0 << 32 | w1;
-                p.counters[6] = (unsigned long long)w2 << 40 | (unsigned long long)best << 32 | rounds;
+                p.counters[6] = (unsigned long long)best << 32 | rounds;
             }
             break;
         }
@@ -392,10 +451,12 @@ __global__ void __launch_bounds__(kRenderThreads, MINB) k_render_pool(const __gr
         // ---- 3. hand up to 32 contexts of that state to the lanes ----
         int id = -1;
         {
+            const uint32_t sh = (uint32_t)(best & 3) * 8u;
+            const bool hi = best >= 4;
             uint32_t base = 0;
 #pragma unroll
             for (int j = 0; j < C; j++) {
-                const bool is = st[j] == (uint32_t)best;
+                const bool is = (((hi ? c1[j] : c0[j]) >> sh) & 1u) != 0u;
                 const unsigned m = __ballot_sync(full, is);
                 const uint32_t r = base + (uint32_t)__popc(m & lt);
                 if (is && r < 32u) stage[r] = lane + 32u * j;
@@ -411,40 +472,14 @@ __global__ void __launch_bounds__(kRenderThreads, MINB) k_render_pool(const __gr
         }
         const Ctx<NC> c{W + (id < 0 ? 0 : id)};
 
-        // ---- 4. the one body of that state ----
-        switch (best) {
-            case S_TEST:   body_test<NC>(c, id >= 0, p, tc); break;
-            case S_CAND:   if (id >= 0) body_cand<NC>(c, p, tc); break;
-            case S_ENTER:  if (id >= 0) body_enter<NC>(c, p, tc); break;
-            case S_STEP:   if (id >= 0) body_step<NC>(c, p, tc); break;
-            case S_END:    if (id >= 0) body_end<NC>(c, p, planes, tc); break;
-            case S_DIFF:
-            case S_DIEL:   if (id >= 0) body_shade<NC>(c, p, nrays); break;
-            case S_SAMPLE: if (id >= 0) body_sample<NC>(c, p, inv_ns, nrays, npaths); break;
-            default: {     // S_CLAIM: ballot/popc-compacted queue pop, one atomic per warp
-                const unsigned m = __ballot_sync(full, id >= 0);
-                uint32_t qbase = 0;
-                const int leader = __ffs(m) - 1;
-                if ((int)lane == leader) qbase = atomicAdd(p.work_counter, (uint32_t)__popc(m));
-                qbase = __shfl_sync(full, qbase, leader);
-                if (id >= 0) {
-                    const uint32_t item = qbase + (uint32_t)__popc(m & lt);
-                    int pi, pj;
-                    if (item >= p.total_items) {
-                        c.su(F_STATE, S_DONE);
-                    } else if (item_to_pixel(p, item, pi, pj)) {
-                        const int pix = pj * p.nx + pi;
-                        c.su(F_PIX, (uint32_t)pix);
-                        c.su(F_SD, 0u);
-                        c.sv3(F_CX, mk(0, 0, 0));
-                        xorwow rng;
-                        pixel_stream(p, pix, rng);
-                        gen_sample<NC>(c, p, pix, rng, nrays, npaths);
-                        c.store_rng(rng);
-                    }                                   // else: a tile position outside the image; claim again
-                }
-            }
-        }
+        // ---- 4. the one body of that state (most frequent first) ----
+        if (best == S_TEST) body_test<NC>(c, id >= 0, p, tc);
+        else if (best == S_CAND) { if (id >= 0) body_cand<NC>(c, p, tc); }
+        else if (best == S_STEP) { if (id >= 0) body_step<NC>(c, p, tc); }
+        else if (best == S_ENTER) { if (id >= 0) body_enter<NC>(c, p, tc); }
+        else if (best == S_END) { if (id >= 0) body_end<NC>(c, p, planes, tc); }
+        else if (best == S_SAMPLE) body_sample<NC>(c, id >= 0, p, inv_ns, lt, nrays, npaths);
+        else { if (id >= 0) body_shade<NC>(c, p, nrays); }       // S_DIFF, S_DIEL
         __syncwarp();
     }
 

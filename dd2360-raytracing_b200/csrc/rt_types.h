@@ -28,7 +28,9 @@ struct CameraData {
 //       that STORES the sphere (i.e. was not dropped on bucket overflow) pass the line/AABB slab test?
 // so the octree is never walked: only its per-sphere cell lists (VisView) and its slab planes are needed.
 constexpr int kMaxBig = 64;                 // big spheres tested directly (beyond that they go into the grid)
-constexpr float kBigRadiusFrac = 0.25f;     // big: radius > this x longest level-3 cell edge
+constexpr float kBigRadiusFrac = 0.25f;     // big: radius > this x longest level-3 cell edge.  Measured: putting the RTIOW
+                                            // r = 1 spheres into the grid stretches its box from the 0.2-high carpet to y = 2 and
+                                            // costs 5x (49 voxel steps per ray through empty space) — they stay in the prolog list
 constexpr uint16_t kEntDropped = 0x8000;    // VisView::ent_cell flag: entry dropped by the reference ("Leaf nodes full")
 
 struct GridView {
@@ -37,6 +39,8 @@ struct GridView {
     int nx, ny, nz;             // 0 = no grid
     const uint2 *vox;           // {first reference, reference count} per voxel
     const uint32_t *refs;       // sphere indices, ascending inside a voxel
+    const float4 *ref_geom;     // geom[refs[k]] copied into list order: the pooled kernel streams candidates with ONE
+                                // dependent load instead of two (16 B per reference; 96 MB at C3, 4.9 GB at C5)
 };
 
 struct VisView {
@@ -56,6 +60,7 @@ struct TreeView {
     VisView vis;
     const uint32_t *prolog;     // first candidate list of every ray: the ground sphere (index 0, tested unconditionally by
     int nprolog;                // hitTree :322-332), then the big spheres in ascending order; nprolog = 1 + nbig
+    const float4 *prolog_geom;  // their geometry in list order
     float planes[3][kPlanes];   // slab plane coordinates per axis (exact floats of the reference subdivision)
     // the reference's own cell lists (USE_FP16 path walks these): cell m (9-bit Morton id) was offered
     // cell_list[cell_start[m] .. cell_start[m+1]) in ascending sphere order and stored the first cell_cap = 8*SPL of them

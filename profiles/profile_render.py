@@ -33,7 +33,7 @@ if len(sys.argv) > 4 and sys.argv[4] == "counters":
     print("counters (1 spp): sphere_tests/ray", round(st["sphere_tests"] / st["rays"], 2), "visibility line tests/ray",
           round(st["node_tests"] / st["rays"], 3), "rays/path", round(st["rays"] / st["paths"], 3))
     dc = rti.debug_counters()
-    names = ["TEST", "CAND", "ENTER", "STEP", "END", "DIFF", "DIEL", "SAMPLE", "CLAIM", "DONE"]
+    names = ["TEST", "CAND", "ENTER", "STEP", "END", "DIFF", "DIEL", "SAMPLE", "DONE", "-"]
     if dc[8:18].sum():
         print("pool scheduler, per state: rounds/kray, contexts/round, visits/ray")
         for s_, nm in enumerate(names):
