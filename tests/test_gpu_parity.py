@@ -381,3 +381,24 @@ def test_fp16_octree_and_flat_list_agree(rt, pkg):
     print("fp16 tree vs list identical:", float((a == b).all(axis=2).mean()), sa["rays"], sb["rays"])
     with pytest.raises(pkg.RtError, match="precision"):
         rt.render(8, 8, 1, use_octree=True)                                # FP32 render on an FP16 tree
+
+
+def test_dropin_class_surface_renders_the_same_frame(rt, pkg, O, tmp_path):
+    """include/rt_dropin.h end to end: a C++ program builds the world with sphere / hitable_list / materials / camera,
+    uploads it through rt_upload_world + rt_apply_camera and renders; same frame as the generated scene."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe, out = str(tmp_path / "render_dropin"), str(tmp_path / "fb.bin")
+    lib_dir = os.path.dirname(pkg.LIB_PATH)
+    subprocess.run(["g++", "-std=c++17", "-O2", "-I", os.path.join(root, "include"), os.path.join(root, "tests", "dropin", "render_dropin.cpp"),
+                    "-o", exe, f"-L{lib_dir}", "-lrt_b200", f"-Wl,-rpath,{lib_dir}"], check=True)
+    sph, _ = O.create_world(488)
+    lines = [str(len(sph))] + [" ".join([float(s["cx"]).hex(), float(s["cy"]).hex(), float(s["cz"]).hex(), float(s["radius"]).hex(),
+                                         str(int(s["mat"])), float(s["ax"]).hex(), float(s["ay"]).hex(), float(s["az"]).hex(),
+                                         float(s["param"]).hex()]) for s in sph]
+    subprocess.run([exe, out], input="\n".join(lines) + "\n", text=True, check=True)
+    got = np.fromfile(out, dtype=np.float32).reshape(48, 64, 3)
+    rt.create_world(488, 0.1)
+    rt.build_octree(30)
+    want, _ = rt.render(64, 48, 2, use_octree=True)
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
