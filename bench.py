@@ -318,6 +318,16 @@ def main():
                             "peak_source": "measured here: dense FFMA microbenchmark (rt_ffma_peak); MEASURED_PEAKS.json has no FP32 figure",
                             "note": "FP32 issue is the bounding unit (SURVEY §8d); HBM traffic is the 12 B/pixel frame only"}
         rti.close()
+        # the same kernel against the HBM roofline, for the record: algorithmic bytes = the 12 B/pixel frame
+        hbm_peak = None
+        try:
+            hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs")
+        except Exception:
+            pass
+        hbm_peak = hbm_peak or 6554.2
+        hbm_achieved = (nx * ny * 12) / (km * 1e-3) / 1e9
+        line["roofline_hbm"] = {"bound": "hbm", "achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_achieved / hbm_peak,
+                                "traffic": traffic, "note": "not the bounding unit: the path writes one frame and re-reads an L2-resident scene"}
     except Exception as e:                                     # the roofline probe must never cost the bench line
         line["roofline"] = {"bound": "fp32", "error": str(e)}
 
