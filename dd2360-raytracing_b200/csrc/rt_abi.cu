@@ -37,6 +37,8 @@ struct rt_context {
     CameraData cam_host{};
     // octree
     OctreeBuilder *octree = nullptr;
+    OctreeBuilder *list_accel = nullptr;     // USE_OCTREE off: the same grid over ALL spheres answers hitable_list::hit
+    bool list_accel_valid = false;
     float grid_density = 4.0f;
     int default_variant = 0;       // RT_RENDER_VARIANT: kernel A/B override for whole test runs (0 = automatic)
     // render scratch
@@ -106,6 +108,7 @@ extern "C" int rt_create(int device, rt_context **out) {
     }
     ctx->stream = ctx->own_stream;
     ctx->octree = new OctreeBuilder();
+    ctx->list_accel = new OctreeBuilder();
     const char *dens = getenv("RT_GRID_DENSITY");
     if (dens && atof(dens) > 0) ctx->grid_density = (float)atof(dens);
     const char *var = getenv("RT_RENDER_VARIANT");
@@ -119,6 +122,7 @@ extern "C" void rt_destroy(rt_context *ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     delete ctx->octree;
+    delete ctx->list_accel;
     cudaFree(ctx->geom); cudaFree(ctx->matl); cudaFree(ctx->tag); cudaFree(ctx->cam_dev);
     cudaFree(ctx->work_counter); cudaFree(ctx->counters); cudaFree(ctx->scratch_fb);
     cudaFree(ctx->skip_tables); cudaFree(ctx->seed_states);
@@ -238,6 +242,7 @@ extern "C" int rt_scene_generate_ex(rt_context *ctx, int n, float radius, int pr
     CK(cudaSetDevice(ctx->device));
     ctx->n = n;
     ctx->half_valid = false;          // the half copy of the scene (USE_FP16 path) is derived on demand
+    ctx->list_accel_valid = false;
     generate_world(n, radius, precision == RT_PREC_FP16, ctx->host_scene);
     return upload_scene(ctx);
 }
@@ -247,6 +252,7 @@ extern "C" int rt_scene_upload(rt_context *ctx, const rt_sphere_desc *spheres, i
     CK(cudaSetDevice(ctx->device));
     ctx->n = n;
     ctx->half_valid = false;          // the half copy of the scene (USE_FP16 path) is derived on demand
+    ctx->list_accel_valid = false;
     ctx->host_scene.assign(spheres, spheres + n);
     for (auto &s : ctx->host_scene)
         if (s.mat == RT_MAT_METAL && !(s.param < 1.0f)) s.param = 1.0f;   // metal::metal clamps fuzz (material.h:67)
@@ -436,6 +442,18 @@ static int do_render(rt_context *ctx, const rt_render_args *a, float *out_dev, b
     memset(&p, 0, sizeof p);
     p.scene.geom = ctx->geom; p.scene.matl = ctx->matl; p.scene.tag = ctx->tag; p.scene.n = ctx->n;
     if (a->use_octree) p.tree = ctx->octree->view();
+    // flat-list mode: hitable_list::hit is "closest over all spheres"; above a few hundred spheres the grid answers it
+    // with a few dozen tests instead of N (the result is the same minimum; variant 20 forces the N-test sweep)
+    bool list_grid = false;
+    if (!a->use_octree && a->precision == RT_PREC_FP32 && ctx->n >= kListGridMinSpheres && a->tune[1] != 20 &&
+        ctx->host_scene[0].mat != RT_MAT_NONE) {      // (the prolog tests sphere 0 unconditionally; an undefined slot 0 must stay unhittable)
+        if (!ctx->list_accel_valid) {
+            CK(ctx->list_accel->build(ctx->stream, ctx->geom, ctx->tag, ctx->n, 30, ctx->grid_density, false, true));
+            ctx->list_accel_valid = true;
+        }
+        p.tree = ctx->list_accel->view();
+        list_grid = true;
+    }
     p.nx = a->nx; p.ny = a->ny;
     p.ns_total = a->ns;
     p.ns_local = a->ns;
@@ -518,7 +536,7 @@ static int do_render(rt_context *ctx, const rt_render_args *a, float *out_dev, b
         CK(launch_render_half(p, a->use_octree != 0, ctx->geom_h, ctx->matl_h, ctx->cam_h, ctx->half_pairs, ctx->prop.multiProcessorCount,
                               ctx->stream, &blocks));
     } else {
-        CK(launch_render(p, a->use_octree != 0, ctx->prop.multiProcessorCount, ctx->prop.sharedMemPerBlockOptin, ctx->stream, &blocks));
+        CK(launch_render(p, a->use_octree != 0 || list_grid, ctx->prop.multiProcessorCount, ctx->prop.sharedMemPerBlockOptin, ctx->stream, &blocks));
     }
     CK(cudaEventRecord(ctx->ev1, ctx->stream));
     if (stats) {

@@ -390,9 +390,11 @@ OctreeBuilder::~OctreeBuilder() {
     for (void *p : ptrs) if (p) cudaFree(p);
 }
 
-cudaError_t OctreeBuilder::build(cudaStream_t st, const float4 *geom, const int *tag, int n, int spl_, float density, bool fp16_) {
+cudaError_t OctreeBuilder::build(cudaStream_t st, const float4 *geom, const int *tag, int n, int spl_, float density, bool fp16_,
+                                 bool all_spheres_) {
     spl = spl_;
     fp16 = fp16_;
+    all_spheres = all_spheres_;
     built = false;
     blob_valid = false;
     RT_CUDA(ensure(d.ranges, cap.ranges, (size_t)n + 1));
@@ -446,6 +448,7 @@ cudaError_t OctreeBuilder::build(cudaStream_t st, const float4 *geom, const int 
     for (int k = 0; k < 3; k++) { init.lo[k] = 0xffffffffu; init.hi[k] = 0u; }
     RT_CUDA(cudaMemcpyAsync(d.prep, &init, sizeof init, cudaMemcpyHostToDevice, st));
     const float big_r = kBigRadiusFrac * fmaxf(planes.p[0][1] - planes.p[0][0], fmaxf(planes.p[1][1] - planes.p[1][0], planes.p[2][1] - planes.p[2][0]));
+    if (all_spheres) RT_CUDA(cudaMemsetAsync(d.sph_flag + 1, 1, (size_t)n - 1, st));     // every sphere but the ground (prolog[0])
     k_grid_prep<<<(n + tb - 1) / tb, tb, 0, st>>>(geom, tag, n, big_r, d.sph_flag, d.prep);
     GridPrep prep;
     RT_CUDA(cudaMemcpyAsync(&prep, d.prep, sizeof prep, cudaMemcpyDeviceToHost, st));
@@ -562,6 +565,7 @@ TreeView OctreeBuilder::view() const {
     v.cell_list = d.vals_sorted;
     v.cell_start = d.cell_start;
     v.cell_cap = 8 * spl;
+    v.check_visibility = all_spheres ? 0 : 1;
     v.prolog = d.big_refs;
     v.prolog_geom = d.prolog_geom;
     v.nprolog = 1 + nbig;

@@ -29,7 +29,10 @@ public:
 
     // replaces D2H(spheres) + buildOctree + H2D(Octree), main.cu:405-415
     // fp16: the USE_FP16 build of the reference (half-rounded scene, half arithmetic in `intersects`)
-    cudaError_t build(cudaStream_t st, const float4 *geom, const int *tag, int n, int spl, float density, bool fp16 = false);
+    // all_spheres: grid over EVERY defined sphere, wherever it lies (the flat-list mode's candidate set), not only over
+    // the ones some octree cell stores
+    cudaError_t build(cudaStream_t st, const float4 *geom, const int *tag, int n, int spl, float density, bool fp16 = false,
+                      bool all_spheres = false);
     static size_t reference_bytes(int spl);
     // the tree in the reference's own layout (acceleration_structure.h:23-61), assembled on the GPU on demand
     cudaError_t export_reference(cudaStream_t st, void *host_blob, size_t bytes);
@@ -39,7 +42,7 @@ public:
     // host == nullptr
     size_t debug_read(cudaStream_t st, int which, void *host, size_t cap) const;
 
-    bool built = false, blob_valid = false, fp16 = false;
+    bool built = false, blob_valid = false, fp16 = false, all_spheres = false;
     int spl = 0, n_spheres = 0, leaf_count_h = 0;
     int nbig = 0;
     uint32_t prolog_h[kMaxBig + 1];   // staging for the async upload (must outlive build())

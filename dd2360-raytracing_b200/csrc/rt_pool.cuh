@@ -254,7 +254,7 @@ __device__ __forceinline__ void body_step(const Ctx<NC> c, const RenderLaunch &p
 template <int NC>
 __device__ __forceinline__ void body_end(const Ctx<NC> c, const RenderLaunch &p, const float *planes, TraceCounters &tc) {
     int hidx = c.i(F_HIDX);
-    if (hidx > 0) {       // the ground sphere (index 0) is tested unconditionally by the reference
+    if (hidx > 0 && p.tree.check_visibility) {       // the ground sphere (index 0) is tested unconditionally by the reference
         const vec3f o = c.v3(F_OX), d = c.v3(F_DX);
         int last_ok = -1;
         if (!sphere_visible(p.tree.vis, planes, hidx, o, d, last_ok, tc)) {

@@ -223,7 +223,7 @@ RT_HD Hit trace_walk(const SceneView &sc, const TreeView &tv, const float *plane
 RT_HD Hit trace_tree(const SceneView &sc, const TreeView &tv, const float *planes, const vec3f o, const vec3f d,
                     TraceCounters &tc) {
     Hit h = trace_walk<false>(sc, tv, planes, o, d, tc);
-    if (h.idx > 0) {                        // the ground sphere (index 0) is tested unconditionally by the reference
+    if (h.idx > 0 && tv.check_visibility) {  // the ground sphere (index 0) is tested unconditionally by the reference
         int last_ok = -1;
         if (!sphere_visible(tv.vis, planes, h.idx, o, d, last_ok, tc)) h = trace_walk<true>(sc, tv, planes, o, d, tc);
     }

@@ -67,6 +67,9 @@ struct TreeView {
     const uint32_t *cell_list;
     const uint32_t *cell_start;
     int cell_cap;
+    // 1: hitTree semantics — a candidate counts only if a cell that stores it is crossed by the ray's line (VisView);
+    // 0: hitable_list semantics — every sphere is a candidate (the grid then serves the flat-list mode, USE_OCTREE off)
+    int check_visibility;
 };
 
 }  // namespace rt

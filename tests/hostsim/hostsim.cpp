@@ -122,6 +122,7 @@ static void view_of(HostTree &T, TreeView &tv) {
     tv.grid.vox = T.vox.data(); tv.grid.refs = T.refs.data();
     tv.vis.ent_off = T.ent_off.data(); tv.vis.ent_cell = T.ent_cell.data();
     tv.prolog = T.prolog.data(); tv.nprolog = (int)T.prolog.size();
+    tv.check_visibility = 1;
     memcpy(tv.planes, T.planes, sizeof tv.planes);
 }
 
@@ -233,6 +234,7 @@ int hs_render_with_tree(const hs_sphere *sph, int n, const float *camera22, cons
     std::vector<uint32_t> prolog(1, 0u);
     prolog.insert(prolog.end(), static_cast<const uint32_t *>(big_refs), static_cast<const uint32_t *>(big_refs) + nbig);
     tv.prolog = prolog.data(); tv.nprolog = (int)prolog.size();
+    tv.check_visibility = 1;
     return render_core(sph, n, camera22, nullptr, p, 0.f, fb_gamma, nullptr, ctr_out, nullptr, &tv);
 }
 

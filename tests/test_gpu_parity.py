@@ -184,6 +184,16 @@ def test_upstream_seeding_spp_shards_use_disjoint_subsequences(rt, pkg):
     assert torch.equal(a, b) and not torch.equal(b, c)
 
 
+@pytest.mark.parametrize("n", [488, 6000, 20000])
+def test_flat_list_grid_and_sweep_kernels_agree(rt, n):
+    """USE_OCTREE off: the default answers hitable_list::hit through the grid over all spheres; variant 20 forces the
+    N-tests-per-ray sweep (shared-memory staged by TMA up to ~14 k spheres, global memory above).  Same frame."""
+    rt.create_world(n, 0.1)
+    a, sa = rt.render(64, 40, 2, use_octree=False)
+    b, sb = rt.render(64, 40, 2, use_octree=False, variant=20)
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32)) and sa["rays"] == sb["rays"]
+
+
 def test_metal_fuzz_is_clamped_like_the_reference_constructor(rt, pkg):
     sph = np.zeros(8, dtype=pkg.SPHERE_DTYPE)
     sph[0] = (0, -1000, -1, 1000, 0, 0.5, 0.5, 0.5, 0)
