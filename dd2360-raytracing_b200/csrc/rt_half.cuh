@@ -475,5 +475,178 @@ __device__ __forceinline__ HitH coop_trace_h(const PairView pv, const NodeTab nt
     return mine;
 }
 
+// ---- warp-cooperative closest hit, second form: filter and roots in separate converged phases -----------------------------------
+// coop_trace_h above runs the exact root evaluation inside the scan loop, under `if (any of my two discriminants > 0)`.
+// About 6 % of the candidates of a passing cell have a positive discriminant, so with 64 candidates per warp iteration
+// that branch is taken by a few lanes in nearly every iteration and its ~150 instructions (two scalar sphere tests with
+// IEEE sqrt / div) dominate the ~20 of the filter.  Here the scan only FILTERS — four pair loads in flight per lane,
+// packed discriminants — and pushes the positives (their scan-order keys) into a 128-entry ring in shared memory with
+// ballot/popc ranks; whenever 32 keys are queued, the 32 lanes evaluate one candidate each, converged.  The octree nodes
+// are also tested compacted: root + level 1 in one warp step, level 2 in one, level 3 only for the children of the
+// level-2 nodes that passed (four parents per step).  The result is the same lexicographic minimum of (accepted root,
+// scan-order key), which does not depend on the order candidates are evaluated in.
+constexpr uint32_t kPairPad = 128;      // every pair list is padded with NaN pairs to a multiple of this (k_pairs_fill)
+struct CoopSmem {
+    uint32_t ring[512];       // scan-order keys of candidates with a positive discriminant (0: the ground sphere)
+    uint32_t plist[64];       // level-2 nodes that passed, compacted
+    uint32_t tail;            // ring write position (shared atomic: the order of the keys in the ring does not matter)
+    uint32_t pad_[3];
+};
+
+__device__ __forceinline__ void coop_eval_h(const PairView pv, const uint2 *geom_h, const uint32_t key, const vec3h o, const vec3h d, const hf a,
+                                            BestH &best) {
+    SphereH s;
+    if (key == 0u) {
+        s = load_sphere_h(geom_h, 0);
+    } else {
+        const uint32_t k = (key - 1u) >> 1, sel = ((key - 1u) & 1u) * 16u;
+        const uint4 g = __ldg(pv.geom + k);
+        s.c = mkh(__ushort_as_half((unsigned short)(g.x >> sel)), __ushort_as_half((unsigned short)(g.y >> sel)),
+                  __ushort_as_half((unsigned short)(g.z >> sel)));
+        s.r = __ushort_as_half((unsigned short)(g.w >> sel));
+    }
+    hf t;
+    if (sphere_test_h(s, o, d, a, f2h(3.402823466e+38f), t)) best_update(best, t, key);
+}
+
+// evaluate the queued candidates 32 at a time, one per lane (everything that is left when `flush`); call converged
+__device__ __forceinline__ void coop_drain_h(CoopSmem &sm, const PairView pv, const uint2 *geom_h, uint32_t &head, const bool flush,
+                                             const unsigned lane, const vec3h o, const vec3h d, const hf a, BestH &best) {
+    __syncwarp();
+    const uint32_t tail = *reinterpret_cast<volatile uint32_t *>(&sm.tail);
+    while (tail - head >= 32u || (flush && tail != head)) {
+        const uint32_t left = tail - head;
+        if (lane < left) coop_eval_h(pv, geom_h, sm.ring[(head + lane) & 511u], o, d, a, best);
+        head += left < 32u ? left : 32u;
+    }
+    __syncwarp();
+}
+
+// all 32 lanes filter pairs [pb, pe) of one list (pe - pb a multiple of kPairPad) for the broadcast ray (o, d)
+__device__ __forceinline__ void coop_filter_h(CoopSmem &sm, const PairView pv, const uint2 *geom_h, const uint32_t pb, const uint32_t pe,
+                                              const unsigned lane, const vec3h o, const vec3h d, const hf a, uint32_t &head, BestH &best) {
+    const unsigned full = 0xffffffffu;
+    const __half2 ox = __half2half2(vx(o)), oy = __half2half2(vy(o)), oz = __half2half2(o.z);
+    const __half2 dx = __half2half2(vx(d)), dy = __half2half2(vy(d)), dz = __half2half2(d.z);
+    const __half2 a2 = __half2half2(a), zero2 = __float2half2_rn(0.0f);
+    for (uint32_t base = pb + lane; base < pe; base += kPairPad) {
+        const uint4 *ptr = pv.geom + base;
+        uint4 g[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) g[i] = __ldg(ptr + 32 * i);
+        uint32_t mine = 0u;       // bit i: low sphere of pair i has a positive discriminant; bit 16 + i: its high sphere
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const __half2 cx = *reinterpret_cast<const __half2 *>(&g[i].x), cy = *reinterpret_cast<const __half2 *>(&g[i].y);
+            const __half2 cz = *reinterpret_cast<const __half2 *>(&g[i].z), r = *reinterpret_cast<const __half2 *>(&g[i].w);
+            const __half2 ocx = __hsub2_rn(ox, cx), ocy = __hsub2_rn(oy, cy), ocz = __hsub2_rn(oz, cz);            // sphere.h:18
+            const __half2 b = __hfma2(ocz, dz, __hfma2(ocx, dx, __hmul2_rn(ocy, dy)));                               // :20
+            const __half2 c = __hfma2(__hneg2(r), r, __hfma2(ocz, ocz, __hfma2(ocx, ocx, __hmul2_rn(ocy, ocy))));   // :21
+            const __half2 disc = __hfma2(b, b, __hneg2(__hmul2_rn(a2, c)));                                          // :22
+            mine |= __hgt2_mask(disc, zero2) & (0x00010001u << i);    // 0xffff per half where positive (NaN: 0)
+        }
+        if (__any_sync(full, mine != 0u)) {
+            while (mine) {                                           // ~0.5 positives per lane and step
+                const uint32_t bit = (uint32_t)__ffs((int)mine) - 1u;
+                mine &= mine - 1u;
+                sm.ring[atomicAdd(&sm.tail, 1u) & 511u] = 2u * (base + 32u * (bit & 15u)) + 1u + (bit >> 4);
+            }
+            coop_drain_h(sm, pv, geom_h, head, false, lane, o, d, a, best);
+        }
+    }
+}
+
+template <bool OCTREE>
+__device__ __forceinline__ HitH coop_trace_h2(CoopSmem &sm, const PairView pv, const NodeTab nt, const uint2 *geom_h, const TreeView &tv,
+                                              const bool have_ray, const vec3h o, const vec3h d) {
+    const unsigned full = 0xffffffffu;
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned lt = (1u << lane) - 1u;
+    HitH mine;
+    mine.t = f2h(3.402823466e+38f);
+    mine.idx = -1;
+    const float *P = &tv.planes[0][0];
+    uint32_t n1 = 0, n2 = 0;
+    if (OCTREE) { n1 = __ldg(nt.count); n2 = __ldg(nt.count + 1); }
+    unsigned todo = __ballot_sync(full, have_ray);
+    while (todo) {
+        const int r = __ffs(todo) - 1;
+        todo &= todo - 1u;
+        vec3h ro, rd;
+        {
+            const uint32_t oxy = __shfl_sync(full, *reinterpret_cast<const uint32_t *>(&o.xy), r);
+            const uint32_t dxy = __shfl_sync(full, *reinterpret_cast<const uint32_t *>(&d.xy), r);
+            const __half2 zz = __halves2half2(o.z, d.z);
+            const uint32_t ozdz = __shfl_sync(full, *reinterpret_cast<const uint32_t *>(&zz), r);
+            ro.xy = *reinterpret_cast<const __half2 *>(&oxy);
+            rd.xy = *reinterpret_cast<const __half2 *>(&dxy);
+            const __half2 z2 = *reinterpret_cast<const __half2 *>(&ozdz);
+            ro.z = __low2half(z2);
+            rd.z = __high2half(z2);
+        }
+        const hf a = dot3h(rd, rd);
+        BestH best;
+        best.t = 0xffffffffu;
+        best.order = 0xffffffffu;
+        uint32_t head = *reinterpret_cast<volatile uint32_t *>(&sm.tail);       // the ring is empty between rays
+        if (!OCTREE) {
+            coop_filter_h(sm, pv, geom_h, __ldg(pv.start), __ldg(pv.start + 1), lane, ro, rd, a, head, best);   // hitable_list.h:16-31
+        } else {
+            if (lane == 0) { sm.ring[head & 511u] = 0u; sm.tail = head + 1u; }     // the ground sphere, tested unconditionally (:322-332)
+            // root (lane 0) and the level-1 nodes (lanes 1..n1) in one step
+            uint2 e = make_uint2(0u, 0u);
+            if (lane >= 1u && lane <= n1) e = __ldg(nt.ent + lane - 1u);
+            const unsigned m01 = __ballot_sync(full, lane <= n1 && node_pass_h(P, e, lane ? 1 : 0, ro, rd));
+            const unsigned m1 = (n1 > 0 && (m01 & 1u)) ? m01 >> 1 : 0u;
+            uint32_t np = 0;
+            if (m1) {
+                for (uint32_t b2 = 0; b2 < n2; b2 += 32u) {     // level 2 (28 nodes in every scene of the reference's generator: one step)
+                    const uint32_t j = b2 + lane;
+                    const uint2 e2 = j < n2 ? __ldg(nt.ent + 8 + j) : make_uint2(0u, 0u);
+                    const bool ok = j < n2 && ((m1 >> (e2.y & 0xffffu)) & 1u) && node_pass_h(P, e2, 2, ro, rd);
+                    const unsigned m2 = __ballot_sync(full, ok);
+                    if (ok) sm.plist[np + __popc(m2 & lt)] = j;
+                    np += __popc(m2);
+                }
+            }
+            __syncwarp();
+            for (uint32_t b3 = 0; b3 < np; b3 += 4u) {          // level 3: the children of four passing level-2 nodes per step
+                const uint32_t slot = b3 + (lane >> 3);
+                uint2 e3 = make_uint2(0u, 0u);
+                bool ok = false;
+                if (slot < np) {
+                    const uint32_t kid = __ldg(nt.count + 4 + sm.plist[slot]);       // first child | count << 16
+                    if ((lane & 7u) < (kid >> 16)) {
+                        e3 = __ldg(nt.ent + 72 + (kid & 0xffffu) + (lane & 7u));
+                        ok = node_pass_h(P, e3, 3, ro, rd);
+                    }
+                }
+                unsigned m3 = __ballot_sync(full, ok);
+                while (m3) {
+                    const int c = __ffs(m3) - 1;
+                    m3 &= m3 - 1u;
+                    const uint32_t cell = __shfl_sync(full, e3.y >> 16, c);
+                    coop_filter_h(sm, pv, geom_h, __ldg(pv.start + cell), __ldg(pv.start + cell + 1), lane, ro, rd, a, head, best);
+                }
+            }
+        }
+        coop_drain_h(sm, pv, geom_h, head, true, lane, ro, rd, a, best);
+        const uint32_t tmin = __reduce_min_sync(full, best.t);
+        if (tmin != 0xffffffffu) {
+            const uint32_t omin = __reduce_min_sync(full, best.t == tmin ? best.order : 0xffffffffu);
+            if ((int)lane == r) {
+                mine.t = __ushort_as_half((unsigned short)tmin);
+                if (omin == 0u) {
+                    mine.idx = 0;
+                } else {
+                    const int2 id = __ldg(pv.idx + ((omin - 1u) >> 1));
+                    mine.idx = ((omin - 1u) & 1u) ? id.y : id.x;
+                }
+            }
+        }
+    }
+    return mine;
+}
+
 }  // namespace h16
 }  // namespace rt

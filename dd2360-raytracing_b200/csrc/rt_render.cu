@@ -279,8 +279,11 @@ cudaError_t launch_render_half(const RenderLaunch &p, bool octree, const uint2 *
     pv.geom = hp.geom; pv.idx = hp.idx; pv.start = hp.start;
     h16::NodeTab nt;
     nt.ent = hp.nodes; nt.count = hp.node_count;
-    return octree ? h16::launch_half<true>(p, geom_h, matl_h, cam_h, pv, nt, sm_count, st, blocks_out)
-                  : h16::launch_half<false>(p, geom_h, matl_h, cam_h, pv, nt, sm_count, st, blocks_out);
+    if (p.variant == 30)        // A/B: root evaluation inside the scan loop (the first cooperative form); same image
+        return octree ? h16::launch_half<true, false>(p, geom_h, matl_h, cam_h, pv, nt, sm_count, st, blocks_out)
+                      : h16::launch_half<false, false>(p, geom_h, matl_h, cam_h, pv, nt, sm_count, st, blocks_out);
+    return octree ? h16::launch_half<true, true>(p, geom_h, matl_h, cam_h, pv, nt, sm_count, st, blocks_out)
+                  : h16::launch_half<false, true>(p, geom_h, matl_h, cam_h, pv, nt, sm_count, st, blocks_out);
 }
 
 // (re)build the pair lists of the USE_FP16 path: lists = 1 (flat mode) or kCells (octree mode)
@@ -291,7 +294,7 @@ cudaError_t build_half_pairs(HalfPairs &hp, const uint2 *geom_h, const int *tag,
         if ((e = cudaMalloc(&hp.count, (kCells + 1) * 4)) != cudaSuccess) return e;
         if ((e = cudaMalloc(&hp.start, (kCells + 2) * 4)) != cudaSuccess) return e;
         if ((e = cudaMalloc(&hp.nodes, (8 + 64 + 512) * sizeof(uint2))) != cudaSuccess) return e;
-        if ((e = cudaMalloc(&hp.node_count, 4 * 4)) != cudaSuccess) return e;
+        if ((e = cudaMalloc(&hp.node_count, (4 + 64) * 4)) != cudaSuccess) return e;
     }
     if (octree) h16::k_fp16_nodes<<<1, 1, 0, st>>>(tv.cell_start, hp.nodes, hp.node_count);
     h16::k_pairs_count<<<(lists + 127) / 128, 128, 0, st>>>(tag, n, lists, tv.cell_start, tv.cell_list, tv.cell_cap, hp.count);

@@ -38,7 +38,7 @@ __global__ void k_pairs_count(const int *__restrict__ tag, int n, int lists, con
         const uint32_t b = cell_start[m], e = min(cell_start[m + 1], b + (uint32_t)cell_cap);
         for (uint32_t k = b; k < e; k++) valid += tag[cell_list[k]] >= 0;
     }
-    pair_count[m] = (valid + 1u) / 2u;
+    pair_count[m] = ((valid + 1u) / 2u + kPairPad - 1u) / kPairPad * kPairPad;       // padded with NaN pairs (coop_filter_h)
 }
 __global__ void k_pairs_scan(const uint32_t *__restrict__ pair_count, int lists, uint32_t *__restrict__ pair_start) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
@@ -78,6 +78,10 @@ __global__ void k_pairs_fill(const uint2 *__restrict__ geom_h, const int *__rest
         for (uint32_t k = b; k < e; k++) feed((int)cell_list[k]);
     }
     if (pend >= 0) emit(pend, -1);
+    for (const uint32_t end = pair_start[m + 1]; out < end; out++) {     // padding up to a multiple of kPairPad: NaN spheres, never hit
+        pair_geom[out] = make_uint4(0x7e007e00u, 0x7e007e00u, 0x7e007e00u, 0x7e007e00u);
+        pair_idx[out] = make_int2(-1, -1);
+    }
 }
 
 // compact per-level tables of the octree nodes that exist (a node was created iff its subtree received an entry):
@@ -86,6 +90,7 @@ __global__ void k_fp16_nodes(const uint32_t *__restrict__ cell_start, uint2 *__r
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     int pos1[8], pos2[64];
     uint32_t n1 = 0, n2 = 0, n3 = 0;
+    for (int k = 0; k < 64; k++) count[4 + k] = 0u;
     for (int c1 = 0; c1 < 8; c1++) {
         pos1[c1] = -1;
         if (cell_start[c1 * 64 + 64] == cell_start[c1 * 64]) continue;
@@ -104,6 +109,9 @@ __global__ void k_fp16_nodes(const uint32_t *__restrict__ cell_start, uint2 *__r
         if (cell_start[m3 + 1] == cell_start[m3]) continue;
         int x, y, z;
         morton_to_xyz(m3, x, y, z);
+        // count[4 + p]: the children of level-2 node p are contiguous in the level-3 table: first child | count << 16
+        uint32_t &kid = count[4 + pos2[m3 >> 3]];
+        kid = (kid >> 16) ? kid + (1u << 16) : (n3 | 1u << 16);
         ent[72 + n3++] = make_uint2((uint32_t)x | (uint32_t)y << 8 | (uint32_t)z << 16, (uint32_t)pos2[m3 >> 3] | (uint32_t)m3 << 16);
     }
     count[0] = n1; count[1] = n2; count[2] = n3;
@@ -143,10 +151,12 @@ __global__ void k_camera_setup_h(const float lfx, const float lfy, const float l
     out[21] = lens_radius;
 }
 
-template <bool OCTREE>
-__global__ void __launch_bounds__(kRenderThreads, 4)
+// COOP2: closest hit by coop_trace_h2 (filter and roots in separate converged phases); false keeps coop_trace_h for A/B runs
+template <bool OCTREE, bool COOP2>
+__global__ void __launch_bounds__(kRenderThreads, 5)
 k_render_h(const __grid_constant__ RenderLaunch p, const uint2 *__restrict__ geom_h, const uint2 *__restrict__ matl_h,
            const __half *__restrict__ cam_h, const PairView pv, const NodeTab nt) {
+    __shared__ CoopSmem coop_sm[COOP2 ? kRenderThreads / 32 : 1];
     CameraH cam;
     {
         vec3h *v[7] = {&cam.origin, &cam.lower_left_corner, &cam.horizontal, &cam.vertical, &cam.u, &cam.v, &cam.w};
@@ -154,6 +164,8 @@ k_render_h(const __grid_constant__ RenderLaunch p, const uint2 *__restrict__ geo
         cam.lens_radius = cam_h[21];
     }
     const unsigned lane = threadIdx.x & 31u;
+    if (COOP2 && lane == 0) coop_sm[threadIdx.x >> 5].tail = 0u;
+    __syncwarp();
     const uint32_t gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     int pix = -1, pi = 0, pj = 0, s = 0, depth = 0;
     xorwow rng;
@@ -208,7 +220,8 @@ k_render_h(const __grid_constant__ RenderLaunch p, const uint2 *__restrict__ geo
             nrays++;
         }
         // closest hit of every lane's ray, one ray at a time by the whole warp (rt_half.cuh coop_trace_h)
-        const HitH h = coop_trace_h<OCTREE>(pv, nt, geom_h, p.tree, have, o, d);
+        const HitH h = COOP2 ? coop_trace_h2<OCTREE>(coop_sm[threadIdx.x >> 5], pv, nt, geom_h, p.tree, have, o, d)
+                             : coop_trace_h<OCTREE>(pv, nt, geom_h, p.tree, have, o, d);
         if (have) {
             bool sample_done = false;
             vec3h contrib = mkh(zero, zero, zero);
@@ -257,10 +270,10 @@ k_render_h(const __grid_constant__ RenderLaunch p, const uint2 *__restrict__ geo
     }
 }
 
-template <bool OCTREE>
+template <bool OCTREE, bool COOP2>
 static cudaError_t launch_half(const RenderLaunch &p, const uint2 *geom_h, const uint2 *matl_h, const __half *cam_h, const PairView pv,
                                const NodeTab nt, int sm_count, cudaStream_t st, int *blocks_out) {
-    auto kern = k_render_h<OCTREE>;
+    auto kern = k_render_h<OCTREE, COOP2>;
     int per_sm = 0;
     cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kRenderThreads, 0);
     if (e != cudaSuccess) return e;

@@ -1,17 +1,22 @@
 """Attribute the SASS of the pooled render kernel to its bodies: walk the instructions in address order and assign each to
 the function of rt_pool.cuh whose source line was seen last (inlined rt_math/rt_shade/rt_trace code inherits it).
-usage: python profiles/ncu_body_breakdown.py file.ncu-rep"""
+usage: python profiles/ncu_body_breakdown.py file.ncu-rep [source-file-in-csrc function-regex start-body]
+       (defaults: rt_pool.cuh and its body functions; for the USE_FP16 kernel:
+        rt_half.cuh 'coop_\w+|node_pass_h|ref_line_test_h|sphere_test_h|scatter_h|camera_ray_h|hit_point_h|sky_h|random_in_unit_sphere_h|best_update' k_render_h)"""
 import csv
 import re
 import subprocess
 import sys
 
 src = sys.argv[1]
-pool_src = open(__file__.rsplit('/', 2)[0] + '/dd2360-raytracing_b200/csrc/rt_pool.cuh').read().splitlines()
+SRC_FILE = sys.argv[2] if len(sys.argv) > 2 else 'rt_pool.cuh'
+FUNCS = sys.argv[3] if len(sys.argv) > 3 else r'body_\w+|gen_sample|begin_walk|maybe_hit|load_voxel|end_walk|rewalk_checked|k_render_pool'
+START = sys.argv[4] if len(sys.argv) > 4 else 'k_render_pool'
+pool_src = open(__file__.rsplit('/', 2)[0] + '/dd2360-raytracing_b200/csrc/' + SRC_FILE).read().splitlines()
 # line -> enclosing function name in rt_pool.cuh
 func_of, cur = {}, 'header'
 for i, l in enumerate(pool_src, 1):
-    m = re.search(r'\b(body_\w+|gen_sample|begin_walk|maybe_hit|load_voxel|end_walk|rewalk_checked|k_render_pool)\b\s*\(', l)
+    m = re.search(r'\b(' + FUNCS + r')\b\s*\(', l)
     if m and ('__device__' in l or '__global__' in l or l.startswith('template') or 'void' in l or 'bool' in l or 'Hit' in l) and ';' not in l.split('{')[0]:
         cur = m.group(1)
     func_of[i] = cur
@@ -33,15 +38,13 @@ for r in csv.reader(txt.splitlines()):
             pass
 rows.sort()
 seen = set()
-agg, cur = {}, 'k_render_pool'
+agg, cur = {}, START
 for addr, f, ln, wi, ti, sass in rows:
     if addr in seen:
         continue
     seen.add(addr)
-    if f == 'rt_pool.cuh' and ln in func_of:
+    if f == SRC_FILE and ln in func_of:
         cur = func_of[ln]
-        if cur in ('maybe_hit', 'load_voxel', 'end_walk', 'begin_walk'):
-            pass
     a = agg.setdefault(cur, [0, 0, 0])
     a[0] += wi; a[1] += ti; a[2] += 1
 tw = sum(a[0] for a in agg.values()); tt = sum(a[1] for a in agg.values())
