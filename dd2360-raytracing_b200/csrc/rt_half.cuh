@@ -488,7 +488,7 @@ __device__ __forceinline__ HitH coop_trace_h(const PairView pv, const NodeTab nt
 constexpr uint32_t kPairPad = 128;      // every pair list is padded with NaN pairs to a multiple of this (k_pairs_fill)
 struct CoopSmem {
     uint32_t ring[512];       // scan-order keys of candidates with a positive discriminant (0: the ground sphere)
-    uint32_t plist[64];       // level-2 nodes that passed, compacted
+    uint32_t cells[16][32];   // [word][lane]: 512-bit mask of the level-3 cells lane's ray passes (walk_cells_h)
     uint32_t tail;            // ring write position (shared atomic: the order of the keys in the ring does not matter)
     uint32_t pad_[3];
 };
@@ -529,11 +529,12 @@ __device__ __forceinline__ void coop_filter_h(CoopSmem &sm, const PairView pv, c
     const __half2 ox = __half2half2(vx(o)), oy = __half2half2(vy(o)), oz = __half2half2(o.z);
     const __half2 dx = __half2half2(vx(d)), dy = __half2half2(vy(d)), dz = __half2half2(d.z);
     const __half2 a2 = __half2half2(a), zero2 = __float2half2_rn(0.0f);
-    for (uint32_t base = pb + lane; base < pe; base += kPairPad) {
-        const uint4 *ptr = pv.geom + base;
-        uint4 g[4];
+    uint4 g[4];
+    if (pb < pe) {
 #pragma unroll
-        for (int i = 0; i < 4; i++) g[i] = __ldg(ptr + 32 * i);
+        for (int i = 0; i < 4; i++) g[i] = __ldg(pv.geom + pb + lane + 32 * i);
+    }
+    for (uint32_t base = pb + lane; base < pe; base += kPairPad) {
         uint32_t mine = 0u;       // bit i: low sphere of pair i has a positive discriminant; bit 16 + i: its high sphere
 #pragma unroll
         for (int i = 0; i < 4; i++) {
@@ -544,6 +545,10 @@ __device__ __forceinline__ void coop_filter_h(CoopSmem &sm, const PairView pv, c
             const __half2 c = __hfma2(__hneg2(r), r, __hfma2(ocz, ocz, __hfma2(ocx, ocx, __hmul2_rn(ocy, ocy))));   // :21
             const __half2 disc = __hfma2(b, b, __hneg2(__hmul2_rn(a2, c)));                                          // :22
             mine |= __hgt2_mask(disc, zero2) & (0x00010001u << i);    // 0xffff per half where positive (NaN: 0)
+        }
+        if (base + kPairPad < pe) {      // the next step's loads fly while this step's positives are queued and evaluated
+#pragma unroll
+            for (int i = 0; i < 4; i++) g[i] = __ldg(pv.geom + base + kPairPad + 32 * i);
         }
         if (__any_sync(full, mine != 0u)) {
             while (mine) {                                           // ~0.5 positives per lane and step
@@ -556,18 +561,54 @@ __device__ __forceinline__ void coop_filter_h(CoopSmem &sm, const PairView pv, c
     }
 }
 
+// Which level-3 cells does each lane's OWN ray pass?  The line tests are per-ray work with nothing to share, so here the
+// lanes do not cooperate: each walks the existing nodes depth-first for its ray (children by octant = table order, the
+// half-precision test at every level, acceleration_structure.h:276-304), one node per loop trip so that the ~60
+// instructions of the test run converged whatever level each lane is at.  planes_h: the 3 x 9 slab planes in half, in
+// shared memory (per-lane indices: constant memory would serialise).  Result: sm.cells[.][lane].
+__device__ __forceinline__ void walk_cells_h(CoopSmem &sm, const hf *planes_h, const NodeTab nt, const uint32_t n1, const bool have_ray,
+                                             const unsigned lane, const vec3h o, const vec3h d) {
+#pragma unroll
+    for (int w = 0; w < 16; w++) sm.cells[w][lane] = 0u;
+    auto pass = [&](const uint32_t ex, const int level) {
+        const int ix = ex & 255, iy = (ex >> 8) & 255, iz = (ex >> 16) & 255, sh = 3 - level;
+        return ref_line_test_h(o, d, planes_h[ix << sh], planes_h[kPlanes + (iy << sh)], planes_h[2 * kPlanes + (iz << sh)],
+                               planes_h[(ix + 1) << sh], planes_h[kPlanes + ((iy + 1) << sh)], planes_h[2 * kPlanes + ((iz + 1) << sh)]);
+    };
+    uint32_t i1 = 0, j2 = 0, end2 = 0, j3 = 0, end3 = 0;
+    bool active = have_ray && n1 > 0u && pass(0u, 0);
+    while (active) {
+        int level;
+        uint2 e;
+        if (j3 < end3) { level = 3; e = __ldg(nt.ent + 72 + j3); j3++; }
+        else if (j2 < end2) { level = 2; e = __ldg(nt.ent + 8 + j2); j2++; }
+        else if (i1 < n1) { level = 1; e = __ldg(nt.ent + i1); i1++; }
+        else break;
+        if (pass(e.x, level)) {
+            if (level == 1) {
+                const uint32_t kid = __ldg(nt.count + 4 + 64 + (i1 - 1u));      // first child | count << 16, in the level-2 table
+                j2 = kid & 0xffffu; end2 = j2 + (kid >> 16);
+            } else if (level == 2) {
+                const uint32_t kid = __ldg(nt.count + 4 + (j2 - 1u));           // ... in the level-3 table
+                j3 = kid & 0xffffu; end3 = j3 + (kid >> 16);
+            } else {
+                const uint32_t m = e.y >> 16;                                    // Morton index of the cell = its pair list
+                sm.cells[m >> 5][lane] |= 1u << (m & 31u);
+            }
+        }
+    }
+    __syncwarp();
+}
+
 template <bool OCTREE>
-__device__ __forceinline__ HitH coop_trace_h2(CoopSmem &sm, const PairView pv, const NodeTab nt, const uint2 *geom_h, const TreeView &tv,
+__device__ __forceinline__ HitH coop_trace_h2(CoopSmem &sm, const hf *planes_h, const PairView pv, const NodeTab nt, const uint2 *geom_h,
                                               const bool have_ray, const vec3h o, const vec3h d) {
     const unsigned full = 0xffffffffu;
     const unsigned lane = threadIdx.x & 31u;
-    const unsigned lt = (1u << lane) - 1u;
     HitH mine;
     mine.t = f2h(3.402823466e+38f);
     mine.idx = -1;
-    const float *P = &tv.planes[0][0];
-    uint32_t n1 = 0, n2 = 0;
-    if (OCTREE) { n1 = __ldg(nt.count); n2 = __ldg(nt.count + 1); }
+    if (OCTREE) walk_cells_h(sm, planes_h, nt, __ldg(nt.count), have_ray, lane, o, d);
     unsigned todo = __ballot_sync(full, have_ray);
     while (todo) {
         const int r = __ffs(todo) - 1;
@@ -593,39 +634,11 @@ __device__ __forceinline__ HitH coop_trace_h2(CoopSmem &sm, const PairView pv, c
             coop_filter_h(sm, pv, geom_h, __ldg(pv.start), __ldg(pv.start + 1), lane, ro, rd, a, head, best);   // hitable_list.h:16-31
         } else {
             if (lane == 0) { sm.ring[head & 511u] = 0u; sm.tail = head + 1u; }     // the ground sphere, tested unconditionally (:322-332)
-            // root (lane 0) and the level-1 nodes (lanes 1..n1) in one step
-            uint2 e = make_uint2(0u, 0u);
-            if (lane >= 1u && lane <= n1) e = __ldg(nt.ent + lane - 1u);
-            const unsigned m01 = __ballot_sync(full, lane <= n1 && node_pass_h(P, e, lane ? 1 : 0, ro, rd));
-            const unsigned m1 = (n1 > 0 && (m01 & 1u)) ? m01 >> 1 : 0u;
-            uint32_t np = 0;
-            if (m1) {
-                for (uint32_t b2 = 0; b2 < n2; b2 += 32u) {     // level 2 (28 nodes in every scene of the reference's generator: one step)
-                    const uint32_t j = b2 + lane;
-                    const uint2 e2 = j < n2 ? __ldg(nt.ent + 8 + j) : make_uint2(0u, 0u);
-                    const bool ok = j < n2 && ((m1 >> (e2.y & 0xffffu)) & 1u) && node_pass_h(P, e2, 2, ro, rd);
-                    const unsigned m2 = __ballot_sync(full, ok);
-                    if (ok) sm.plist[np + __popc(m2 & lt)] = j;
-                    np += __popc(m2);
-                }
-            }
-            __syncwarp();
-            for (uint32_t b3 = 0; b3 < np; b3 += 4u) {          // level 3: the children of four passing level-2 nodes per step
-                const uint32_t slot = b3 + (lane >> 3);
-                uint2 e3 = make_uint2(0u, 0u);
-                bool ok = false;
-                if (slot < np) {
-                    const uint32_t kid = __ldg(nt.count + 4 + sm.plist[slot]);       // first child | count << 16
-                    if ((lane & 7u) < (kid >> 16)) {
-                        e3 = __ldg(nt.ent + 72 + (kid & 0xffffu) + (lane & 7u));
-                        ok = node_pass_h(P, e3, 3, ro, rd);
-                    }
-                }
-                unsigned m3 = __ballot_sync(full, ok);
-                while (m3) {
-                    const int c = __ffs(m3) - 1;
-                    m3 &= m3 - 1u;
-                    const uint32_t cell = __shfl_sync(full, e3.y >> 16, c);
+            for (int w = 0; w < 16; w++) {                                          // the cells ray r passes, in Morton order
+                uint32_t word = sm.cells[w][r];
+                while (word) {
+                    const uint32_t cell = 32u * w + (uint32_t)__ffs((int)word) - 1u;
+                    word &= word - 1u;
                     coop_filter_h(sm, pv, geom_h, __ldg(pv.start + cell), __ldg(pv.start + cell + 1), lane, ro, rd, a, head, best);
                 }
             }

@@ -294,7 +294,7 @@ cudaError_t build_half_pairs(HalfPairs &hp, const uint2 *geom_h, const int *tag,
         if ((e = cudaMalloc(&hp.count, (kCells + 1) * 4)) != cudaSuccess) return e;
         if ((e = cudaMalloc(&hp.start, (kCells + 2) * 4)) != cudaSuccess) return e;
         if ((e = cudaMalloc(&hp.nodes, (8 + 64 + 512) * sizeof(uint2))) != cudaSuccess) return e;
-        if ((e = cudaMalloc(&hp.node_count, (4 + 64) * 4)) != cudaSuccess) return e;
+        if ((e = cudaMalloc(&hp.node_count, (4 + 64 + 8) * 4)) != cudaSuccess) return e;
     }
     if (octree) h16::k_fp16_nodes<<<1, 1, 0, st>>>(tv.cell_start, hp.nodes, hp.node_count);
     h16::k_pairs_count<<<(lists + 127) / 128, 128, 0, st>>>(tag, n, lists, tv.cell_start, tv.cell_list, tv.cell_cap, hp.count);

@@ -90,7 +90,7 @@ __global__ void k_fp16_nodes(const uint32_t *__restrict__ cell_start, uint2 *__r
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     int pos1[8], pos2[64];
     uint32_t n1 = 0, n2 = 0, n3 = 0;
-    for (int k = 0; k < 64; k++) count[4 + k] = 0u;
+    for (int k = 0; k < 64 + 8; k++) count[4 + k] = 0u;
     for (int c1 = 0; c1 < 8; c1++) {
         pos1[c1] = -1;
         if (cell_start[c1 * 64 + 64] == cell_start[c1 * 64]) continue;
@@ -103,6 +103,8 @@ __global__ void k_fp16_nodes(const uint32_t *__restrict__ cell_start, uint2 *__r
         const int c1 = m2 >> 3, c2 = m2 & 7;
         const int x = (c1 >> 2) * 2 + (c2 >> 2), y = ((c1 >> 1) & 1) * 2 + ((c2 >> 1) & 1), z = (c1 & 1) * 2 + (c2 & 1);
         pos2[m2] = (int)n2;
+        uint32_t &kid1 = count[4 + 64 + pos1[c1]];      // children of level-1 node pos1[c1] in the level-2 table: first | count << 16
+        kid1 = (kid1 >> 16) ? kid1 + (1u << 16) : (n2 | 1u << 16);
         ent[8 + n2++] = make_uint2((uint32_t)x | (uint32_t)y << 8 | (uint32_t)z << 16, (uint32_t)pos1[c1] | (uint32_t)m2 << 16);
     }
     for (int m3 = 0; m3 < 512; m3++) {
@@ -157,6 +159,9 @@ __global__ void __launch_bounds__(kRenderThreads, 5)
 k_render_h(const __grid_constant__ RenderLaunch p, const uint2 *__restrict__ geom_h, const uint2 *__restrict__ matl_h,
            const __half *__restrict__ cam_h, const PairView pv, const NodeTab nt) {
     __shared__ CoopSmem coop_sm[COOP2 ? kRenderThreads / 32 : 1];
+    __shared__ hf planes_h[3 * kPlanes];      // the slab planes of the octree boxes, rounded to half as AABB's real_t members are
+    if (COOP2 && OCTREE && threadIdx.x < 3 * kPlanes) planes_h[threadIdx.x] = f2h((&p.tree.planes[0][0])[threadIdx.x]);
+    __syncthreads();
     CameraH cam;
     {
         vec3h *v[7] = {&cam.origin, &cam.lower_left_corner, &cam.horizontal, &cam.vertical, &cam.u, &cam.v, &cam.w};
@@ -220,7 +225,7 @@ k_render_h(const __grid_constant__ RenderLaunch p, const uint2 *__restrict__ geo
             nrays++;
         }
         // closest hit of every lane's ray, one ray at a time by the whole warp (rt_half.cuh coop_trace_h)
-        const HitH h = COOP2 ? coop_trace_h2<OCTREE>(coop_sm[threadIdx.x >> 5], pv, nt, geom_h, p.tree, have, o, d)
+        const HitH h = COOP2 ? coop_trace_h2<OCTREE>(coop_sm[threadIdx.x >> 5], planes_h, pv, nt, geom_h, have, o, d)
                              : coop_trace_h<OCTREE>(pv, nt, geom_h, p.tree, have, o, d);
         if (have) {
             bool sample_done = false;

@@ -1,4 +1,4 @@
-"""Attribute the SASS of the pooled render kernel to its bodies: walk the instructions in address order and assign each to
+r"""Attribute the SASS of the pooled render kernel to its bodies: walk the instructions in address order and assign each to
 the function of rt_pool.cuh whose source line was seen last (inlined rt_math/rt_shade/rt_trace code inherits it).
 usage: python profiles/ncu_body_breakdown.py file.ncu-rep [source-file-in-csrc function-regex start-body]
        (defaults: rt_pool.cuh and its body functions; for the USE_FP16 kernel:
