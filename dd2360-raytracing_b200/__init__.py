@@ -40,6 +40,7 @@ ABI_SYMBOLS = [
     "rt_scene_generate", "rt_scene_generate_ex", "rt_scene_upload", "rt_scene_download", "rt_scene_size", "rt_camera_set", "rt_camera_get", "rt_camera_get_half",
     "rt_octree_build", "rt_octree_build_ex", "rt_octree_reference_bytes", "rt_octree_export_reference", "rt_octree_debug_read", "rt_xorwow_state", "rt_debug_counters", "rt_trace_rays",
     "rt_render_accumulate", "rt_finalize", "rt_render", "rt_render_to_host", "rt_format_ppm",
+    "rt_ppm_format", "rt_ppm_read", "rt_render_to_ppm",
     "rt_ffma_peak", "rt_malloc", "rt_free", "rt_memcpy_to_host", "rt_synchronize",
 ]
 
@@ -118,6 +119,9 @@ def load_library(path: str | None = None) -> C.CDLL:
         "rt_render": (i32, [vp, C.POINTER(RenderArgs), vp, C.POINTER(RenderStats)]),
         "rt_render_to_host": (i32, [vp, C.POINTER(RenderArgs), vp, C.POINTER(RenderStats)]),
         "rt_format_ppm": (sz, [vp, i32, i32, vp, sz]),
+        "rt_ppm_format": (i32, [vp, vp, i32, i32, C.POINTER(sz)]),
+        "rt_ppm_read": (i32, [vp, vp, sz]),
+        "rt_render_to_ppm": (i32, [vp, C.POINTER(RenderArgs), C.POINTER(RenderStats), C.POINTER(sz)]),
         "rt_ffma_peak": (i32, [vp, C.POINTER(f32), C.POINTER(f32)]),
         "rt_malloc": (i32, [vp, sz, C.POINTER(vp)]),
         "rt_free": (i32, [vp, vp]),
@@ -288,6 +292,23 @@ class RayTracer:
         st = RenderStats()
         self._ck(self.L.rt_render_to_host(self._ctx, C.byref(a), fb.ctypes.data, C.byref(st)), "rt_render_to_host")
         return fb, st.as_dict()
+
+    def format_ppm_device(self, fb_dev_ptr: int, nx: int, ny: int) -> bytes:
+        """output_to_stream (main.cu:321-333) on the device: P3 text of a DEVICE frame; only the text is copied back."""
+        n = C.c_size_t()
+        self._ck(self.L.rt_ppm_format(self._ctx, C.c_void_p(fb_dev_ptr), nx, ny, C.byref(n)), "rt_ppm_format")
+        buf = C.create_string_buffer(max(n.value, 1))
+        self._ck(self.L.rt_ppm_read(self._ctx, buf, n.value), "rt_ppm_read")
+        return buf.raw[:n.value]
+
+    def render_ppm(self, nx, ny, ns, use_octree=True, **kw):
+        """render + output_to_stream without the float frame ever leaving the GPU.  Returns (P3 text, stats)."""
+        a = self.args(nx, ny, ns, use_octree, **kw)
+        st, n = RenderStats(), C.c_size_t()
+        self._ck(self.L.rt_render_to_ppm(self._ctx, C.byref(a), C.byref(st), C.byref(n)), "rt_render_to_ppm")
+        buf = C.create_string_buffer(max(n.value, 1))
+        self._ck(self.L.rt_ppm_read(self._ctx, buf, n.value), "rt_ppm_read")
+        return buf.raw[:n.value], st.as_dict()
 
     def render_device(self, args: RenderArgs, fb_dev_ptr: int, want_stats=True):
         st = RenderStats()

@@ -73,23 +73,25 @@ int main(int argc, char **argv) {
     if (use_octree) CHECK(rt_octree_build_ex(ctx, spl, precision, nullptr));
     CHECK(rt_camera_set(ctx, nullptr, nx, ny));
 
-    std::vector<float> fb((size_t)nx * ny * 3);
     rt_render_args a{};
     a.nx = nx; a.ny = ny; a.ns = ns; a.max_depth = 50; a.use_octree = use_octree;
     a.precision = precision;
     a.seed_mode = env_int("RT_SEED_MODE", RT_SEED_HEAD);
     rt_render_stats st{};
     const auto t0 = std::chrono::steady_clock::now();
-    CHECK(rt_render_to_host(ctx, &a, fb.data(), &st));
+    size_t need = 0;
+    const bool want_text = output_mode == 0 || output_mode == 3;
+    std::vector<float> fb(want_text ? 0 : (size_t)nx * ny * 3);
+    if (want_text) CHECK(rt_render_to_ppm(ctx, &a, &st, &need));          // the frame is quantised and formatted on the GPU
+    else CHECK(rt_render_to_host(ctx, &a, fb.data(), &st));
     const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     std::cerr << "took " << secs << " seconds.\n";
     if (getenv("RT_VERBOSE"))
         std::cerr << "rays " << st.rays << ", kernel " << st.kernel_ms << " ms, " << (st.rays / (st.kernel_ms * 1e3)) << " Mrays/s\n";
 
     if (output_mode == 0 || output_mode == 3) {
-        const size_t need = rt_format_ppm(fb.data(), nx, ny, nullptr, 0);
         std::string txt(need, '\0');
-        rt_format_ppm(fb.data(), nx, ny, &txt[0], need);
+        CHECK(rt_ppm_read(ctx, &txt[0], need));
         if (output_mode == 0) {
             std::cout.write(txt.data(), (std::streamsize)need);
         } else {

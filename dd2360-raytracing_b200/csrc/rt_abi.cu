@@ -46,6 +46,7 @@ struct rt_context {
     unsigned long long *counters = nullptr;
     float *scratch_fb = nullptr;
     size_t scratch_fb_bytes = 0;
+    PpmWorkspace ppm;
     float *pinned = nullptr;
     size_t pinned_bytes = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -123,6 +124,7 @@ extern "C" void rt_destroy(rt_context *ctx) {
     cudaStreamSynchronize(ctx->stream);
     delete ctx->octree;
     delete ctx->list_accel;
+    ppm_free(ctx->ppm);
     cudaFree(ctx->geom); cudaFree(ctx->matl); cudaFree(ctx->tag); cudaFree(ctx->cam_dev);
     cudaFree(ctx->work_counter); cudaFree(ctx->counters); cudaFree(ctx->scratch_fb);
     cudaFree(ctx->skip_tables); cudaFree(ctx->seed_states);
@@ -483,6 +485,7 @@ static int do_render(rt_context *ctx, const rt_render_args *a, float *out_dev, b
     p.total_items = (uint32_t)(owned * 32);
     p.finalize = finalize ? 1 : 0;
     p.variant = a->tune[1] ? a->tune[1] : ctx->default_variant;
+    if (p.variant == 21) p.tree.check_visibility = 0;   // MEASUREMENT ONLY: cost of the visibility rule (same image only when nothing was dropped)
     p.tune_sticky = a->tune[3] > 0 ? a->tune[3] : 4;
     p.tune_sticky_min = a->tune[4] > 0 ? a->tune[4] : 8;
     p.max_rounds = a->tune[2] > 0 ? (uint32_t)a->tune[2] : 0x7fffffffu;            // A/B measurement knob; every variant renders the same image
@@ -630,6 +633,39 @@ extern "C" int rt_render_to_host(rt_context *ctx, const rt_render_args *args, fl
     if (rc) return rc;
     CK(cudaMemcpyAsync(fb_host, ctx->scratch_fb, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    return RT_OK;
+}
+
+// ---- output on the device (rt_ppm.cu) ---------------------------------------------------------------------------------
+extern "C" int rt_ppm_format(rt_context *ctx, const float *fb_dev, int nx, int ny, size_t *len_out) {
+    if (!ctx || !fb_dev || nx < 0 || ny < 0) return fail(ctx, RT_ERR_INVALID, "rt_ppm_format: bad argument");
+    CK(cudaSetDevice(ctx->device));
+    CK(ppm_format_device(ctx->ppm, fb_dev, nx, ny, ctx->stream, len_out));
+    return RT_OK;
+}
+
+extern "C" int rt_ppm_read(rt_context *ctx, char *buf_host, size_t cap) {
+    if (!ctx || !buf_host) return fail(ctx, RT_ERR_INVALID, "rt_ppm_read: null argument");
+    if (!ctx->ppm.text || cap < ctx->ppm.text_len) return fail(ctx, RT_ERR_INVALID, "rt_ppm_read: no formatted frame, or the buffer is smaller than its text");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpyAsync(buf_host, ctx->ppm.text, ctx->ppm.text_len, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return RT_OK;
+}
+
+extern "C" int rt_render_to_ppm(rt_context *ctx, const rt_render_args *args, rt_render_stats *stats, size_t *len_out) {
+    if (!ctx || !args) return fail(ctx, RT_ERR_INVALID, "rt_render_to_ppm: null argument");
+    CK(cudaSetDevice(ctx->device));
+    const size_t bytes = (size_t)args->nx * args->ny * 3 * sizeof(float);
+    if (bytes > ctx->scratch_fb_bytes) {
+        cudaFree(ctx->scratch_fb);
+        ctx->scratch_fb = nullptr; ctx->scratch_fb_bytes = 0;
+        CK(cudaMalloc(&ctx->scratch_fb, bytes));
+        ctx->scratch_fb_bytes = bytes;
+    }
+    const int rc = do_render(ctx, args, ctx->scratch_fb, true, stats);
+    if (rc) return rc;
+    CK(ppm_format_device(ctx->ppm, ctx->scratch_fb, args->nx, args->ny, ctx->stream, len_out));
     return RT_OK;
 }
 

@@ -570,6 +570,8 @@ TreeView OctreeBuilder::view() const {
     v.prolog_geom = d.prolog_geom;
     v.nprolog = 1 + nbig;
     for (int a = 0; a < 3; a++) for (int i = 0; i < kPlanes; i++) v.planes[a][i] = planes.p[a][i];
+    v.no_drops = stats_h[1] == 0 ? 1 : 0;
+    for (int a = 0; a < 3; a++) v.cell_inv[a] = 8.0f / (planes.p[a][kPlanes - 1] - planes.p[a][0]);
     return v;
 }
 

@@ -257,7 +257,7 @@ __device__ __forceinline__ void body_end(const Ctx<NC> c, const RenderLaunch &p,
     if (hidx > 0 && p.tree.check_visibility) {       // the ground sphere (index 0) is tested unconditionally by the reference
         const vec3f o = c.v3(F_OX), d = c.v3(F_DX);
         int last_ok = -1;
-        if (!sphere_visible(p.tree.vis, planes, hidx, o, d, last_ok, tc)) {
+        if (!visible_fast(p.tree, planes, __ldg(p.scene.geom + hidx), o, d, c.f(F_HT)) && !sphere_visible(p.tree.vis, planes, hidx, o, d, last_ok, tc)) {
             const Hit h = rewalk_checked(p.scene, p.tree, planes, o, d);
             c.sf(F_HT, h.t);
             c.su(F_HIDX, (uint32_t)h.idx);

@@ -59,6 +59,16 @@ struct HalfPairs {            // candidate lists as transposed sphere pairs (rt_
 cudaError_t build_half_pairs(HalfPairs &hp, const uint2 *geom_h, const int *tag, int n, bool octree, const TreeView &tv, cudaStream_t st);
 cudaError_t launch_render_half(const RenderLaunch &p, bool octree, const uint2 *geom_h, const uint2 *matl_h, const __half *cam_h,
                                const HalfPairs &hp, int sm_count, cudaStream_t st, int *blocks_out);
+// ---- output_to_stream on the device (rt_ppm.cu) ----
+struct PpmWorkspace {
+    uint32_t *block_len = nullptr;
+    unsigned long long *block_off = nullptr;
+    size_t block_cap = 0;
+    char *text = nullptr;
+    size_t text_cap = 0, text_len = 0;
+};
+cudaError_t ppm_format_device(PpmWorkspace &ws, const float *fb, int nx, int ny, cudaStream_t st, size_t *len_out);
+void ppm_free(PpmWorkspace &ws);
 cudaError_t launch_finalize(const float *accum, float *fb, int nx, int ny, int ns, cudaStream_t st);
 
 }  // namespace rt

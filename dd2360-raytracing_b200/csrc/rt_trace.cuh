@@ -132,6 +132,34 @@ bool sphere_visible(const VisView vis, const float *planes, const int idx, const
     return false;
 }
 
+// A sufficient condition for the rule above that needs no division and no list: the hit point P = o + t*d lies on the
+// ray's line, so if P is strictly inside some level-3 cell that stores the sphere, the line crosses that cell and the
+// reference's slab test passes — PROVIDED the margins absorb its float rounding.  With P inside [lo + m, hi - m] per
+// axis, the exact slab parameters bracket t with slack m/|d_i|; the reference's two roundings per parameter move each
+// by at most 1.2e-7 * |plane - o_i|, and computing P here by at most 2.4e-7 * (|o_i| + |P_i|): m = 1e-4 + 4e-6 * (|o_i|
+// + |P_i|) covers both many times over (zero direction components give -inf / +inf slabs, which pass).  The cell
+// stores the sphere iff `intersects` (acceleration_structure.h:82-93: centre inside the box expanded by r, evaluated in
+// float) held at every level — parents contain children and float add/sub are monotone, so the level-3 box decides —
+// and the entry was not dropped on overflow (tv.no_drops).  The centre test uses its own margin for the rounding of
+// lo - r and hi + r.  False only means "ask sphere_visible".
+RT_HD bool visible_fast(const TreeView &tv, const float *planes, const float4 s, const vec3f o, const vec3f d, const float t) {
+    if (!tv.no_drops) return false;
+    const float P[3] = {o.x + t * d.x, o.y + t * d.y, o.z + t * d.z};
+    const float O[3] = {o.x, o.y, o.z}, C[3] = {s.x, s.y, s.z};
+    bool ok = true;
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+        const float *pl = planes + a * kPlanes;
+        int i = (int)((P[a] - pl[0]) * tv.cell_inv[a]);
+        i = i < 0 ? 0 : (i > 7 ? 7 : i);
+        const float lo = pl[i], hi = pl[i + 1];
+        const float m = 1e-4f + 4e-6f * (fabsf(O[a]) + fabsf(P[a]));
+        const float mc = 1e-4f + 4e-6f * (fabsf(lo) + fabsf(hi) + s.w);
+        ok = ok && (P[a] >= lo + m) && (P[a] <= hi - m) && (C[a] > lo - s.w + mc) && (C[a] < hi + s.w - mc);
+    }
+    return ok;
+}
+
 // One pass over the candidates.  CHECKED = true applies the visibility rule to every candidate before it may become
 // the closest hit (always exact); CHECKED = false takes the plain minimum over all candidates.
 template <bool CHECKED>
@@ -223,8 +251,8 @@ RT_HD Hit trace_walk(const SceneView &sc, const TreeView &tv, const float *plane
 RT_HD Hit trace_tree(const SceneView &sc, const TreeView &tv, const float *planes, const vec3f o, const vec3f d,
                     TraceCounters &tc) {
     Hit h = trace_walk<false>(sc, tv, planes, o, d, tc);
-    if (h.idx > 0 && tv.check_visibility) {  // the ground sphere (index 0) is tested unconditionally by the reference
-        int last_ok = -1;
+    if (h.idx > 0 && tv.check_visibility && !visible_fast(tv, planes, RT_LDG(sc.geom + h.idx), o, d, h.t)) {
+        int last_ok = -1;                    // (the ground sphere, index 0, is tested unconditionally by the reference)
         if (!sphere_visible(tv.vis, planes, h.idx, o, d, last_ok, tc)) h = trace_walk<true>(sc, tv, planes, o, d, tc);
     }
     return h;

@@ -70,6 +70,10 @@ struct TreeView {
     // 1: hitTree semantics — a candidate counts only if a cell that stores it is crossed by the ray's line (VisView);
     // 0: hitable_list semantics — every sphere is a candidate (the grid then serves the flat-list mode, USE_OCTREE off)
     int check_visibility;
+    // inputs of the cheap sufficient condition in front of the visibility rule (rt_trace.cuh visible_fast):
+    int no_drops;               // 1: the build dropped no entry ("Leaf nodes full" never happened), so a cell stores every sphere
+                                //    whose centre its r-expanded box contains
+    float cell_inv[3];          // 8 / root box extent per axis: cell index guess from a coordinate
 };
 
 }  // namespace rt

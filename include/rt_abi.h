@@ -155,6 +155,14 @@ int rt_render_to_host(rt_context *ctx, const rt_render_args *args, float *fb_hos
 /* ---- output: replaces output_to_stream (main.cu:321-333) -------------------------------------------------- */
 /* P3 text, byte-identical to the reference writer.  Returns bytes needed when buf == NULL. */
 size_t rt_format_ppm(const float *fb_host, int nx, int ny, char *buf, size_t cap);
+/* The same writer on the device (csrc/rt_ppm.cu): quantise + format in HBM, so only the text crosses PCIe — at 4K the host
+ * writer above costs more than the render.  rt_ppm_format formats a DEVICE frame into a context-owned device buffer and
+ * returns the text length; rt_ppm_read copies that text to the host (cap >= length).  rt_render_to_ppm = rt_render into
+ * the context's scratch frame + rt_ppm_format: what main() does for output modes 0 and 3 (main.cu:427 + :435-452).
+ * Bytes identical to rt_format_ppm for every finite frame. */
+int rt_ppm_format(rt_context *ctx, const float *fb_dev, int nx, int ny, size_t *len_out);
+int rt_ppm_read(rt_context *ctx, char *buf_host, size_t cap);
+int rt_render_to_ppm(rt_context *ctx, const rt_render_args *args, rt_render_stats *stats, size_t *len_out);
 
 /* ---- measurement: dense FP32 FFMA rate of this GPU (2 flop per FFMA), the denominator of the FP32 roofline -------- */
 int rt_ffma_peak(rt_context *ctx, float *tflops, float *kernel_ms);

@@ -33,6 +33,7 @@ struct HostTree {
     std::vector<uint16_t> ent_cell;
     GridView grid;
     float planes[3][kPlanes];
+    bool no_drops = true;
 };
 
 static void make_planes(float P[3][kPlanes]) {
@@ -67,6 +68,21 @@ static void build_host_tree(const std::vector<float4> &geom, const std::vector<i
             const int32_t *lf = bl + (size_t)leaf * (size_t)(spl + 1);
             for (int j = 0; j < lf[spl]; j++) cells_of[(size_t)lf[j]].push_back((uint16_t)m);
         }
+    }
+    // did the reference drop an entry?  (a defined sphere `intersects` more level-3 boxes than leaf buckets list it in;
+    // acceleration_structure.h:82-93 with its float expansion and the (low, high] x interval)
+    T.no_drops = true;
+    for (int i = 1; i < n && T.no_drops; i++) {
+        const float4 s = geom[(size_t)i];
+        int cnt[3] = {0, 0, 0};
+        for (int a = 0; a < 3; a++) {
+            const float c = a == 0 ? s.x : (a == 1 ? s.y : s.z);
+            for (int k = 0; k < 8; k++) {
+                const float lo = T.planes[a][k] - s.w, hi = T.planes[a][k + 1] + s.w;
+                cnt[a] += (a == 0 ? c > lo : c >= lo) && c <= hi;
+            }
+        }
+        if ((size_t)(cnt[0] * cnt[1] * cnt[2]) != cells_of[(size_t)i].size()) T.no_drops = false;
     }
     T.ent_off.assign((size_t)n + 1, 0);
     for (int i = 0; i < n; i++) {
@@ -124,6 +140,8 @@ static void view_of(HostTree &T, TreeView &tv) {
     tv.prolog = T.prolog.data(); tv.nprolog = (int)T.prolog.size();
     tv.check_visibility = 1;
     memcpy(tv.planes, T.planes, sizeof tv.planes);
+    tv.no_drops = T.no_drops ? 1 : 0;
+    for (int a = 0; a < 3; a++) tv.cell_inv[a] = 8.0f / (T.planes[a][kPlanes - 1] - T.planes[a][0]);
 }
 
 extern "C" {
@@ -149,6 +167,7 @@ static int render_core(const hs_sphere *sph, int n, const float *camera22, const
         tv = *given;
         make_planes(T.planes);
         memcpy(tv.planes, T.planes, sizeof tv.planes);
+        for (int a = 0; a < 3; a++) tv.cell_inv[a] = 8.0f / (T.planes[a][kPlanes - 1] - T.planes[a][0]);
     } else if (p->use_octree) {
         build_host_tree(geom, tag, static_cast<const int32_t *>(blob), p->spl, density, T);
         view_of(T, tv);
@@ -235,6 +254,8 @@ int hs_render_with_tree(const hs_sphere *sph, int n, const float *camera22, cons
     prolog.insert(prolog.end(), static_cast<const uint32_t *>(big_refs), static_cast<const uint32_t *>(big_refs) + nbig);
     tv.prolog = prolog.data(); tv.nprolog = (int)prolog.size();
     tv.check_visibility = 1;
+    tv.no_drops = 1;
+    for (uint32_t k = 0, e = tv.vis.ent_off[n]; k < e; k++) if (tv.vis.ent_cell[k] & kEntDropped) tv.no_drops = 0;
     return render_core(sph, n, camera22, nullptr, p, 0.f, fb_gamma, nullptr, ctr_out, nullptr, &tv);
 }
 

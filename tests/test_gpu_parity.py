@@ -412,3 +412,62 @@ def test_dropin_class_surface_renders_the_same_frame(rt, pkg, O, tmp_path):
     rt.build_octree(30)
     want, _ = rt.render(64, 48, 2, use_octree=True)
     assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
+def test_experiment_harness_sweep(tmp_path):
+    """analysis/run_experiment.py (the reference's run_experiment.sh + notebook tables): a 2-size sweep writes runs.csv,
+    summary.md and a PPM per run in the reference's naming; BASELINE and OCTREE trace the same rays."""
+    import csv
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = str(tmp_path / "experiments")
+    subprocess.run([sys.executable, os.path.join(root, "analysis", "run_experiment.py"), "--sizes", "488,2000", "--radii", "0.1", "--iters", "2",
+                    "--nx", "120", "--ny", "80", "--ns", "2", "--out", out, "--ppm"], check=True, stdout=subprocess.DEVNULL)
+    rows = list(csv.DictReader(open(os.path.join(out, "runs.csv"))))
+    assert len(rows) == 2 * 2 * 2 and all(float(r["kernel_ms"]) > 0 for r in rows)
+    by = {(r["mode"], r["n"], r["iter"]): r for r in rows}
+    assert by[("BASELINE", "488", "1")]["rays"] == by[("OCTREE", "488", "1")]["rays"]
+    assert open(by[("OCTREE", "2000", "2")]["ppm"], "rb").read(3) == b"P3\n"
+    assert "octree speed-up" in open(os.path.join(out, "summary.md")).read()
+
+
+def test_device_ppm_writer_matches_host_writer_byte_for_byte(rt, pkg):
+    """csrc/rt_ppm.cu against rt_format_ppm (itself pinned on the reference's writer): rendered frames, odd sizes, and
+    values the quantiser must treat like the x86 cast does (negative, > 1, huge, inf, NaN)."""
+    import torch
+    rt.create_world(488, 0.1)
+    rt.build_octree(30)
+    txt, st = rt.render_ppm(203, 117, 2, use_octree=True)
+    fb, _ = rt.render(203, 117, 2, use_octree=True)
+    assert txt == pkg.format_ppm(fb) and txt.startswith(b"P3\n203 117\n255\n") and st["rays"] > 0
+    rng = np.random.default_rng(7)
+    for nx, ny in [(1, 1), (7, 3), (256, 1), (257, 5), (1200, 800), (33, 1031)]:
+        fb = rng.random((ny, nx, 3), dtype=np.float32)
+        flat = fb.reshape(-1)
+        k = min(flat.size, 12)
+        flat[:k] = np.array([0.0, 1.0, -0.5, 3.7, 1e4, -1e6, 8388607.0, 1e12, -1e30, np.inf, -np.inf, np.nan], dtype=np.float32)[:k]
+        dev = torch.from_numpy(fb).cuda()
+        assert rt.format_ppm_device(dev.data_ptr(), nx, ny) == pkg.format_ppm(fb), (nx, ny)
+
+
+def test_cli_modes_write_the_reference_image(pkg, golden_dir, tmp_path):
+    """`RayTracing [mode]` (main.cu:347-477) at BASELINE config 2: mode 3 writes output.ppm, mode 0 the same bytes to stdout,
+    mode 1 nothing; the pixels are the reference CUDA build's 8-bit image; a non-numeric mode throws like std::stoi."""
+    import subprocess
+    exe = os.path.join(os.path.dirname(pkg.LIB_PATH), "RayTracing")
+    env = dict(os.environ, RT_NUM_SPHERES="488", RT_SPHERES_PER_LEAF="30")
+    r3 = subprocess.run([exe, "3"], cwd=tmp_path, env=env, capture_output=True, check=True)
+    ppm = (tmp_path / "output.ppm").read_bytes()
+    assert r3.stdout == b"" and b"took " in r3.stderr and b"Number of spheres: 488" in r3.stderr
+    tok = ppm.split()
+    assert tok[:4] == [b"P3", b"1200", b"800", b"255"]
+    rgb = np.array(tok[4:], dtype=np.int64).reshape(800, 1200, 3)
+    gold = np.load(os.path.join(golden_dir, "ref_cuda", "C2_1200x800x10_u8.npz"))["rgb"]
+    assert np.array_equal(rgb, gold)
+    r0 = subprocess.run([exe], cwd=tmp_path, env=env, capture_output=True, check=True)
+    assert r0.stdout == ppm
+    (tmp_path / "output.ppm").unlink()
+    r1 = subprocess.run([exe, "1"], cwd=tmp_path, env=env, capture_output=True, check=True)
+    assert r1.stdout == b"" and not (tmp_path / "output.ppm").exists()
+    assert subprocess.run([exe, "x"], cwd=tmp_path, env=env, capture_output=True).returncode != 0
