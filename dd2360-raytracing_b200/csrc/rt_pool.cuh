@@ -317,9 +317,15 @@ __device__ __forceinline__ void gen_sample(const Ctx<NC> c, const RenderLaunch &
 // (main.cu:68-71,107-115).  Entered by all 32 lanes (`have` = this lane was handed a context) because the queue pop is
 // compacted per warp with ballot/popc: one atomic for all lanes whose pixel just finished.  F_PIX < 0 marks a context
 // that has no pixel yet (start of the kernel, or a tile position outside the image).
+// Pixels are claimed in whole tiles PER WARP (`stock`: the unclaimed rest of this warp's last batch; `batch` = 32 or 64 queue
+// items = one or two 8x4 tiles): a context that finishes its pixel continues with the next pixel of its warp's own tile,
+// so the contexts of a warp stay neighbours in the image however long their sample chains are.  With one global
+// pixel-granular queue they drifted apart — contexts finish one at a time, and every claim landed wherever the
+// frame-wide queue head was — and the warp's candidate loads stopped sharing cache lines: at 64 spp the 1 M-sphere scene
+// ran at 60 % of its 1-spp rate (profiles/README.md r02a).
 template <int NC>
 __device__ __forceinline__ void body_sample(const Ctx<NC> c, const bool have, const RenderLaunch &p, const float inv_ns, const unsigned lt,
-                                            uint32_t &nrays, uint32_t &npaths) {
+                                            uint32_t &nrays, uint32_t &npaths, uint32_t &stock_next, uint32_t &stock_end, const uint32_t batch) {
     int pix = -1;
     bool need_pixel = false;
     xorwow rng;
@@ -357,12 +363,21 @@ __device__ __forceinline__ void body_sample(const Ctx<NC> c, const bool have, co
     // ---- queue pop for the lanes whose context needs a pixel ----
     const unsigned m = __ballot_sync(0xffffffffu, need_pixel);
     if (m) {
-        uint32_t qbase = 0;
-        const int leader = __ffs(m) - 1;
-        if ((int)(threadIdx.x & 31u) == leader) qbase = atomicAdd(p.work_counter, (uint32_t)__popc(m));
-        qbase = __shfl_sync(0xffffffffu, qbase, leader);
+        const uint32_t k = (uint32_t)__popc(m), rank = (uint32_t)__popc(m & lt), avail = stock_end - stock_next;
+        uint32_t item = stock_next + rank;
+        if (k <= avail) {
+            stock_next += k;
+        } else {                                   // the stock runs out: the rest comes from a fresh batch of whole tiles
+            const uint32_t need = k - avail, claim = (need + batch - 1u) / batch * batch;
+            uint32_t qbase = 0;
+            const int leader = __ffs(m) - 1;
+            if ((int)(threadIdx.x & 31u) == leader) qbase = atomicAdd(p.work_counter, claim);
+            qbase = __shfl_sync(0xffffffffu, qbase, leader);
+            if (rank >= avail) item = qbase + (rank - avail);
+            stock_next = qbase + need;
+            stock_end = qbase + claim;
+        }
         if (need_pixel) {
-            const uint32_t item = qbase + (uint32_t)__popc(m & lt);
             int pi, pj;
             pix = -1;
             if (item >= p.total_items) {
@@ -411,6 +426,12 @@ __global__ void __launch_bounds__(kRenderThreads, MINB) k_render_pool(const __gr
     uint32_t nrays = 0, npaths = 0;
     TraceCounters tc;
     tc.sphere_tests = tc.node_tests = tc.voxel_steps = 0;
+    uint32_t stock_next = 0, stock_end = 0;      // this warp's unclaimed queue items (body_sample)
+    // pixels per context decide the claim size: two tiles with plenty of work, one tile in between, and single pixels
+    // (no stock: the old frame-wide queue) when a context sees fewer than 4 pixels — there the tail of the frame is
+    // what matters and stocked pixels would only start later (measured, profiles/README.md r02a)
+    const uint32_t per_ctx = p.total_items / (gridDim.x * (kRenderThreads / 32) * NC);
+    const uint32_t batch = per_ctx >= 24u ? 64u : (per_ctx >= 4u ? 32u : 1u);
 
     uint32_t rounds = 0;
 #ifdef RT_COUNTERS
@@ -478,7 +499,7 @@ __global__ void __launch_bounds__(kRenderThreads, MINB) k_render_pool(const __gr
         else if (best == S_STEP) { if (id >= 0) body_step<NC>(c, p, tc); }
         else if (best == S_ENTER) { if (id >= 0) body_enter<NC>(c, p, tc); }
         else if (best == S_END) { if (id >= 0) body_end<NC>(c, p, planes, tc); }
-        else if (best == S_SAMPLE) body_sample<NC>(c, id >= 0, p, inv_ns, lt, nrays, npaths);
+        else if (best == S_SAMPLE) body_sample<NC>(c, id >= 0, p, inv_ns, lt, nrays, npaths, stock_next, stock_end, batch);
         else { if (id >= 0) body_shade<NC>(c, p, nrays); }       // S_DIFF, S_DIEL
         __syncwarp();
     }

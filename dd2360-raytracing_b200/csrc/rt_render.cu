@@ -112,6 +112,36 @@ __device__ __forceinline__ bool item_to_pixel(const RenderLaunch &p, uint32_t it
     return i < p.nx && j < p.ny;
 }
 
+// Queue pop for the lanes in `m` (ballot of the lanes that need a pixel), compacted per warp and served from the WARP'S
+// OWN stock of whole tiles: [stock_next, stock_end) is the unclaimed rest of the last tile this warp took from the
+// frame-wide queue (one atomicAdd of `batch` items when it runs out).  A lane that finishes its pixel continues inside
+// its warp's tile, so the rays of a warp stay neighbours in the image however long the sample chains are (with one
+// pixel-granular queue they drift apart: lanes finish one at a time, wherever the frame-wide head happens to be).
+// batch = 1 restores that queue — for frames with only a few pixels per lane, where the tail of the frame is what counts.
+// Every lane of the warp calls; the result is meaningful for the lanes in m.
+__device__ __forceinline__ uint32_t claim_items(const RenderLaunch &p, const unsigned m, const unsigned lane, uint32_t &stock_next,
+                                                uint32_t &stock_end, const uint32_t batch) {
+    const uint32_t k = (uint32_t)__popc(m), rank = (uint32_t)__popc(m & ((1u << lane) - 1u)), avail = stock_end - stock_next;
+    uint32_t item = stock_next + rank;
+    if (k <= avail) {
+        stock_next += k;
+    } else {
+        const uint32_t need = k - avail, claim = (need + batch - 1u) / batch * batch;
+        uint32_t base = 0;
+        const int leader = __ffs(m) - 1;
+        if ((int)lane == leader) base = atomicAdd(p.work_counter, claim);
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (rank >= avail) item = base + (rank - avail);
+        stock_next = base + need;
+        stock_end = base + claim;
+    }
+    return item;
+}
+__device__ __forceinline__ uint32_t claim_batch(const RenderLaunch &p) {   // pixels per lane decide: whole tiles, or single pixels
+    if (p.variant == 31) return 1u;          // A/B: the frame-wide pixel queue
+    return p.total_items / (gridDim.x * blockDim.x) >= 4u ? 32u : 1u;
+}
+
 template <bool OCTREE, bool GEOM_SMEM>
 __global__ void __launch_bounds__(kRenderThreads, 4) k_render(const __grid_constant__ RenderLaunch p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -147,8 +177,8 @@ __global__ void __launch_bounds__(kRenderThreads, 4) k_render(const __grid_const
     TraceCounters tc;
     tc.sphere_tests = tc.node_tests = tc.voxel_steps = 0;
     bool exhausted = false;
-    uint32_t first_item = gwarp * 32u + lane;   // the first claim needs no atomic: the queue head starts past the grid
-    bool first = true;
+    uint32_t stock_next = gwarp * 32u, stock_end = stock_next + 32u;   // the first tile needs no atomic: the queue head starts past the grid
+    const uint32_t batch = claim_batch(p);
     const float inv_ns = __fdiv_rn(1.0f, (float)p.ns_total);   // vec3.h:137-144: k = 1.0/t
 
     while (true) {
@@ -157,16 +187,7 @@ __global__ void __launch_bounds__(kRenderThreads, 4) k_render(const __grid_const
             const bool need = pix < 0 && !exhausted;
             const unsigned m = __ballot_sync(0xffffffffu, need);
             if (!m) break;
-            uint32_t item;
-            if (first) {
-                item = first_item;
-            } else {
-                uint32_t base = 0;
-                const int leader = __ffs(m) - 1;
-                if ((int)lane == leader) base = atomicAdd(p.work_counter, (uint32_t)__popc(m));
-                base = __shfl_sync(0xffffffffu, base, leader);
-                item = base + (uint32_t)__popc(m & ((1u << lane) - 1u));
-            }
+            const uint32_t item = claim_items(p, m, lane, stock_next, stock_end, batch);
             if (need) {
                 if (item >= p.total_items) {
                     exhausted = true;
@@ -177,7 +198,6 @@ __global__ void __launch_bounds__(kRenderThreads, 4) k_render(const __grid_const
                     pixel_stream(p, pix, rng);
                 }
             }
-            first = false;
         }
         if (!__ballot_sync(0xffffffffu, pix >= 0)) break;
 
