@@ -471,3 +471,36 @@ def test_cli_modes_write_the_reference_image(pkg, golden_dir, tmp_path):
     r1 = subprocess.run([exe, "1"], cwd=tmp_path, env=env, capture_output=True, check=True)
     assert r1.stdout == b"" and not (tmp_path / "output.ppm").exists()
     assert subprocess.run([exe, "x"], cwd=tmp_path, env=env, capture_output=True).returncode != 0
+
+
+@pytest.mark.parametrize("n,spl,nx,ny,ns", [
+    (100000, 300, 192, 108, 2),
+    (8000, 30, 240, 160, 4),
+    (20000, 30, 160, 96, 2),             # bucket overflow: no_drops = 0, every hit goes through the exact visibility rule
+    (488, 30, 37, 23, 5),                # big spheres in the prolog list, image not a multiple of the tile
+])
+def test_pooled_kernel_matches_oracle(rt, O, n, spl, nx, ny, ns):
+    """k_render_pool forced (variant 11; the automatic choice keeps it for big scenes and big frames) against the oracle."""
+    rt.create_world(n, 0.1)
+    rt.build_octree(spl)
+    sph, _ = O.create_world(n)
+    blob, _ = O.build_octree(sph, spl)
+    fb, s = rt.render(nx, ny, ns, use_octree=True, variant=11)
+    ref, _, ctr = O.render(sph, O.camera(nx, ny, O.ARITH_DEVICE), O.make_params(nx, ny, ns, True, spl, O.ARITH_DEVICE), blob)
+    assert _frac_identical(fb, ref) >= 1 - POWF_ALLOWANCE
+    assert abs(int(s["rays"]) - ctr["rays"]) <= max(2, int(POWF_ALLOWANCE * ctr["rays"])) and s["paths"] == nx * ny * ns
+
+
+def test_pooled_and_plain_kernels_agree_at_4k(rt):
+    """Config 3 scene at 3840x2160 (two-tile claims per warp in the pooled kernel, tile claims in the plain one, single-pixel
+    claims with variant 31): the same frame from k_render_pool (automatic here), k_render (variant 1) and the pixel queue."""
+    import torch
+    nx, ny = 3840, 2160
+    rt.create_world(100000, 0.1)
+    rt.build_octree(300)
+    fbs = []
+    for v in (0, 1, 31):
+        fb = torch.empty((ny, nx, 3), dtype=torch.float32, device="cuda")
+        st = rt.render_device(rt.args(nx, ny, 1, True, variant=v), fb.data_ptr())
+        fbs.append((fb, st["rays"]))
+    assert torch.equal(fbs[0][0], fbs[1][0]) and torch.equal(fbs[0][0], fbs[2][0]) and fbs[0][1] == fbs[1][1] == fbs[2][1]
