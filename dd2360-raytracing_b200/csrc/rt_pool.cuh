@@ -322,7 +322,7 @@ __device__ __forceinline__ void gen_sample(const Ctx<NC> c, const RenderLaunch &
 // so the contexts of a warp stay neighbours in the image however long their sample chains are.  With one global
 // pixel-granular queue they drifted apart — contexts finish one at a time, and every claim landed wherever the
 // frame-wide queue head was — and the warp's candidate loads stopped sharing cache lines: at 64 spp the 1 M-sphere scene
-// ran at 60 % of its 1-spp rate (profiles/README.md r02a).
+// ran at 60 % of its 1-spp rate (profiles/README.md "tile stock").
 template <int NC>
 __device__ __forceinline__ void body_sample(const Ctx<NC> c, const bool have, const RenderLaunch &p, const float inv_ns, const unsigned lt,
                                             uint32_t &nrays, uint32_t &npaths, uint32_t &stock_next, uint32_t &stock_end, const uint32_t batch) {
@@ -429,7 +429,7 @@ __global__ void __launch_bounds__(kRenderThreads, MINB) k_render_pool(const __gr
     uint32_t stock_next = 0, stock_end = 0;      // this warp's unclaimed queue items (body_sample)
     // pixels per context decide the claim size: two tiles with plenty of work, one tile in between, and single pixels
     // (no stock: the old frame-wide queue) when a context sees fewer than 4 pixels — there the tail of the frame is
-    // what matters and stocked pixels would only start later (measured, profiles/README.md r02a)
+    // what matters and stocked pixels would only start later (measured, profiles/README.md "tile stock")
     const uint32_t per_ctx = p.total_items / (gridDim.x * (kRenderThreads / 32) * NC);
     const uint32_t batch = per_ctx >= 24u ? 64u : (per_ctx >= 4u ? 32u : 1u);
 

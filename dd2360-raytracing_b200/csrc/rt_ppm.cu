@@ -77,19 +77,30 @@ __global__ void __launch_bounds__(kPpmThreads) k_ppm_len(const float *__restrict
 
 // exclusive scan of n block lengths into 64-bit offsets starting at `first`; off[n] = total
 __global__ void __launch_bounds__(1024) k_ppm_scan(const uint32_t *__restrict__ len, size_t n, unsigned long long first, unsigned long long *__restrict__ off) {
-    __shared__ unsigned long long part[1024];
+    __shared__ unsigned long long warp_tot[32];
     const size_t per = (n + 1023) / 1024, b = threadIdx.x * per, e = b + per < n ? b + per : n;
     unsigned long long s = 0;
     for (size_t k = b; k < e; k++) s += len[k];
-    part[threadIdx.x] = s;
+    // exclusive block scan of the per-thread sums: shuffles inside a warp, then the 32 warp totals
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    unsigned long long incl = s;
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= (unsigned)o) incl += v;
+    }
+    if (lane == 31u) warp_tot[warp] = incl;
     __syncthreads();
-    if (threadIdx.x == 0) {
-        unsigned long long acc = first;
-        for (int k = 0; k < 1024; k++) { const unsigned long long v = part[k]; part[k] = acc; acc += v; }
-        off[n] = acc;
+    if (warp == 0) {
+        unsigned long long t = warp_tot[lane], ti = t;
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long v = __shfl_up_sync(0xffffffffu, ti, o);
+            if (lane >= (unsigned)o) ti += v;
+        }
+        warp_tot[lane] = ti - t;                    // exclusive
+        if (lane == 31u) off[n] = first + ti;       // total text length
     }
     __syncthreads();
-    unsigned long long acc = part[threadIdx.x];
+    unsigned long long acc = first + warp_tot[warp] + (incl - s);
     for (size_t k = b; k < e; k++) { off[k] = acc; acc += len[k]; }
 }
 

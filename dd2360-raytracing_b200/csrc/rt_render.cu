@@ -400,12 +400,13 @@ cudaError_t launch_render(const RenderLaunch &p, bool octree, int sm_count, size
             case 12: return pool::launch_pool<128, 3>(p, sm_count, st, blocks_out);
             case 13: return pool::launch_pool<32, 8>(p, sm_count, st, blocks_out);
             case 14: return pool::launch_pool<64, 4>(p, sm_count, st, blocks_out);
+            case 15: return pool::launch_pool<64, 5>(p, sm_count, st, blocks_out);
             case 1: return launch_variant<true, false>(p, 0, sm_count, st, blocks_out);
             default:
                 // measured on B200 (profiles/README.md r01m): the pooled kernel wins once candidate lists are long
                 // (+28 % at 100 k spheres 4K, +34 % at 1 M); short lists (< ~50 k spheres) leave its scheduling rounds
                 // too little work to amortise, there the pixel-per-lane kernel is ~30 % faster
-                // (r02a sweep, profiles/sweep_pool_threshold.py: crossover at ~30 k spheres for a 4K frame; a frame with only
+                // (profiles/sweep_pool_threshold.py: crossover at ~30 k spheres for a 4K frame; a frame with only
                 // a few pixels per pool context — 1200x800 — pays the pool's start-up and tail until ~100 k spheres)
                 if (p.scene.n >= kPoolMinSpheres &&
                     (p.scene.n >= 3 * kPoolMinSpheres || p.total_items >= 8u * (uint32_t)sm_count * 6u * (kRenderThreads / 32) * 64u))
