@@ -600,7 +600,10 @@ __device__ __forceinline__ void walk_cells_h(CoopSmem &sm, const hf *planes_h, c
     __syncwarp();
 }
 
-template <bool OCTREE>
+// COOPN (the default): the line tests of ray r by the whole warp (root + level 1 in one step, level 2 in one, level 3 for
+// the children of four passing level-2 nodes per step; slab planes as halves in shared memory).  COOPN = false runs
+// walk_cells_h instead — measured 4 % (C4) to 20 % (488 spheres) slower, kept as the A/B partner (variant 33)
+template <bool OCTREE, bool COOPN>
 __device__ __forceinline__ HitH coop_trace_h2(CoopSmem &sm, const hf *planes_h, const PairView pv, const NodeTab nt, const uint2 *geom_h,
                                               const bool have_ray, const vec3h o, const vec3h d) {
     const unsigned full = 0xffffffffu;
@@ -608,7 +611,15 @@ __device__ __forceinline__ HitH coop_trace_h2(CoopSmem &sm, const hf *planes_h, 
     HitH mine;
     mine.t = f2h(3.402823466e+38f);
     mine.idx = -1;
-    if (OCTREE) walk_cells_h(sm, planes_h, nt, __ldg(nt.count), have_ray, lane, o, d);
+    if (OCTREE && !COOPN) walk_cells_h(sm, planes_h, nt, __ldg(nt.count), have_ray, lane, o, d);
+    const unsigned lt = (1u << lane) - 1u;
+    uint32_t n1 = 0, n2 = 0;
+    if (OCTREE && COOPN) { n1 = __ldg(nt.count); n2 = __ldg(nt.count + 1); }
+    auto pass = [&](const uint32_t ex, const int level, const vec3h ro, const vec3h rd) {
+        const int ix = ex & 255, iy = (ex >> 8) & 255, iz = (ex >> 16) & 255, sh = 3 - level;
+        return ref_line_test_h(ro, rd, planes_h[ix << sh], planes_h[kPlanes + (iy << sh)], planes_h[2 * kPlanes + (iz << sh)],
+                               planes_h[(ix + 1) << sh], planes_h[kPlanes + ((iy + 1) << sh)], planes_h[2 * kPlanes + ((iz + 1) << sh)]);
+    };
     unsigned todo = __ballot_sync(full, have_ray);
     while (todo) {
         const int r = __ffs(todo) - 1;
@@ -634,13 +645,53 @@ __device__ __forceinline__ HitH coop_trace_h2(CoopSmem &sm, const hf *planes_h, 
             coop_filter_h(sm, pv, geom_h, __ldg(pv.start), __ldg(pv.start + 1), lane, ro, rd, a, head, best);   // hitable_list.h:16-31
         } else {
             if (lane == 0) { sm.ring[head & 511u] = 0u; sm.tail = head + 1u; }     // the ground sphere, tested unconditionally (:322-332)
-            for (int w = 0; w < 16; w++) {                                          // the cells ray r passes, in Morton order
-                uint32_t word = sm.cells[w][r];
-                while (word) {
-                    const uint32_t cell = 32u * w + (uint32_t)__ffs((int)word) - 1u;
-                    word &= word - 1u;
-                    coop_filter_h(sm, pv, geom_h, __ldg(pv.start + cell), __ldg(pv.start + cell + 1), lane, ro, rd, a, head, best);
+            if (!COOPN) {
+                for (int w = 0; w < 16; w++) {                                      // the cells ray r passes, in Morton order
+                    uint32_t word = sm.cells[w][r];
+                    while (word) {
+                        const uint32_t cell = 32u * w + (uint32_t)__ffs((int)word) - 1u;
+                        word &= word - 1u;
+                        coop_filter_h(sm, pv, geom_h, __ldg(pv.start + cell), __ldg(pv.start + cell + 1), lane, ro, rd, a, head, best);
+                    }
                 }
+            } else {
+                uint32_t *plist = &sm.cells[0][0];                                  // level-2 nodes that passed, compacted
+                uint2 e = make_uint2(0u, 0u);
+                if (lane >= 1u && lane <= n1) e = __ldg(nt.ent + lane - 1u);
+                const unsigned m01 = __ballot_sync(full, lane <= n1 && pass(e.x, lane ? 1 : 0, ro, rd));
+                const unsigned m1 = (n1 > 0 && (m01 & 1u)) ? m01 >> 1 : 0u;
+                uint32_t np = 0;
+                if (m1) {
+                    for (uint32_t b2 = 0; b2 < n2; b2 += 32u) {
+                        const uint32_t j = b2 + lane;
+                        const uint2 e2 = j < n2 ? __ldg(nt.ent + 8 + j) : make_uint2(0u, 0u);
+                        const bool ok = j < n2 && ((m1 >> (e2.y & 0xffffu)) & 1u) && pass(e2.x, 2, ro, rd);
+                        const unsigned m2 = __ballot_sync(full, ok);
+                        if (ok) plist[np + __popc(m2 & lt)] = j;
+                        np += __popc(m2);
+                    }
+                }
+                __syncwarp();
+                for (uint32_t b3 = 0; b3 < np; b3 += 4u) {
+                    const uint32_t slot = b3 + (lane >> 3);
+                    uint2 e3 = make_uint2(0u, 0u);
+                    bool ok = false;
+                    if (slot < np) {
+                        const uint32_t kid = __ldg(nt.count + 4 + plist[slot]);       // first child | count << 16
+                        if ((lane & 7u) < (kid >> 16)) {
+                            e3 = __ldg(nt.ent + 72 + (kid & 0xffffu) + (lane & 7u));
+                            ok = pass(e3.x, 3, ro, rd);
+                        }
+                    }
+                    unsigned m3 = __ballot_sync(full, ok);
+                    while (m3) {
+                        const int c = __ffs(m3) - 1;
+                        m3 &= m3 - 1u;
+                        const uint32_t cell = __shfl_sync(full, e3.y >> 16, c);
+                        coop_filter_h(sm, pv, geom_h, __ldg(pv.start + cell), __ldg(pv.start + cell + 1), lane, ro, rd, a, head, best);
+                    }
+                }
+                __syncwarp();
             }
         }
         coop_drain_h(sm, pv, geom_h, head, true, lane, ro, rd, a, best);

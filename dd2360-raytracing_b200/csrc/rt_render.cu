@@ -302,7 +302,9 @@ cudaError_t launch_render_half(const RenderLaunch &p, bool octree, const uint2 *
     if (p.variant == 30)        // A/B: root evaluation inside the scan loop (the first cooperative form); same image
         return octree ? h16::launch_half<true, false>(p, geom_h, matl_h, cam_h, pv, nt, sm_count, st, blocks_out)
                       : h16::launch_half<false, false>(p, geom_h, matl_h, cam_h, pv, nt, sm_count, st, blocks_out);
-    return octree ? h16::launch_half<true, true>(p, geom_h, matl_h, cam_h, pv, nt, sm_count, st, blocks_out)
+    if (p.variant == 33 && octree)      // A/B: the octree line tests as a per-lane walk (walk_cells_h) instead of by the whole warp per ray;
+        return h16::launch_half<true, true, false>(p, geom_h, matl_h, cam_h, pv, nt, sm_count, st, blocks_out);   // same image, 4 - 20 % slower
+    return octree ? h16::launch_half<true, true, true>(p, geom_h, matl_h, cam_h, pv, nt, sm_count, st, blocks_out)
                   : h16::launch_half<false, true>(p, geom_h, matl_h, cam_h, pv, nt, sm_count, st, blocks_out);
 }
 

@@ -154,7 +154,7 @@ __global__ void k_camera_setup_h(const float lfx, const float lfy, const float l
 }
 
 // COOP2: closest hit by coop_trace_h2 (filter and roots in separate converged phases); false keeps coop_trace_h for A/B runs
-template <bool OCTREE, bool COOP2>
+template <bool OCTREE, bool COOP2, bool COOPN = false>
 __global__ void __launch_bounds__(kRenderThreads, 5)
 k_render_h(const __grid_constant__ RenderLaunch p, const uint2 *__restrict__ geom_h, const uint2 *__restrict__ matl_h,
            const __half *__restrict__ cam_h, const PairView pv, const NodeTab nt) {
@@ -218,7 +218,7 @@ k_render_h(const __grid_constant__ RenderLaunch p, const uint2 *__restrict__ geo
             nrays++;
         }
         // closest hit of every lane's ray, one ray at a time by the whole warp (rt_half.cuh coop_trace_h)
-        const HitH h = COOP2 ? coop_trace_h2<OCTREE>(coop_sm[threadIdx.x >> 5], planes_h, pv, nt, geom_h, have, o, d)
+        const HitH h = COOP2 ? coop_trace_h2<OCTREE, COOPN>(coop_sm[threadIdx.x >> 5], planes_h, pv, nt, geom_h, have, o, d)
                              : coop_trace_h<OCTREE>(pv, nt, geom_h, p.tree, have, o, d);
         if (have) {
             bool sample_done = false;
@@ -268,10 +268,10 @@ k_render_h(const __grid_constant__ RenderLaunch p, const uint2 *__restrict__ geo
     }
 }
 
-template <bool OCTREE, bool COOP2>
+template <bool OCTREE, bool COOP2, bool COOPN = false>
 static cudaError_t launch_half(const RenderLaunch &p, const uint2 *geom_h, const uint2 *matl_h, const __half *cam_h, const PairView pv,
                                const NodeTab nt, int sm_count, cudaStream_t st, int *blocks_out) {
-    auto kern = k_render_h<OCTREE, COOP2>;
+    auto kern = k_render_h<OCTREE, COOP2, COOPN>;
     int per_sm = 0;
     cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kRenderThreads, 0);
     if (e != cudaSuccess) return e;
