@@ -211,7 +211,7 @@ __device__ __forceinline__ void body_enter(const Ctx<NC> c, const RenderLaunch &
     if (g.nx == 0) { end_walk(c); return; }
     RayPre r;
     r.o = o; r.d = d; r.a = 0.f;
-    r.inv = mk(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+    r.inv = mk(rcp_trav(d.x), rcp_trav(d.y), rcp_trav(d.z));
     float te, tx;
     if (!ray_box(r, g.org, g.hi, ht * (1.0f + kTSlackRel) + kTSlackAbs, te, tx)) { end_walk(c); return; }
     int ix = (int)floorf((o.x + d.x * te - g.org[0]) * g.inv_vs[0]);

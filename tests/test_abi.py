@@ -86,3 +86,24 @@ def test_library_skip_ahead_matches_curand(pkg, golden_dir):
         assert [int(x) for x in pkg.xorwow_state(c["seed"], c["subsequence"])] == c["state"], c
     with pytest.raises(pkg.RtError):
         pkg.xorwow_state(1984, 2 ** 40)
+
+
+def test_experiment_harness_tables_on_cpu():
+    """analysis/run_experiment.py: the summary tables (the notebook's two figures) from synthetic run rows — no GPU needed;
+    also that the product scripts never reach into oracle/."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("run_experiment", os.path.join(ROOT, "analysis", "run_experiment.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    assert [mod.spheres_per_leaf(n) for n in (488, 9000, 100000, 1000000)] == [30, 30, 300, 3000]
+    rows = []
+    for mode, k in (("BASELINE", 4.0), ("OCTREE", 2.0)):
+        for it in (1, 2, 3):
+            rows.append({"mode": mode, "n": 488, "radius": 0.1, "iter": it, "spl": 30, "world_s": 1e-3, "octree_s": 2e-4, "render_s": 5e-3,
+                         "kernel_ms": k + 0.1 * it, "total_s": 8e-3, "rays": 19_000_000, "mrays_s": 19_000 / (k + 0.1 * it),
+                         "mem_used_mib": 640.0, "ppm": ""})
+    md = mod.summarise(rows, 1200, 800, 10)
+    line = [l for l in md.splitlines() if l.startswith("| 488 |")][0]
+    assert "| 4.200 | 2.200 | 1.91x |" in line and "median of 3 runs" in md and "SPHERE_RADIUS = 0.1" in md
+    src = open(os.path.join(ROOT, "analysis", "run_experiment.py")).read()
+    assert "load_oracle" not in src and "oracle_py" not in src
