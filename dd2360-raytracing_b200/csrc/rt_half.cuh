@@ -262,80 +262,15 @@ struct PairView {
     const uint32_t *start;    // pairs of list m: [start[m], start[m+1])
 };
 
-__device__ __forceinline__ void scan_pairs_h(const PairView pv, const uint2 *geom_h, const uint32_t pb, const uint32_t pe, const vec3h o,
-                                             const vec3h d, const hf a, HitH &h) {
-    const __half2 ox = __half2half2(vx(o)), oy = __half2half2(vy(o)), oz = __half2half2(o.z);
-    const __half2 dx = __half2half2(vx(d)), dy = __half2half2(vy(d)), dz = __half2half2(d.z);
-    const __half2 a2 = __half2half2(a);
-    const __half2 zero2 = __float2half2_rn(0.0f);
-    for (uint32_t k = pb; k < pe; k++) {
-        const uint4 g = __ldg(pv.geom + k);
-        const __half2 cx = *reinterpret_cast<const __half2 *>(&g.x), cy = *reinterpret_cast<const __half2 *>(&g.y);
-        const __half2 cz = *reinterpret_cast<const __half2 *>(&g.z), r = *reinterpret_cast<const __half2 *>(&g.w);
-        const __half2 ocx = __hsub2_rn(ox, cx), ocy = __hsub2_rn(oy, cy), ocz = __hsub2_rn(oz, cz);        // sphere.h:18
-        const __half2 b = __hfma2(ocz, dz, __hfma2(ocx, dx, __hmul2_rn(ocy, dy)));                           // :20
-        const __half2 c = __hfma2(__hneg2(r), r, __hfma2(ocz, ocz, __hfma2(ocx, ocx, __hmul2_rn(ocy, ocy))));   // :21
-        const __half2 disc = __hfma2(b, b, __hneg2(__hmul2_rn(a2, c)));                                      // :22
-        const __half2 pos = __hgt2(disc, zero2);                      // 1.0 where the discriminant is positive (NaN: 0)
-        if (*reinterpret_cast<const uint32_t *>(&pos) != 0u) {
-            const int2 id = __ldg(pv.idx + k);
-            hf t;
-            if (__hgt(__low2half(disc), __float2half_rn(0.0f)) && sphere_test_h(load_sphere_h(geom_h, id.x), o, d, a, h.t, t)) { h.t = t; h.idx = id.x; }
-            if (__hgt(__high2half(disc), __float2half_rn(0.0f)) && id.y >= 0 && sphere_test_h(load_sphere_h(geom_h, id.y), o, d, a, h.t, t)) { h.t = t; h.idx = id.y; }
-        }
-    }
-}
-
-// hitable_list.h:16-31 under USE_FP16: every sphere in ascending index order, strict '<'.
-__device__ __forceinline__ HitH trace_list_h(const PairView pv, const uint2 *geom_h, const vec3h o, const vec3h d) {
-    HitH h;
-    h.t = f2h(3.402823466e+38f);          // real_t(FLT_MAX) = +inf
-    h.idx = -1;
-    scan_pairs_h(pv, geom_h, __ldg(pv.start), __ldg(pv.start + 1), o, d, dot3h(d, d), h);
-    return h;
-}
-
-// acceleration_structure.h:276-342 under USE_FP16: ground sphere first, then the tree in the reference's own order —
-// children by octant index at every level (= ascending Morton code), the stored list of each level-3 cell in
-// insertion (= ascending sphere index) order — with the half-precision line test at EVERY level (approximate __hdiv is
-// not monotone, so a child's pass does not imply its parent's).  No sub-grid here: in half arithmetic a sphere can
-// "hit" far from where it is, so every sphere of a passing cell is a real candidate, exactly as in the reference.
-__device__ __forceinline__ HitH trace_tree_h(const PairView pv, const uint2 *geom_h, const TreeView &tv, const vec3h o, const vec3h d) {
-    HitH h;
-    h.t = f2h(3.402823466e+38f);
-    h.idx = -1;
-    const hf a = dot3h(d, d);
-    {
-        hf t;
-        if (sphere_test_h(load_sphere_h(geom_h, 0), o, d, a, h.t, t)) { h.t = t; h.idx = 0; }     // :322-332
-    }
-    const float *P = &tv.planes[0][0];
-    auto box_pass = [&](int level, int ix, int iy, int iz) {
-        const int sh = 3 - level;
-        return ref_line_test_h(o, d, f2h(P[ix << sh]), f2h(P[kPlanes + (iy << sh)]), f2h(P[2 * kPlanes + (iz << sh)]),
-                               f2h(P[(ix + 1) << sh]), f2h(P[kPlanes + ((iy + 1) << sh)]), f2h(P[2 * kPlanes + ((iz + 1) << sh)]));
-    };
-    const uint32_t *cs = tv.cell_start;                  // node existence: a node was created iff its subtree received an entry
-    if (__ldg(cs + kCells) == 0u || !box_pass(0, 0, 0, 0)) return h;
-    for (int c1 = 0; c1 < 8; c1++) {
-        if (__ldg(cs + c1 * 64 + 64) == __ldg(cs + c1 * 64)) continue;                  // child node never created
-        const int x1 = c1 >> 2, y1 = (c1 >> 1) & 1, z1 = c1 & 1;
-        if (!box_pass(1, x1, y1, z1)) continue;
-        for (int c2 = 0; c2 < 8; c2++) {
-            const int m2 = c1 * 8 + c2;
-            if (__ldg(cs + m2 * 8 + 8) == __ldg(cs + m2 * 8)) continue;
-            const int x2 = x1 * 2 + (c2 >> 2), y2 = y1 * 2 + ((c2 >> 1) & 1), z2 = z1 * 2 + (c2 & 1);
-            if (!box_pass(2, x2, y2, z2)) continue;
-            for (int c3 = 0; c3 < 8; c3++) {
-                const int m3 = m2 * 8 + c3;
-                if (__ldg(cs + m3 + 1) == __ldg(cs + m3)) continue;
-                if (!box_pass(3, x2 * 2 + (c3 >> 2), y2 * 2 + ((c3 >> 1) & 1), z2 * 2 + (c3 & 1))) continue;
-                scan_pairs_h(pv, geom_h, __ldg(pv.start + m3), __ldg(pv.start + m3 + 1), o, d, a, h);   // entries beyond 8*SPL were dropped (:135)
-            }
-        }
-    }
-    return h;
-}
+// Semantics the cooperative scans below reproduce (the per-lane statement of it lived here until the warp-cooperative
+// forms replaced it):
+//   flat list (hitable_list.h:16-31): every sphere in ascending index order, strict '<' against closest_so_far;
+//   octree (acceleration_structure.h:276-342): ground sphere first, then the tree in the reference's own order — children
+//   by octant index at every level (= ascending Morton code), the stored list of each level-3 cell in insertion
+//   (= ascending sphere index) order — with the half-precision line test at EVERY level (approximate __hdiv is not
+//   monotone, so a child's pass does not imply its parent's); entries beyond 8*SPL per cell were dropped (:135).
+//   No sub-grid: in half arithmetic a sphere can "hit" far from where it is, so every sphere of a passing cell is a real
+//   candidate, exactly as in the reference.
 
 // ---- warp-cooperative closest hit ---------------------------------------------------------------------------------------------
 // The USE_FP16 closest hit is an exhaustive scan (every sphere of every passing cell: ~2 000 candidates per ray at 100 k

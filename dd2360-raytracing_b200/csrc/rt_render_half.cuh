@@ -3,7 +3,7 @@
 //
 // Same persistent, queue-fed kernel shape as k_render (one pixel chain per lane, ballot/popc-compacted claims), with the
 // per-lane state in half: ray, attenuation and — as in the reference, whose `vec3 col` is three halves (main.cu:101) —
-// the pixel accumulator.  Octree mode walks the reference's own cells (rt_half.cuh trace_tree_h): the sub-grid of the
+// the pixel accumulator.  Octree mode walks the reference's own cells (rt_half.cuh coop_trace_h2): the sub-grid of the
 // FP32 path is built on float error bounds that half arithmetic does not honour.
 #pragma once
 // (rt_half.cuh is included by rt_render.cu at file scope)
