@@ -318,6 +318,19 @@ def main():
                             "peak_source": "measured here: dense FFMA microbenchmark (rt_ffma_peak); MEASURED_PEAKS.json has no FP32 figure",
                             "note": "FP32 issue is the bounding unit (SURVEY §8d); HBM traffic is the 12 B/pixel frame only"}
         rti.close()
+        # the unit that actually bounds it: warp-instruction issue slots (4 schedulers per SM, one warp instruction per
+        # cycle each).  Instructions per ray come from the committed ncu capture of this kernel (profiles/), the rate is live.
+        try:
+            wpr = json.load(open(pj)).get(args.config, {}).get("warp_instructions_per_ray")
+            info = rt.device_info()
+            if wpr:
+                issue_peak = info["sm_count"] * 4 * info["clock_khz"] * 1e3
+                issue_ach = (total_rays / args.steps / world) * wpr / (km * 1e-3)
+                line["roofline_issue"] = {"bound": "issue", "achieved": issue_ach / 1e9, "peak": issue_peak / 1e9, "unit": "Gwarp-inst/s",
+                                          "frac": issue_ach / issue_peak, "warp_instructions_per_ray": wpr,
+                                          "note": "instructions per ray from profiles/roofline_inputs.json (ncu smsp__inst_executed.sum), rate measured here"}
+        except Exception:
+            pass
         # the same kernel against the HBM roofline, for the record: algorithmic bytes = the 12 B/pixel frame
         hbm_peak = None
         try:
