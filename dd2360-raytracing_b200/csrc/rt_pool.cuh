@@ -457,7 +457,11 @@ __global__ void __launch_bounds__(kRenderThreads, MINB) k_render_pool(const __gr
         int best;
         {
             const uint32_t word = lane < 4u ? w0 : w1;
-            const uint32_t key = lane < 8u ? ((word >> ((lane & 3u) * 8u)) & 255u) << 4 | (15u - lane) : 0u;
+            uint32_t cnt = (word >> ((lane & 3u) * 8u)) & 255u;
+            // a TEST round with few contexts wastes the most lanes of the most expensive body: below tune_test_min waiting
+            // contexts its count is quartered, so that fuller states (ENTER, STEP, CAND: the ones that feed TEST) run first
+            if (lane == (unsigned)S_TEST && cnt < (uint32_t)p.tune_test_min) cnt = (cnt + 3u) >> 2;
+            const uint32_t key = lane < 8u ? cnt << 4 | (15u - lane) : 0u;
             best = 15 - (int)(__reduce_max_sync(full, key) & 15u);
         }
         if (++rounds > p.max_rounds) {          // watchdog: a scheduling bug must never hang the GPU; the host reports it
