@@ -486,8 +486,8 @@ static int do_render(rt_context *ctx, const rt_render_args *a, float *out_dev, b
     p.finalize = finalize ? 1 : 0;
     p.variant = a->tune[1] ? a->tune[1] : ctx->default_variant;
     if (p.variant == 21) p.tree.check_visibility = 0;   // MEASUREMENT ONLY: cost of the visibility rule (same image only when nothing was dropped)
-    p.tune_sticky = a->tune[3] > 0 ? a->tune[3] : 4;
-    p.tune_sticky_min = a->tune[4] > 0 ? a->tune[4] : 8;
+    p.tune_sticky = a->tune[3] > 0 ? a->tune[3] : 8;              // re-swept after the tile stock (profiles/sweep_tune.py): 8 / 16
+    p.tune_sticky_min = a->tune[4] > 0 ? a->tune[4] : 16;
     p.tune_test_min = a->tune[5] > 0 ? a->tune[5] : (a->tune[5] < 0 ? 0 : 24);     // measured: C3 +2 %, C5 +6 % over 0 (profiles/sweep_test_min.py)
     p.max_rounds = a->tune[2] > 0 ? (uint32_t)a->tune[2] : 0x7fffffffu;            // A/B measurement knob; every variant renders the same image
     p.out = out_dev;
