@@ -143,7 +143,7 @@ __device__ __forceinline__ uint32_t claim_batch(const RenderLaunch &p) {   // pi
 }
 
 template <bool OCTREE, bool GEOM_SMEM>
-__global__ void __launch_bounds__(kRenderThreads, 4) k_render(const __grid_constant__ RenderLaunch p) {
+__global__ void __launch_bounds__(kRenderThreads, 6) k_render(const __grid_constant__ RenderLaunch p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t bar;
 
@@ -405,11 +405,11 @@ cudaError_t launch_render(const RenderLaunch &p, bool octree, int sm_count, size
             case 15: return pool::launch_pool<64, 5>(p, sm_count, st, blocks_out);
             case 1: return launch_variant<true, false>(p, 0, sm_count, st, blocks_out);
             default:
-                // measured on B200 (profiles/README.md r01m): the pooled kernel wins once candidate lists are long
-                // (+28 % at 100 k spheres 4K, +34 % at 1 M); short lists (< ~50 k spheres) leave its scheduling rounds
-                // too little work to amortise, there the pixel-per-lane kernel is ~30 % faster
-                // (profiles/sweep_pool_threshold.py: crossover at ~30 k spheres for a 4K frame; a frame with only
-                // a few pixels per pool context — 1200x800 — pays the pool's start-up and tail until ~100 k spheres)
+                // measured on B200 (profiles/README.md): the pooled kernel wins once candidate lists are long (+9 % at 100 k
+                // spheres at 4K, +62 % at 300 k); short lists leave its scheduling rounds too little work to amortise, there
+                // the pixel-per-lane kernel is 10 - 35 % faster
+                // (profiles/sweep_pool_threshold.py: crossover at ~75 k spheres for a 4K frame; a frame with only
+                // a few pixels per pool context — 1200x800 — pays the pool's start-up and tail until ~200 k spheres)
                 if (p.scene.n >= kPoolMinSpheres &&
                     (p.scene.n >= 3 * kPoolMinSpheres || p.total_items >= 8u * (uint32_t)sm_count * 6u * (kRenderThreads / 32) * 64u))
                     return pool::launch_pool<64, 6>(p, sm_count, st, blocks_out);
