@@ -580,6 +580,7 @@ __device__ __forceinline__ HitH coop_trace_h2(CoopSmem &sm, const hf *planes_h, 
             coop_filter_h(sm, pv, geom_h, __ldg(pv.start), __ldg(pv.start + 1), lane, ro, rd, a, head, best);   // hitable_list.h:16-31
         } else {
             if (lane == 0) { sm.ring[head & 511u] = 0u; sm.tail = head + 1u; }     // the ground sphere, tested unconditionally (:322-332)
+            __syncwarp();                                                           // the other lanes' ring pushes (shared atomics) come after this store
             if (!COOPN) {
                 for (int w = 0; w < 16; w++) {                                      // the cells ray r passes, in Morton order
                     uint32_t word = sm.cells[w][r];
