@@ -259,4 +259,62 @@ int hs_render_with_tree(const hs_sphere *sph, int n, const float *camera22, cons
     return render_core(sph, n, camera22, nullptr, p, 0.f, fb_gamma, nullptr, ctr_out, nullptr, &tv);
 }
 
+// Soundness of visible_fast (rt_trace.cuh) against the rule it short-cuts: for `nrays` pseudo-random rays — aimed at sphere
+// surfaces, many of them with origins ON cell planes, axis-parallel or zero direction components, far-away origins and
+// hits within 1e-3 of a cell face — every accepted root of every probed sphere is classified both ways.
+// out[0] hits probed, out[1] fast accepts, out[2] exact accepts, out[3] fast accepts the exact rule REJECTS (must be 0).
+int hs_visible_soundness(const hs_sphere *sph, int n, const void *blob, int spl, uint64_t seed, int nrays, uint64_t *out) {
+    std::vector<float4> geom((size_t)n);
+    std::vector<int> tag((size_t)n);
+    for (int i = 0; i < n; i++) { geom[(size_t)i] = make_float4(sph[i].cx, sph[i].cy, sph[i].cz, sph[i].radius); tag[(size_t)i] = sph[i].mat; }
+    HostTree T;
+    TreeView tv;
+    build_host_tree(geom, tag, static_cast<const int32_t *>(blob), spl, 4.0f, T);
+    view_of(T, tv);
+    const float *planes = &tv.planes[0][0];
+    uint64_t st = seed * 6364136223846793005ull + 1442695040888963407ull;
+    auto rnd = [&]() { st = st * 6364136223846793005ull + 1442695040888963407ull; return (float)((st >> 40) & 0xffffff) / 16777216.0f; };
+    out[0] = out[1] = out[2] = out[3] = 0;
+    TraceCounters tc;
+    tc.sphere_tests = tc.node_tests = tc.voxel_steps = 0;
+    for (int r = 0; r < nrays; r++) {
+        const int idx = 1 + (int)(rnd() * (float)(n - 1)) % (n - 1);
+        const float4 s = geom[(size_t)idx];
+        if (tag[(size_t)idx] < 0) continue;
+        // a point on (or, for grazing rays, just outside) the sphere, and an origin somewhere around the scene
+        float u = 2.f * rnd() - 1.f, ph = 6.2831853f * rnd(), q = sqrtf(fmaxf(0.f, 1.f - u * u));
+        const float graze = (r % 7 == 0) ? 1.0f + 1e-4f * rnd() : 1.0f;
+        vec3f target = mk(s.x + graze * s.w * q * cosf(ph), s.y + graze * s.w * u, s.z + graze * s.w * q * sinf(ph));
+        vec3f o = mk(-14.f + 28.f * rnd(), -0.5f + 4.f * rnd(), -14.f + 28.f * rnd());
+        const int kind = r % 11;
+        if (kind == 1) o.x = planes[(int)(rnd() * 8.99f)];                          // origin exactly on a cell plane
+        if (kind == 2) o.y = planes[kPlanes + (int)(rnd() * 8.99f)];
+        if (kind == 3) o.z = planes[2 * kPlanes + (int)(rnd() * 8.99f)];
+        if (kind == 4) o = mk(1e4f * (rnd() - 0.5f), 50.f * rnd(), 1e4f * (rnd() - 0.5f));   // far away
+        if (kind == 5) {                                                            // target within 1e-3 of a cell face
+            const int a = (int)(rnd() * 2.99f);
+            const float pl = planes[a * kPlanes + (int)(rnd() * 8.99f)] + 2e-3f * (rnd() - 0.5f);
+            if (a == 0) target.x = pl; else if (a == 1) target.y = pl; else target.z = pl;
+        }
+        vec3f d = mk(target.x - o.x, target.y - o.y, target.z - o.z);
+        if (kind == 6) { o.x = target.x; d.x = 0.0f; }                              // zero direction components
+        if (kind == 7) { o.z = target.z; d.z = -0.0f; }
+        if (kind == 8) { o.x = target.x; o.z = target.z; d.x = 0.0f; d.z = 0.0f; }  // vertical ray
+        if (kind == 9) d = mk(d.x * 1e-3f, d.y * 1e-3f, d.z * 1e-3f);              // short direction: large t
+        const float a = dot3(d, d);
+        // probe the aimed sphere and a few neighbours in index order (overlapping spheres in dense scenes)
+        for (int dj = 0; dj < 4; dj++) {
+            const int j = 1 + (idx - 1 + dj * 37) % (n - 1);
+            if (tag[(size_t)j] < 0) continue;
+            float t;
+            if (!sphere_test(geom[(size_t)j], o, d, a, kTMax, t)) continue;
+            int last_ok = -1;
+            const bool fast = visible_fast(tv, planes, geom[(size_t)j], o, d, t);
+            const bool exact = sphere_visible(tv.vis, planes, j, o, d, last_ok, tc);
+            out[0]++; out[1] += fast; out[2] += exact; out[3] += fast && !exact;
+        }
+    }
+    return 0;
+}
+
 }  // extern "C"

@@ -56,3 +56,23 @@ def test_irregular_scene(hostsim, O):
     fb, ref, c, ctr = _run(hostsim, O, n, 30, True, 120, 80, 3, spheres=sph)
     assert c.rays == ctr["rays"]
     assert np.array_equal(fb.view(np.uint32), ref.view(np.uint32))
+
+
+@pytest.mark.parametrize("n,spl,expect_fast", [(488, 30, True), (8000, 30, True), (100000, 300, True), (20000, 30, False)])
+def test_visible_fast_never_accepts_what_the_reference_rule_rejects(hostsim, O, n, spl, expect_fast):
+    """rt_trace.cuh visible_fast is a SUFFICIENT condition for the reference's visibility rule (a cell that stores the sphere
+    passes the line test): on 200 k adversarial rays per scene — origins on cell planes, zero direction components, far
+    origins, hits next to cell faces, grazing hits — it must never say yes where sphere_visible says no, and it should
+    settle most hits.  With overflowed buckets (20 000 spheres at SPL 30) it must defer everything to the exact rule."""
+    sph, _ = O.create_world(n)
+    blob, _ = O.build_octree(sph, spl)
+    out = np.zeros(4, dtype=np.uint64)
+    hostsim.hs_visible_soundness.restype = C.c_int
+    hostsim.hs_visible_soundness(C.c_void_p(sph.ctypes.data), len(sph), C.c_void_p(blob.ctypes.data), spl, C.c_uint64(1984 + n),
+                                 200000, C.c_void_p(out.ctypes.data))
+    hits, fast, exact, unsound = (int(x) for x in out)
+    assert hits > 100000 and unsound == 0, (hits, fast, exact, unsound)
+    if expect_fast:
+        assert fast >= 0.85 * exact, (hits, fast, exact)
+    else:
+        assert fast == 0
