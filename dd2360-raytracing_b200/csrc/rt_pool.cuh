@@ -70,25 +70,8 @@ struct Ctx {
 };
 
 __device__ __forceinline__ float rcp_fast(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
-__device__ __forceinline__ float sqrt_fast(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 
-// sphere.h:18-23 up to the discriminant (the same fused operations as sphere_test), then a conservative pre-filter
-// in front of the IEEE sqrt and divisions: both roots are estimated with approximate arithmetic; `true` means an
-// estimate is within its error bound of the accepted interval (kTMin, t_max) and the exact evaluation must decide.
-// Error bound: reciprocal and square root good to 2^-22 plus three roundings keep |estimate - float root| below
-// 3e-6 * (|b| + sqrt(disc)) / a; the filter allows 1e-5.  NaNs make every comparison false -> `true` (exact path).
-__device__ __forceinline__ bool maybe_hit(const float4 s, const vec3f o, const vec3f d, const float a, const float ia, const float t_max) {
-    const vec3f oc = mk(sub_(o.x, s.x), sub_(o.y, s.y), sub_(o.z, s.z));
-    const float b = dot3(oc, d);
-    const float c = fma_(-s.w, s.w, dot3(oc, oc));
-    const float disc = fma_(b, b, -mul_(a, c));
-    // branch-free on purpose: the lanes of a warp test unrelated spheres, so a branch on disc > 0 would split every test
-    const float sa = sqrt_fast(fmaxf(disc, 0.0f));
-    const float t1 = (-b - sa) * ia, t2 = (sa - b) * ia;
-    const float eps = (fabsf(b) + sa) * ia * 1e-5f;
-    const bool reject = (t1 - eps > t_max) | (t2 + eps < kTMin) | ((t1 + eps < kTMin) & (t2 - eps > t_max));
-    return (disc > 0.0f) & !reject;
-}
+// (the conservative root pre-filter `maybe_hit` lives in rt_trace.cuh: the pixel-per-lane kernel uses it too)
 
 // the careful re-walk (winner not visible) is rare: out of line, so it costs the bodies no registers
 __device__ __noinline__ Hit rewalk_checked(const SceneView &sc, const TreeView &tv, const float *planes, const vec3f o, const vec3f d) {

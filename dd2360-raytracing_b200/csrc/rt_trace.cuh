@@ -93,6 +93,34 @@ RT_HD float rcp_trav(const float x) {
 #endif
 }
 
+RT_HD float sqrt_trav(const float x) {
+#if defined(__CUDA_ARCH__)
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+#else
+    return sqrtf(x);
+#endif
+}
+
+// sphere.h:18-23 up to the discriminant (the same fused operations as sphere_test, so the compiler shares them), then a
+// conservative pre-filter in front of the IEEE sqrt and divisions: both roots are estimated with approximate arithmetic;
+// `true` means an estimate is within its error bound of the accepted interval (kTMin, t_max) and the exact evaluation
+// must decide.  Error bound: reciprocal and square root good to 2^-22 plus three roundings keep |estimate - float root|
+// below 3e-6 * (|b| + sqrt(disc)) / a; the filter allows 1e-5.  A NaN discriminant is not > 0: no candidate, as in
+// sphere_test.  ia = rcp_trav(a).  Branch-free on purpose: the lanes of a warp test unrelated spheres.
+RT_HD bool maybe_hit(const float4 s, const vec3f o, const vec3f d, const float a, const float ia, const float t_max) {
+    const vec3f oc = mk(sub_(o.x, s.x), sub_(o.y, s.y), sub_(o.z, s.z));
+    const float b = dot3(oc, d);
+    const float c = fma_(-s.w, s.w, dot3(oc, oc));
+    const float disc = fma_(b, b, -mul_(a, c));
+    const float sa = sqrt_trav(fmaxf(disc, 0.0f));
+    const float t1 = (-b - sa) * ia, t2 = (sa - b) * ia;
+    const float eps = (fabsf(b) + sa) * ia * 1e-5f;
+    const bool reject = (t1 - eps > t_max) | (t2 + eps < kTMin) | ((t1 + eps < kTMin) & (t2 - eps > t_max));
+    return (disc > 0.0f) & !reject;
+}
+
 struct RayPre {
     vec3f o, d, inv;    // inv = 1/d (IEEE; +-inf for zero components)
     float a;            // dot(d,d)
@@ -183,6 +211,7 @@ RT_HD Hit trace_walk(const SceneView &sc, const TreeView &tv, const float *plane
     RayPre r;
     r.o = o; r.d = d;
     r.a = dot3(d, d);
+    const float ia = rcp_trav(r.a);
     {   // ground sphere first, unconditionally (:322-332)
         float t;
         RT_COUNT(sphere_tests);
@@ -193,7 +222,8 @@ RT_HD Hit trace_walk(const SceneView &sc, const TreeView &tv, const float *plane
         const int idx = (int)RT_LDG(tv.prolog + k);
         float t;
         RT_COUNT(sphere_tests);
-        if (sphere_test(RT_LDG(sc.geom + idx), o, d, r.a, h.t, t) &&
+        const float4 s = RT_LDG(sc.geom + idx);
+        if (maybe_hit(s, o, d, r.a, ia, h.t) && sphere_test(s, o, d, r.a, h.t, t) &&
             (!CHECKED || sphere_visible(tv.vis, planes, idx, o, d, last_ok, tc))) {
             h.t = t; h.idx = idx;
         }
@@ -243,14 +273,21 @@ RT_HD Hit trace_walk(const SceneView &sc, const TreeView &tv, const float *plane
             }
         }
         if (walking && k < e) {
-            const int idx = (int)RT_LDG(g.refs + k);
-            k++;
-            const float4 s = RT_LDG(sc.geom + idx);
+            // candidate geometry in list order (one dependent load; the index is only needed for a hit) and the
+            // conservative pre-filter in front of the exact test: ~8 of a ray's candidates have a positive discriminant,
+            // fewer than 2 can be the closest hit
+#if defined(__CUDA_ARCH__)
+            const float4 s = RT_LDG(g.ref_geom + k);
+#else
+            const float4 s = sc.geom[g.refs[k]];
+#endif
             float t;
             RT_COUNT(sphere_tests);
-            if (sphere_test(s, o, d, r.a, h.t, t) && (!CHECKED || sphere_visible(tv.vis, planes, idx, o, d, last_ok, tc))) {
-                h.t = t; h.idx = idx;
+            if (maybe_hit(s, o, d, r.a, ia, h.t) && sphere_test(s, o, d, r.a, h.t, t)) {
+                const int idx = (int)RT_LDG(g.refs + k);
+                if (!CHECKED || sphere_visible(tv.vis, planes, idx, o, d, last_ok, tc)) { h.t = t; h.idx = idx; }
             }
+            k++;
         }
     }
     return h;
