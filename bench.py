@@ -313,7 +313,7 @@ def main():
         if os.path.exists(pj):
             traffic = json.load(open(pj)).get(args.config, {}).get("dram_bytes_per_launch")
         line["roofline"] = {"bound": "fp32", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                            "traffic": traffic, "kernel": "k_render_pool<64,6>" if (octree and n >= 75000) else "k_render", "flop_per_ray": flop_per_ray,
+                            "traffic": traffic, "kernel": "k_render_pool<64,6>" if (octree and n >= 200000) else "k_render", "flop_per_ray": flop_per_ray,
                             "sphere_tests_per_ray": S, "node_tests_per_ray": B,
                             "peak_source": "measured here: dense FFMA microbenchmark (rt_ffma_peak); MEASURED_PEAKS.json has no FP32 figure",
                             "note": "FP32 issue is the bounding unit (SURVEY §8d); HBM traffic is the 12 B/pixel frame only"}

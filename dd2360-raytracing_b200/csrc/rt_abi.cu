@@ -485,6 +485,7 @@ static int do_render(rt_context *ctx, const rt_render_args *a, float *out_dev, b
     p.total_items = (uint32_t)(owned * 32);
     p.finalize = finalize ? 1 : 0;
     p.variant = a->tune[1] ? a->tune[1] : ctx->default_variant;
+    if (p.variant == 22) p.tree.walk_single = 1;         // A/B: one candidate per loop trip in the pixel-per-lane walk
     if (p.variant == 21) p.tree.check_visibility = 0;   // MEASUREMENT ONLY: cost of the visibility rule (same image only when nothing was dropped)
     p.tune_sticky = a->tune[3] > 0 ? a->tune[3] : 8;              // re-swept after the tile stock (profiles/sweep_tune.py): 8 / 16
     p.tune_sticky_min = a->tune[4] > 0 ? a->tune[4] : 16;

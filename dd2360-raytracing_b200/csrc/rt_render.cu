@@ -405,11 +405,9 @@ cudaError_t launch_render(const RenderLaunch &p, bool octree, int sm_count, size
             case 15: return pool::launch_pool<64, 5>(p, sm_count, st, blocks_out);
             case 1: return launch_variant<true, false>(p, 0, sm_count, st, blocks_out);
             default:
-                // measured on B200 (profiles/README.md): the pooled kernel wins once candidate lists are long (+9 % at 100 k
-                // spheres at 4K, +62 % at 300 k); short lists leave its scheduling rounds too little work to amortise, there
-                // the pixel-per-lane kernel is 10 - 35 % faster
-                // (profiles/sweep_pool_threshold.py: crossover at ~75 k spheres for a 4K frame; a frame with only
-                // a few pixels per pool context — 1200x800 — pays the pool's start-up and tail until ~200 k spheres)
+                // measured on B200 (profiles/README.md, profiles/sweep_pool_threshold.py at 4K): pooled / pixel-per-lane speed
+                // 0.87x at 100 k spheres, 1.07x at 300 k, ~1.5x at 1 M — the pooled kernel pays off once candidate lists are
+                // long; a frame with only a few pixels per pool context (1200x800) pays its start-up and tail for longer
                 if (p.scene.n >= kPoolMinSpheres &&
                     (p.scene.n >= 3 * kPoolMinSpheres || p.total_items >= 8u * (uint32_t)sm_count * 6u * (kRenderThreads / 32) * 64u))
                     return pool::launch_pool<64, 6>(p, sm_count, st, blocks_out);

@@ -275,19 +275,28 @@ RT_HD Hit trace_walk(const SceneView &sc, const TreeView &tv, const float *plane
         if (walking && k < e) {
             // candidate geometry in list order (one dependent load; the index is only needed for a hit) and the
             // conservative pre-filter in front of the exact test: ~8 of a ray's candidates have a positive discriminant,
-            // fewer than 2 can be the closest hit
+            // fewer than 2 can be the closest hit.  Two candidates per trip: their loads and filters are independent
+            // (the second filter sees the closest hit as it was before the first candidate — a larger bound, still
+            // conservative); the exact tests run in list order against the up-to-date bound.
+            const bool two = !tv.walk_single && k + 1 < e;
 #if defined(__CUDA_ARCH__)
-            const float4 s = RT_LDG(g.ref_geom + k);
+            const float4 s0 = RT_LDG(g.ref_geom + k), s1 = RT_LDG(g.ref_geom + (two ? k + 1 : k));
 #else
-            const float4 s = sc.geom[g.refs[k]];
+            const float4 s0 = sc.geom[g.refs[k]], s1 = sc.geom[g.refs[two ? k + 1 : k]];
 #endif
+            const bool m0 = maybe_hit(s0, o, d, r.a, ia, h.t), m1 = two & maybe_hit(s1, o, d, r.a, ia, h.t);
             float t;
             RT_COUNT(sphere_tests);
-            if (maybe_hit(s, o, d, r.a, ia, h.t) && sphere_test(s, o, d, r.a, h.t, t)) {
+            if (m0 && sphere_test(s0, o, d, r.a, h.t, t)) {
                 const int idx = (int)RT_LDG(g.refs + k);
                 if (!CHECKED || sphere_visible(tv.vis, planes, idx, o, d, last_ok, tc)) { h.t = t; h.idx = idx; }
             }
-            k++;
+            if (two) RT_COUNT(sphere_tests);
+            if (m1 && sphere_test(s1, o, d, r.a, h.t, t)) {
+                const int idx = (int)RT_LDG(g.refs + k + 1);
+                if (!CHECKED || sphere_visible(tv.vis, planes, idx, o, d, last_ok, tc)) { h.t = t; h.idx = idx; }
+            }
+            k += two ? 2u : 1u;
         }
     }
     return h;

@@ -74,6 +74,7 @@ struct TreeView {
     int no_drops;               // 1: the build dropped no entry ("Leaf nodes full" never happened), so a cell stores every sphere
                                 //    whose centre its r-expanded box contains
     float cell_inv[3];          // 8 / root box extent per axis: cell index guess from a coordinate
+    int walk_single;            // A/B knob: 1 = the pixel-per-lane walk tests one candidate per loop trip instead of two
 };
 
 }  // namespace rt

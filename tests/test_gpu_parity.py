@@ -480,7 +480,7 @@ def test_cli_modes_write_the_reference_image(pkg, golden_dir, tmp_path):
     (488, 30, 37, 23, 5),                # big spheres in the prolog list, image not a multiple of the tile
 ])
 def test_pooled_kernel_matches_oracle(rt, O, n, spl, nx, ny, ns):
-    """k_render_pool forced (variant 11; the automatic choice keeps it for big scenes and big frames) against the oracle."""
+    """k_render_pool forced (variant 11; the automatic choice keeps it for scenes from 200 k spheres on big frames) against the oracle."""
     rt.create_world(n, 0.1)
     rt.build_octree(spl)
     sph, _ = O.create_world(n)
@@ -493,13 +493,13 @@ def test_pooled_kernel_matches_oracle(rt, O, n, spl, nx, ny, ns):
 
 def test_pooled_and_plain_kernels_agree_at_4k(rt):
     """Config 3 scene at 3840x2160 (two-tile claims per warp in the pooled kernel, tile claims in the plain one, single-pixel
-    claims with variant 31): the same frame from k_render_pool (automatic here), k_render (variant 1) and the pixel queue."""
+    claims with variant 31): the same frame from k_render_pool (variant 11), k_render (variant 1) and the pixel queue."""
     import torch
     nx, ny = 3840, 2160
     rt.create_world(100000, 0.1)
     rt.build_octree(300)
     fbs = []
-    for v in (0, 1, 31):
+    for v in (11, 1, 31):
         fb = torch.empty((ny, nx, 3), dtype=torch.float32, device="cuda")
         st = rt.render_device(rt.args(nx, ny, 1, True, variant=v), fb.data_ptr())
         fbs.append((fb, st["rays"]))
