@@ -407,10 +407,8 @@ cudaError_t launch_render(const RenderLaunch &p, bool octree, int sm_count, size
             default:
                 // measured on B200 (profiles/README.md, profiles/sweep_pool_threshold.py at 4K): pooled / pixel-per-lane speed
                 // 0.87x at 100 k spheres, 1.07x at 300 k, ~1.5x at 1 M — the pooled kernel pays off once candidate lists are
-                // long; a frame with only a few pixels per pool context (1200x800) pays its start-up and tail for longer
-                if (p.scene.n >= kPoolMinSpheres &&
-                    (p.scene.n >= 3 * kPoolMinSpheres || p.total_items >= 8u * (uint32_t)sm_count * 6u * (kRenderThreads / 32) * 64u))
-                    return pool::launch_pool<64, 6>(p, sm_count, st, blocks_out);
+                // long (at 1200x800 the crossover sits in the same place: k_render ahead at 100 k, the pool at 300 k)
+                if (p.scene.n >= kPoolMinSpheres) return pool::launch_pool<64, 6>(p, sm_count, st, blocks_out);
                 return launch_variant<true, false>(p, 0, sm_count, st, blocks_out);
         }
     }

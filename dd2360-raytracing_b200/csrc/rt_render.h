@@ -10,7 +10,7 @@ namespace rt {
 
 constexpr int kRenderThreads = 128;
 constexpr int kListGridMinSpheres = 256;   // flat-list mode: scenes at least this large are answered through the grid
-constexpr int kPoolMinSpheres = 200000;  // octree mode: scenes at least this large use the pooled kernel (rt_pool.cuh) on big frames; 3x this on small ones
+constexpr int kPoolMinSpheres = 200000;  // octree mode: scenes at least this large use the pooled kernel (rt_pool.cuh)
 
 struct RenderLaunch {
     SceneView scene;
