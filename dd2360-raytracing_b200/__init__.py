@@ -41,7 +41,7 @@ ABI_SYMBOLS = [
     "rt_octree_build", "rt_octree_build_ex", "rt_octree_reference_bytes", "rt_octree_export_reference", "rt_octree_debug_read", "rt_xorwow_state", "rt_debug_counters", "rt_trace_rays",
     "rt_render_accumulate", "rt_finalize", "rt_render", "rt_render_to_host", "rt_format_ppm",
     "rt_ppm_format", "rt_ppm_read", "rt_render_to_ppm",
-    "rt_ffma_peak", "rt_malloc", "rt_free", "rt_memcpy_to_host", "rt_synchronize",
+    "rt_ffma_peak", "rt_malloc", "rt_free", "rt_memcpy_to_host", "rt_synchronize", "rt_kernel_name",
 ]
 
 
@@ -62,10 +62,12 @@ class RenderArgs(C.Structure):
 
 class RenderStats(C.Structure):
     _fields_ = [("rays", C.c_uint64), ("paths", C.c_uint64), ("sphere_tests", C.c_uint64), ("node_tests", C.c_uint64),
-                ("kernel_ms", C.c_float), ("launches", C.c_int32)]
+                ("kernel_ms", C.c_float), ("launches", C.c_int32), ("kernel_id", C.c_int32), ("reserved", C.c_int32)]
 
     def as_dict(self):
-        return {k: getattr(self, k) for k, _ in self._fields_}
+        d = {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
+        d["kernel"] = load_library().rt_kernel_name(self.kernel_id).decode()
+        return d
 
 
 class CameraDesc(C.Structure):
@@ -97,6 +99,7 @@ def load_library(path: str | None = None) -> C.CDLL:
         "rt_destroy": (None, [vp]),
         "rt_last_error": (C.c_char_p, [vp]),
         "rt_set_stream": (i32, [vp, vp]),
+        "rt_kernel_name": (C.c_char_p, [i32]),
         "rt_device_info": (i32, [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(sz)]),
         "rt_scene_generate": (i32, [vp, i32, f32]),
         "rt_scene_generate_ex": (i32, [vp, i32, f32, i32]),
@@ -195,7 +198,13 @@ class RayTracer:
             pass
 
     def set_stream(self, cuda_stream_handle: int | None):
-        self._ck(self.L.rt_set_stream(self._ctx, C.c_void_p(cuda_stream_handle or 0)), "rt_set_stream")
+        """Launch on the given cudaStream_t.  None = the context's own (blocking) stream; 0 — what
+        torch.cuda.current_stream().cuda_stream returns for the default stream — selects the LEGACY DEFAULT stream
+        (cudaStreamLegacy), so that the library's kernels are ordered with torch's and NCCL's work on it."""
+        CUDA_STREAM_LEGACY = 1
+        h = 0 if cuda_stream_handle is None else (cuda_stream_handle or CUDA_STREAM_LEGACY)
+        self._ck(self.L.rt_set_stream(self._ctx, C.c_void_p(h)), "rt_set_stream")
+
 
     def device_info(self):
         sm, clk, mem = C.c_int(), C.c_int(), C.c_size_t()

@@ -41,6 +41,7 @@ struct rt_context {
     bool list_accel_valid = false;
     float grid_density = 4.0f;
     int default_variant = 0;       // RT_RENDER_VARIANT: kernel A/B override for whole test runs (0 = automatic)
+    int last_kernel = 0;           // KernelId of the last render launch
     // render scratch
     uint32_t *work_counter = nullptr;
     unsigned long long *counters = nullptr;
@@ -100,7 +101,7 @@ extern "C" int rt_create(int device, rt_context **out) {
     rt_context *ctx = new rt_context();
     ctx->device = device;
     if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaGetDeviceProperties(&ctx->prop, device)) != cudaSuccess ||
-        (e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamDefault)) != cudaSuccess ||
         (e = cudaEventCreate(&ctx->ev0)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev1)) != cudaSuccess ||
         (e = cudaMalloc(&ctx->work_counter, 4)) != cudaSuccess || (e = cudaMalloc(&ctx->counters, 32 * 8)) != cudaSuccess ||
         (e = cudaMalloc(&ctx->cam_dev, sizeof(CameraData))) != cudaSuccess) {
@@ -144,6 +145,17 @@ extern "C" int rt_set_stream(rt_context *ctx, void *s) {
     if (!ctx) return RT_ERR_INVALID;
     ctx->stream = s ? (cudaStream_t)s : ctx->own_stream;
     return RT_OK;
+}
+
+extern "C" const char *rt_kernel_name(int kernel_id) {
+    switch (kernel_id) {
+        case kKernelLane: return "k_render<octree> (pixel per lane, grid walk)";
+        case kKernelListSweep: return "k_render<list> (N-test sweep)";
+        case kKernelPool: return "k_render_pool<64,6>";
+        case kKernelCoop: return "k_render_coop (warp-cooperative candidate tests)";
+        case kKernelHalf: return "k_render_h (USE_FP16)";
+        default: return "none";
+    }
 }
 
 extern "C" int rt_device_info(const rt_context *ctx, int *sm_count, int *clock_khz, size_t *mem_bytes) {
@@ -329,7 +341,6 @@ extern "C" int rt_camera_set(rt_context *ctx, const rt_camera_desc *desc, int nx
     ctx->cam_h_nx = ctx->cam_h_ny = 0;          // the half camera is derived on demand
     k_camera_setup<<<1, 1, 0, ctx->stream>>>(c, ctx->cam_dev);
     CK(cudaGetLastError());
-    CK(upload_camera_from_device(ctx->cam_dev, ctx->stream));
     CK(cudaMemcpyAsync(&ctx->cam_host, ctx->cam_dev, sizeof(CameraData), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->have_camera = true;
@@ -432,7 +443,10 @@ static int do_render(rt_context *ctx, const rt_render_args *a, float *out_dev, b
         return fail(ctx, RT_ERR_STATE, "render: the octree was built for the other precision (rt_octree_build_ex)");
     CK(cudaSetDevice(ctx->device));
     if (!ctx->have_camera || ctx->cam_nx != a->nx || ctx->cam_ny != a->ny) {
-        const int rc = rt_camera_set(ctx, nullptr, a->nx, a->ny);
+        // only the default main.cu camera follows the frame size (its aspect ratio is nx/ny, main.cu:198); a description
+        // given through rt_camera_set(desc) / rt_apply_camera is kept as it is, aspect included
+        const rt_camera_desc keep = ctx->cam_desc;
+        const int rc = rt_camera_set(ctx, ctx->have_camera && ctx->cam_desc_custom ? &keep : nullptr, a->nx, a->ny);
         if (rc) return rc;
     }
     const int count = a->shard_mode == RT_SHARD_NONE ? 1 : (a->shard_count < 1 ? 1 : a->shard_count);
@@ -456,6 +470,7 @@ static int do_render(rt_context *ctx, const rt_render_args *a, float *out_dev, b
         p.tree = ctx->list_accel->view();
         list_grid = true;
     }
+    p.cam = ctx->cam_host;                        // per-context camera, by value in the launch parameters
     p.nx = a->nx; p.ny = a->ny;
     p.ns_total = a->ns;
     p.ns_local = a->ns;
@@ -540,10 +555,16 @@ static int do_render(rt_context *ctx, const rt_render_args *a, float *out_dev, b
         }
         CK(launch_render_half(p, a->use_octree != 0, ctx->geom_h, ctx->matl_h, ctx->cam_h, ctx->half_pairs, ctx->prop.multiProcessorCount,
                               ctx->stream, &blocks));
+        ctx->last_kernel = kKernelHalf;
     } else {
-        CK(launch_render(p, a->use_octree != 0 || list_grid, ctx->prop.multiProcessorCount, ctx->prop.sharedMemPerBlockOptin, ctx->stream, &blocks));
+        CK(launch_render(p, a->use_octree != 0 || list_grid, ctx->prop.multiProcessorCount, ctx->prop.sharedMemPerBlockOptin, ctx->stream, &blocks,
+                         &ctx->last_kernel));
     }
     CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    rt_render_stats local_stats;
+    // the pooled kernel's watchdog (a scheduling bug must never hang the GPU) truncates the frame when it trips: such a frame
+    // must fail the call whether or not the caller asked for statistics, so pooled launches always read the counters back
+    if (!stats && ctx->last_kernel == kKernelPool) stats = &local_stats;
     if (stats) {
         unsigned long long c[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         CK(cudaMemcpyAsync(c, ctx->counters, sizeof c, cudaMemcpyDeviceToHost, ctx->stream));
@@ -552,6 +573,7 @@ static int do_render(rt_context *ctx, const rt_render_args *a, float *out_dev, b
         memset(stats, 0, sizeof *stats);
         stats->rays = c[0]; stats->paths = c[1];
         stats->sphere_tests = c[2]; stats->node_tests = c[3];   // zero unless built with -DRT_COUNTERS
+        stats->kernel_id = ctx->last_kernel;
         if (c[7]) {
             return fail(ctx, RT_ERR_STATE, "render: scheduler watchdog tripped in %llu warps (w0|w1 %016llx, w2|rounds %016llx)",
                         c[7], c[5], c[6]);
@@ -598,6 +620,7 @@ extern "C" int rt_trace_rays(rt_context *ctx, int use_octree, int n, const float
     memset(&p, 0, sizeof p);
     p.scene.geom = ctx->geom; p.scene.matl = ctx->matl; p.scene.tag = ctx->tag; p.scene.n = ctx->n;
     if (use_octree) p.tree = ctx->octree->view();
+    p.variant = ctx->default_variant;
     CK(launch_trace_rays(p, use_octree != 0, d_o, d_d, n, d_i, d_t, ctx->stream));
     CK(cudaMemcpyAsync(out_idx, d_i, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaMemcpyAsync(out_t, d_t, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));

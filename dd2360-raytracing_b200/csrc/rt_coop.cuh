@@ -1,0 +1,373 @@
+// rt_coop.cuh — warp-cooperative closest hit ("flattened candidates") and the render kernel built on it.
+// Included by rt_render.cu inside namespace rt.
+//
+// Why: in the pixel-per-lane walk (k_render) every lane tests the candidates of ITS OWN ray, so a warp runs as long as the
+// lane with the longest candidate lists: profiles/warp_model.py (the product's traversal code replayed on the host in
+// lock-step) shows, for BASELINE config 3, 28 % of the rays missing the grid altogether, 1.5 voxels visited per ray with
+// ~13 references each, 0..75 candidates per ray — and 44 % of the lane-trips of the walk loop doing work.  The exact
+// root evaluation (IEEE sqrt + two divisions) sat in that loop under a branch taken by 3.6 lanes.
+//
+// Here the lanes still own one pixel chain each (ray, RNG and pixel state in registers, shading as in k_render), but the
+// candidate tests of the warp's 32 rays are pooled:
+//   round   : every walking lane publishes the reference range of its CURRENT voxel; an inclusive warp scan lays the
+//             ranges end to end (a flat list of `total` (ray, reference) items);
+//   chunks  : 32 items at a time, item -> owner lane by a REDUX.OR of the segment starts + one CLZ; the lane reads the
+//             owner's ray from shared memory, one float4 of list-order geometry from L1/L2 and runs the conservative root
+//             pre-filter (maybe_hit) against the owner's current closest hit.  Trip count is warp-uniform: total / 32;
+//   ring    : candidates that pass (1.3 per ray at config 3) are appended to a per-warp ring in shared memory by
+//             ballot/popc (no atomics: the warp is converged); whenever 32 are queued — and at the end of a round — the
+//             lanes evaluate the EXACT reference test (sphere.h:17-46, IEEE) on one entry each and fold the result into the
+//             owner's (t, sphere index) key with a 64-bit shared-memory atomicMin;
+//   advance : owners re-read their closest hit and step the 3D-DDA to their next non-empty voxel (or stop).
+// The closest hit of hitable_list::hit / hitTree is a strict-'<' minimum over a candidate set, so it does not depend on the
+// order of evaluation; a candidate's accepted root does not depend on closest_so_far either:
+//   sphere::hit(t_max) accepts root1 if t_min < root1 < t_max, else root2 if t_min < root2 < t_max; root2 >= root1 (the
+//   rounding of (-b -+ sq)/a is monotone, a > 0), hence  hit(t_max) = [acc < t_max] with acc = root1 if root1 > t_min,
+//   else root2 if root2 > t_min — exactly what sphere_test(.., t_max = FLT_MAX, ..) returns.
+// Ties (two DIFFERENT spheres with bit-identical t) go to the smaller sphere index, independent of scheduling.
+#pragma once
+
+namespace coop {
+
+constexpr unsigned kFull = 0xffffffffu;
+constexpr uint32_t kPrologFlag = 0x80000000u;    // ring reference: index into the prolog list instead of the voxel lists
+constexpr int kRing = 64;                        // >= 31 (left over) + 32 (one chunk's pushes)
+
+struct __align__(16) WarpShared {
+    float4 ro[32];                   // ray origin, a = dot(d, d)
+    float4 rd[32];                   // ray direction, 1/a (approximate: pre-filter only)
+    unsigned long long best[32];     // closest hit so far: float bits of t << 32 | sphere index (0xffffffff: none)
+    float bound[32];                 // t of best[] (what the pre-filter and the walk prune against)
+    int koff[32];                    // first reference of the lane's current voxel - its offset in the flat item list
+    uint32_t slot[32];               // chunk position of a segment start -> owner lane
+    uint2 ring[kRing];               // {owner lane, reference}
+};
+
+__device__ __forceinline__ unsigned long long pack_hit(const float t, const uint32_t idx) {
+    return (unsigned long long)__float_as_uint(t) << 32 | idx;
+}
+
+// Exact test of up to 32 queued candidates, one per lane, folded into the owners' keys.  Entries [first, first + n).
+__device__ __forceinline__ void drain(WarpShared &ws, const SceneView &sc, const TreeView &tv, const unsigned lane, const int first, const int n) {
+    if ((int)lane < n) {
+        const uint2 e = ws.ring[first + (int)lane];
+        const float4 ro = ws.ro[e.x], rd = ws.rd[e.x];
+        const bool pro = (e.y & kPrologFlag) != 0u;
+        const uint32_t k = e.y & ~kPrologFlag;
+        const float4 s = pro ? __ldg(tv.prolog_geom + k) : __ldg(tv.grid.ref_geom + k);
+        float t;
+        if (sphere_test(s, mk(ro.x, ro.y, ro.z), mk(rd.x, rd.y, rd.z), ro.w, kTMax, t)) {
+            const uint32_t idx = pro ? __ldg(tv.prolog + k) : __ldg(tv.grid.refs + k);
+            atomicMin(&ws.best[e.x], pack_hit(t, idx));
+        }
+    }
+    __syncwarp();
+}
+
+// Append the lanes with `pass` to the ring; drains 32 entries when that many are queued.  Warp-uniform `count`.
+__device__ __forceinline__ void push(WarpShared &ws, const SceneView &sc, const TreeView &tv, const unsigned lane, const bool pass,
+                                     const uint32_t owner, const uint32_t ref, int &count) {
+    const unsigned m = __ballot_sync(kFull, pass);
+    if (!m) return;
+    if (pass) ws.ring[count + __popc(m & ((1u << lane) - 1u))] = make_uint2(owner, ref);
+    count += __popc(m);
+    __syncwarp();
+    if (count >= 32) {
+        drain(ws, sc, tv, lane, count - 32, 32);      // the newest 32; what is left stays at the front
+        count -= 32;
+        ws.bound[lane] = __uint_as_float((uint32_t)(ws.best[lane] >> 32));
+        __syncwarp();
+    }
+}
+
+// Closest hit for the rays of the whole warp (lane `has` a ray or idles along).  Every lane of the warp must call.
+// Returns the minimum over ALL candidates (the visibility rule is applied by the caller, as in trace_tree).
+__device__ __forceinline__ Hit coop_trace(WarpShared &ws, const SceneView &sc, const TreeView &tv, const unsigned lane, const bool has,
+                                          const vec3f o, const vec3f d, TraceCounters &tc) {
+    const float a = dot3(d, d);
+    const float ia = rcp_trav(a);
+    __syncwarp();
+    ws.ro[lane] = make_float4(o.x, o.y, o.z, a);
+    ws.rd[lane] = make_float4(d.x, d.y, d.z, ia);
+    float best_t = kTMax;
+    {   // ground sphere first, unconditionally (acceleration_structure.h:322-332)
+        uint32_t idx = 0xffffffffu;
+        float t;
+        if (has) {
+            RT_COUNT(sphere_tests);
+            if (sphere_test(__ldg(sc.geom), o, d, a, kTMax, t)) { best_t = t; idx = 0u; }
+        }
+        ws.best[lane] = pack_hit(best_t, idx);
+        ws.bound[lane] = best_t;
+    }
+    __syncwarp();
+    int count = 0;
+    for (int k = 1; k < tv.nprolog; k++) {   // big spheres: one pre-filter per lane, exact tests through the ring
+        const float4 s = __ldg(tv.prolog_geom + k);
+        if (has) RT_COUNT(sphere_tests);
+        push(ws, sc, tv, lane, has && maybe_hit(s, o, d, a, ia, ws.bound[lane]), lane, kPrologFlag | (uint32_t)k, count);
+    }
+    if (count) {
+        drain(ws, sc, tv, lane, 0, count);
+        count = 0;
+    }
+    best_t = __uint_as_float((uint32_t)(ws.best[lane] >> 32));
+    ws.bound[lane] = best_t;
+
+    // ---- 3D-DDA set-up, per lane (as trace_walk) ----
+    const GridView &g = tv.grid;
+    bool walking = has && g.nx != 0;
+    int ix = 0, iy = 0, iz = 0;
+    float tmx = kTMax, tmy = kTMax, tmz = kTMax, dtx = 0.f, dty = 0.f, dtz = 0.f, t_exit = 0.f;
+    const int sx = d.x >= 0.0f ? 1 : -1, sy = d.y >= 0.0f ? 1 : -1, sz = d.z >= 0.0f ? 1 : -1;
+    uint32_t k = 0, cnt = 0;
+    if (walking) {
+        RayPre r;
+        r.o = o; r.d = d; r.a = a;
+        r.inv = mk(rcp_trav(d.x), rcp_trav(d.y), rcp_trav(d.z));
+        float te;
+        walking = ray_box(r, g.org, g.hi, best_t * (1.0f + kTSlackRel) + kTSlackAbs, te, t_exit);
+        if (walking) {
+            ix = (int)floorf((o.x + d.x * te - g.org[0]) * g.inv_vs[0]);
+            iy = (int)floorf((o.y + d.y * te - g.org[1]) * g.inv_vs[1]);
+            iz = (int)floorf((o.z + d.z * te - g.org[2]) * g.inv_vs[2]);
+            ix = imin(imax(ix, 0), g.nx - 1);
+            iy = imin(imax(iy, 0), g.ny - 1);
+            iz = imin(imax(iz, 0), g.nz - 1);
+            if (fabsf(d.x) > 0.0f) tmx = (g.org[0] + (float)(ix + (sx > 0)) * g.vs[0] - o.x) * r.inv.x;
+            if (fabsf(d.y) > 0.0f) tmy = (g.org[1] + (float)(iy + (sy > 0)) * g.vs[1] - o.y) * r.inv.y;
+            if (fabsf(d.z) > 0.0f) tmz = (g.org[2] + (float)(iz + (sz > 0)) * g.vs[2] - o.z) * r.inv.z;
+            dtx = fabsf(g.vs[0] * r.inv.x); dty = fabsf(g.vs[1] * r.inv.y); dtz = fabsf(g.vs[2] * r.inv.z);
+            RT_COUNT(voxel_steps);
+            const uint2 v = __ldg(g.vox + ((size_t)(iz * g.ny + iy) * g.nx + ix));
+            k = v.x; cnt = v.y;
+        }
+    }
+    int budget = g.nx + g.ny + g.nz + 4;       // hard bound on voxel steps: the walk always terminates
+
+    while (true) {
+        // ---- advance the lanes whose voxel is empty (or used up) until every walking lane has candidates; each pass of
+        //      this loop is one DDA step for the lanes that need it ----
+        while (__any_sync(kFull, walking && cnt == 0u)) {
+            if (walking && cnt == 0u) {
+                float t_in;
+                if (tmx <= tmy && tmx <= tmz) { t_in = tmx; ix += sx; tmx += dtx; walking = (unsigned)ix < (unsigned)g.nx; }
+                else if (tmy <= tmz)          { t_in = tmy; iy += sy; tmy += dty; walking = (unsigned)iy < (unsigned)g.ny; }
+                else                          { t_in = tmz; iz += sz; tmz += dtz; walking = (unsigned)iz < (unsigned)g.nz; }
+                // a later voxel can only hold hits at t >= t_in (minus the float slack); also stop at the grid exit
+                if (t_in > best_t * (1.0f + kTSlackRel) + kTSlackAbs || t_in > t_exit * (1.0f + 1e-5f) + 1e-6f || --budget < 0) walking = false;
+                if (walking) {
+                    RT_COUNT(voxel_steps);
+                    const uint2 v = __ldg(g.vox + ((size_t)(iz * g.ny + iy) * g.nx + ix));
+                    k = v.x; cnt = v.y;
+                }
+            }
+        }
+        if (!__any_sync(kFull, walking)) break;
+
+        // ---- lay the lanes' reference ranges end to end ----
+        const uint32_t mine = walking ? cnt : 0u;
+        uint32_t incl = mine;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const uint32_t v = __shfl_up_sync(kFull, incl, off);
+            if ((int)lane >= off) incl += v;
+        }
+        const uint32_t total = __shfl_sync(kFull, incl, 31);
+        const uint32_t excl = incl - mine;
+        ws.koff[lane] = (int)k - (int)excl;
+        __syncwarp();
+
+        for (uint32_t base = 0; base < total; base += 32u) {
+            // segment starts inside this chunk: a lane owns items [max(excl, base), min(incl, base + 32))
+            const uint32_t s_pos = excl > base ? excl : base;
+            const uint32_t e_pos = incl < base + 32u ? incl : base + 32u;
+            const bool owns = s_pos < e_pos;
+            if (owns) ws.slot[s_pos - base] = lane;
+            const unsigned starts = __reduce_or_sync(kFull, owns ? 1u << (s_pos - base) : 0u);
+            __syncwarp();
+            const uint32_t item = base + lane;
+            const bool valid = item < total;
+            const uint32_t owner = ws.slot[31 - __clz(starts & (0xffffffffu >> (31u - lane)))];   // bit 0 is always a start
+            const float4 ro = ws.ro[owner], rd = ws.rd[owner];
+            const uint32_t ref = (uint32_t)(ws.koff[owner] + (int)item);
+            bool pass = false;
+            if (valid) {
+                RT_COUNT(sphere_tests);
+                pass = maybe_hit(__ldg(g.ref_geom + ref), mk(ro.x, ro.y, ro.z), mk(rd.x, rd.y, rd.z), ro.w, rd.w, ws.bound[owner]);
+            }
+            __syncwarp();                       // slot[] is rewritten by the next chunk
+            push(ws, sc, tv, lane, pass, owner, ref, count);
+        }
+        if (count) {
+            drain(ws, sc, tv, lane, 0, count);
+            count = 0;
+        }
+        best_t = __uint_as_float((uint32_t)(ws.best[lane] >> 32));
+        ws.bound[lane] = best_t;
+        cnt = 0u;                               // every published range was consumed: the advance loop steps on
+        __syncwarp();
+    }
+    const unsigned long long key = ws.best[lane];
+    Hit h;
+    h.t = __uint_as_float((uint32_t)(key >> 32));
+    h.idx = (int)(uint32_t)key;                 // 0xffffffff -> -1
+    return h;
+}
+
+// hitTree semantics on top of coop_trace: the visibility rule on the winner (as trace_tree), the rare failures re-walked per lane
+__device__ __forceinline__ Hit coop_trace_tree(WarpShared &ws, const SceneView &sc, const TreeView &tv, const float *planes, const unsigned lane,
+                                               const bool has, const vec3f o, const vec3f d, TraceCounters &tc) {
+    Hit h = coop_trace(ws, sc, tv, lane, has, o, d, tc);
+    if (has && h.idx > 0 && tv.check_visibility && !visible_fast(tv, planes, __ldg(sc.geom + h.idx), o, d, h.t)) {
+        int last_ok = -1;
+        if (!sphere_visible(tv.vis, planes, h.idx, o, d, last_ok, tc)) h = trace_walk<true>(sc, tv, planes, o, d, tc);
+    }
+    return h;
+}
+
+template <int MINB>
+__global__ void __launch_bounds__(kRenderThreads, MINB) k_render_coop(const __grid_constant__ RenderLaunch p) {
+    __shared__ WarpShared wsh[kRenderThreads / 32];
+    WarpShared &ws = wsh[threadIdx.x >> 5];
+    const SceneView sc = p.scene;
+    const unsigned lane = threadIdx.x & 31u;
+    const uint32_t gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+
+    int pix = -1, pi = 0, pj = 0;
+    int s = 0, depth = 0;
+    xorwow rng;
+    rng.d = rng.v0 = rng.v1 = rng.v2 = rng.v3 = rng.v4 = 0;
+    vec3f o = mk(0, 0, 0), d = mk(0, 0, 1), att = mk(1, 1, 1), col = mk(0, 0, 0);
+    uint32_t nrays = 0, npaths = 0;
+    TraceCounters tc;
+    tc.sphere_tests = tc.node_tests = tc.voxel_steps = 0;
+    bool exhausted = false;
+    uint32_t stock_next = gwarp * 32u, stock_end = stock_next + 32u;   // the first tile needs no atomic: the queue head starts past the grid
+    const uint32_t batch = claim_batch(p);
+    const float inv_ns = __fdiv_rn(1.0f, (float)p.ns_total);   // vec3.h:137-144: k = 1.0/t
+
+    while (true) {
+        while (true) {      // claim pixels for idle lanes (ballot/popc-compacted queue pop, whole tiles per warp)
+            const bool need = pix < 0 && !exhausted;
+            const unsigned m = __ballot_sync(kFull, need);
+            if (!m) break;
+            const uint32_t item = claim_items(p, m, lane, stock_next, stock_end, batch);
+            if (need) {
+                if (item >= p.total_items) {
+                    exhausted = true;
+                } else if (item_to_pixel(p, item, pi, pj)) {
+                    pix = pj * p.nx + pi;
+                    s = 0; depth = 0;
+                    col = mk(0, 0, 0);
+                    pixel_stream(p, pix, rng);
+                }
+            }
+        }
+        if (!__ballot_sync(kFull, pix >= 0)) break;
+
+        const bool has = pix >= 0;
+        if (has && depth == 0) {   // new sample: main.cu:104-106
+            const float u = div_(add_((float)pi, xorwow_uniform(rng)), (float)p.nx);
+            const float v = div_(add_((float)pj, xorwow_uniform(rng)), (float)p.ny);
+            camera_ray(p.cam, u, v, rng, o, d);
+            att = mk(1.0f, 1.0f, 1.0f);
+            npaths++;
+        }
+        if (has) nrays++;
+        __syncwarp();
+        const Hit h = coop_trace_tree(ws, sc, p.tree, &p.tree.planes[0][0], lane, has, o, d, tc);
+        if (has) {   // ---- one iteration of color()'s loop (main.cu:47-73) ----
+            bool sample_done = false;
+            vec3f contrib = mk(0, 0, 0);
+            if (h.idx >= 0) {
+                const float4 g = __ldg(sc.geom + h.idx);
+                const float4 m = __ldg(sc.matl + h.idx);
+                const int tag = __ldg(sc.tag + h.idx);
+                vec3f hp, hn, a, dn;
+                hit_point(g, o, d, h.t, hp, hn);
+                if (scatter(tag, m, d, hp, hn, a, dn, rng)) {
+                    att = mk(mul_(att.x, a.x), mul_(att.y, a.y), mul_(att.z, a.z));
+                    o = hp; d = dn;
+                    depth++;
+                    if (depth >= p.max_depth) sample_done = true;        // main.cu:74: return black
+                } else {
+                    sample_done = true;                                   // absorbed: main.cu:64
+                }
+            } else {
+                const vec3f c = sky(d);
+                contrib = mk(mul_(att.x, c.x), mul_(att.y, c.y), mul_(att.z, c.z));
+                sample_done = true;
+            }
+            if (sample_done) {
+                col = mk(add_(col.x, contrib.x), add_(col.y, contrib.y), add_(col.z, contrib.z));   // main.cu:107
+                depth = 0;
+                s++;
+                if (s >= p.ns_local) {
+                    float *out = p.out + (size_t)pix * 3;
+                    if (p.finalize) {   // main.cu:111-115
+                        out[0] = sqrt_(mul_(col.x, inv_ns));
+                        out[1] = sqrt_(mul_(col.y, inv_ns));
+                        out[2] = sqrt_(mul_(col.z, inv_ns));
+                    } else {
+                        out[0] = col.x; out[1] = col.y; out[2] = col.z;
+                    }
+                    pix = -1;
+                }
+            }
+        }
+        __syncwarp();
+    }
+
+    unsigned long long r64 = nrays, p64 = npaths;
+    for (int off = 16; off > 0; off >>= 1) {
+        r64 += __shfl_xor_sync(kFull, r64, off);
+        p64 += __shfl_xor_sync(kFull, p64, off);
+    }
+    if (lane == 0) {
+        atomicAdd(p.counters + 0, r64);
+        atomicAdd(p.counters + 1, p64);
+    }
+#ifdef RT_COUNTERS
+    unsigned long long c64[3] = {tc.sphere_tests, tc.node_tests, tc.voxel_steps};
+    for (int k = 0; k < 3; k++) {
+        for (int off = 16; off > 0; off >>= 1) c64[k] += __shfl_xor_sync(kFull, c64[k], off);
+        if (lane == 0) atomicAdd(p.counters + 2 + k, c64[k]);
+    }
+#endif
+}
+
+// test hook: closest hit of caller-supplied rays through the cooperative trace (32 rays per warp)
+__global__ void __launch_bounds__(kRenderThreads) k_trace_rays_coop(const __grid_constant__ RenderLaunch p, const float *__restrict__ org,
+                                                                   const float *__restrict__ dir, int n, int *__restrict__ out_idx,
+                                                                   float *__restrict__ out_t) {
+    __shared__ WarpShared wsh[kRenderThreads / 32];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool has = i < n;
+    const vec3f o = has ? mk(org[3 * i], org[3 * i + 1], org[3 * i + 2]) : mk(0, 0, 0);
+    const vec3f d = has ? mk(dir[3 * i], dir[3 * i + 1], dir[3 * i + 2]) : mk(0, 0, 1);
+    TraceCounters tc;
+    tc.sphere_tests = tc.node_tests = tc.voxel_steps = 0;
+    const Hit h = coop_trace_tree(wsh[threadIdx.x >> 5], p.scene, p.tree, &p.tree.planes[0][0], threadIdx.x & 31u, has, o, d, tc);
+    if (has) { out_idx[i] = h.idx; out_t[i] = h.t; }
+}
+
+template <int MINB>
+static cudaError_t launch_coop(const RenderLaunch &p, int sm_count, cudaStream_t st, int *blocks_out) {
+    auto kern = k_render_coop<MINB>;
+    int per_sm = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kRenderThreads, 0);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+    long long blocks = (long long)per_sm * sm_count;       // persistent grid: exactly what is resident
+    const long long need = ((long long)p.total_items + kRenderThreads - 1) / kRenderThreads;
+    if (blocks > need) blocks = need < 1 ? 1 : need;
+    const uint32_t head = (uint32_t)(blocks * kRenderThreads);
+    e = cudaMemcpyAsync(p.work_counter, &head, 4, cudaMemcpyHostToDevice, st);   // queue head starts past the grid
+    if (e != cudaSuccess) return e;
+    kern<<<(unsigned)blocks, kRenderThreads, 0, st>>>(p);
+    if (blocks_out) *blocks_out = (int)blocks;
+    return cudaGetLastError();
+}
+
+}  // namespace coop

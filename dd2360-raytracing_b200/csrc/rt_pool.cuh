@@ -287,7 +287,7 @@ __device__ __forceinline__ void gen_sample(const Ctx<NC> c, const RenderLaunch &
     const float u = div_(add_((float)pi, xorwow_uniform(rng)), (float)p.nx);
     const float v = div_(add_((float)pj, xorwow_uniform(rng)), (float)p.ny);
     vec3f o, d;
-    camera_ray(c_camera, u, v, rng, o, d);
+    camera_ray(p.cam, u, v, rng, o, d);
     c.sv3(F_OX, o);
     c.sv3(F_DX, d);
     c.sv3(F_AX, mk(1.0f, 1.0f, 1.0f));

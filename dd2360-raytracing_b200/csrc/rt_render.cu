@@ -25,14 +25,8 @@
 
 namespace rt {
 
-__constant__ CameraData c_camera;
-
-cudaError_t upload_camera(const CameraData &cam, cudaStream_t st) {
-    return cudaMemcpyToSymbolAsync(c_camera, &cam, sizeof cam, 0, cudaMemcpyHostToDevice, st);
-}
-cudaError_t upload_camera_from_device(const CameraData *cam_dev, cudaStream_t st) {
-    return cudaMemcpyToSymbolAsync(c_camera, cam_dev, sizeof(CameraData), 0, cudaMemcpyDeviceToDevice, st);
-}
+// The camera is per-CONTEXT state: it travels in the launch parameters (RenderLaunch::cam, constant bank), not in a
+// per-library __constant__ symbol that two contexts on one GPU would overwrite for each other.
 
 // ---- TMA 1-D bulk copy global -> shared, completion on an mbarrier -------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -205,7 +199,7 @@ __global__ void __launch_bounds__(kRenderThreads, 6) k_render(const __grid_const
             if (depth == 0) {   // new sample: main.cu:104-106
                 const float u = div_(add_((float)pi, xorwow_uniform(rng)), (float)p.nx);
                 const float v = div_(add_((float)pj, xorwow_uniform(rng)), (float)p.ny);
-                camera_ray(c_camera, u, v, rng, o, d);
+                camera_ray(p.cam, u, v, rng, o, d);
                 att = mk(1.0f, 1.0f, 1.0f);
                 npaths++;
             }
@@ -278,6 +272,7 @@ __global__ void __launch_bounds__(kRenderThreads, 6) k_render(const __grid_const
 }  // namespace rt
 namespace rt {
 #include "rt_pool.cuh"
+#include "rt_coop.cuh"
 }  // namespace rt
 namespace rt {
 
@@ -354,7 +349,10 @@ __global__ void k_trace_rays(const __grid_constant__ RenderLaunch p, int octree,
 
 cudaError_t launch_trace_rays(const RenderLaunch &p, bool octree, const float *org, const float *dir, int n, int *out_idx,
                               float *out_t, cudaStream_t st) {
-    k_trace_rays<<<(n + 127) / 128, 128, 0, st>>>(p, octree ? 1 : 0, org, dir, n, out_idx, out_t);
+    if (octree && p.variant != 1)     // the render kernels' default trace: warp-cooperative (rt_coop.cuh); variant 1 = the per-lane walk
+        coop::k_trace_rays_coop<<<(n + kRenderThreads - 1) / kRenderThreads, kRenderThreads, 0, st>>>(p, org, dir, n, out_idx, out_t);
+    else
+        k_trace_rays<<<(n + 127) / 128, 128, 0, st>>>(p, octree ? 1 : 0, org, dir, n, out_idx, out_t);
     return cudaGetLastError();
 }
 
@@ -394,24 +392,42 @@ static cudaError_t launch_variant(const RenderLaunch &p, size_t smem, int sm_cou
 }
 
 cudaError_t launch_render(const RenderLaunch &p, bool octree, int sm_count, size_t smem_limit, cudaStream_t st,
-                          int *blocks_out) {
+                          int *blocks_out, int *kernel_out) {
+    int dummy;
+    int &which = kernel_out ? *kernel_out : dummy;
     if (octree) {
-        switch (p.variant) {          // A/B measurement variants; all produce the same image
+        // the pooled kernel packs depth into 8 bits and the sample number into 24 (rt_pool.cuh F_SD): outside that range the
+        // other kernels render the frame
+        const bool pool_ok = p.max_depth <= 255 && p.ns_local < (1 << 24);
+        which = kKernelPool;
+        switch (pool_ok ? p.variant : -1) {          // A/B measurement variants; all produce the same image
             case 10: return pool::launch_pool<96, 4>(p, sm_count, st, blocks_out);
             case 11: return pool::launch_pool<64, 6>(p, sm_count, st, blocks_out);
             case 12: return pool::launch_pool<128, 3>(p, sm_count, st, blocks_out);
             case 13: return pool::launch_pool<32, 8>(p, sm_count, st, blocks_out);
             case 14: return pool::launch_pool<64, 4>(p, sm_count, st, blocks_out);
             case 15: return pool::launch_pool<64, 5>(p, sm_count, st, blocks_out);
-            case 1: return launch_variant<true, false>(p, 0, sm_count, st, blocks_out);
-            default:
-                // measured on B200 (profiles/README.md, profiles/sweep_pool_threshold.py at 4K): pooled / pixel-per-lane speed
-                // 0.87x at 100 k spheres, 1.07x at 300 k, ~1.5x at 1 M — the pooled kernel pays off once candidate lists are
-                // long (at 1200x800 the crossover sits in the same place: k_render ahead at 100 k, the pool at 300 k)
-                if (p.scene.n >= kPoolMinSpheres) return pool::launch_pool<64, 6>(p, sm_count, st, blocks_out);
-                return launch_variant<true, false>(p, 0, sm_count, st, blocks_out);
+            default: break;
         }
+        which = kKernelCoop;
+        switch (p.variant) {
+            case 40: return coop::launch_coop<6>(p, sm_count, st, blocks_out);
+            case 41: return coop::launch_coop<5>(p, sm_count, st, blocks_out);
+            case 42: return coop::launch_coop<4>(p, sm_count, st, blocks_out);
+            case 43: return coop::launch_coop<8>(p, sm_count, st, blocks_out);
+            default: break;
+        }
+        // measured on B200 (profiles/README.md, profiles/sweep_pool_threshold.py at 4K): pooled / pixel-per-lane speed
+        // 0.87x at 100 k spheres, 1.07x at 300 k, ~1.5x at 1 M — the pooled kernel pays off once candidate lists are
+        // long (at 1200x800 the crossover sits in the same place: k_render ahead at 100 k, the pool at 300 k)
+        if (p.variant != 1 && pool_ok && p.scene.n >= kPoolMinSpheres) {
+            which = kKernelPool;
+            return pool::launch_pool<64, 6>(p, sm_count, st, blocks_out);
+        }
+        which = kKernelLane;
+        return launch_variant<true, false>(p, 0, sm_count, st, blocks_out);
     }
+    which = kKernelListSweep;
     const size_t geom_bytes = (size_t)p.scene.n * sizeof(float4);
     if (geom_bytes + 1024 <= smem_limit) return launch_variant<false, true>(p, geom_bytes, sm_count, st, blocks_out);
     return launch_variant<false, false>(p, 0, sm_count, st, blocks_out);

@@ -15,6 +15,7 @@ constexpr int kPoolMinSpheres = 200000;  // octree mode: scenes at least this la
 struct RenderLaunch {
     SceneView scene;
     TreeView tree;
+    CameraData cam;          // camera.h:51-58 as computed by k_camera_setup for THIS context and frame size
     int nx, ny;
     int ns_total;            // samples per pixel of the whole frame (divisor of the final average)
     int ns_local;            // samples this launch traces per pixel
@@ -34,10 +35,10 @@ struct RenderLaunch {
     unsigned long long *counters;   // [0] rays, [1] paths
 };
 
-cudaError_t upload_camera(const CameraData &cam, cudaStream_t st);
-cudaError_t upload_camera_from_device(const CameraData *cam_dev, cudaStream_t st);
+// which kernel a launch used (reported in rt_render_stats::kernel_id; names: rt_kernel_name)
+enum KernelId { kKernelNone = 0, kKernelLane = 1, kKernelListSweep = 2, kKernelPool = 3, kKernelCoop = 4, kKernelHalf = 5 };
 cudaError_t launch_render(const RenderLaunch &p, bool octree, int sm_count, size_t smem_limit, cudaStream_t st,
-                          int *blocks_out);
+                          int *blocks_out, int *kernel_out);
 cudaError_t launch_trace_rays(const RenderLaunch &p, bool octree, const float *org, const float *dir, int n, int *out_idx,
                               float *out_t, cudaStream_t st);
 // render_init with the upstream seeding curand_init(1984, pixel_index + subsequence_base, 0) (main.cu:90)

@@ -91,6 +91,8 @@ typedef struct rt_render_stats {
     uint64_t node_tests;     /* octree node tests executed (same) */
     float kernel_ms;         /* device time of the render kernel(s), CUDA events on the context's stream */
     int32_t launches;        /* kernels launched by this call */
+    int32_t kernel_id;       /* which render kernel ran (rt_kernel_name) */
+    int32_t reserved;
 } rt_render_stats;
 
 typedef struct rt_context rt_context;
@@ -100,7 +102,10 @@ int rt_abi_version(void);
 int rt_create(int device, rt_context **out);                 /* replaces nothing; cudaSetDevice + stream */
 void rt_destroy(rt_context *ctx);                            /* replaces free_world + cudaFree x7 (main.cu:459-474) */
 const char *rt_last_error(const rt_context *ctx);
-int rt_set_stream(rt_context *ctx, void *cuda_stream);       /* cudaStream_t; NULL = the context's own stream */
+/* cudaStream_t to launch on.  NULL = the context's own stream (a BLOCKING stream: ordered with the legacy default stream).
+ * To run on the legacy default stream itself pass cudaStreamLegacy ((void *)0x1), not NULL. */
+int rt_set_stream(rt_context *ctx, void *cuda_stream);
+const char *rt_kernel_name(int kernel_id);                   /* name of rt_render_stats::kernel_id */
 int rt_device_info(const rt_context *ctx, int *sm_count, int *clock_khz, size_t *mem_bytes);
 
 /* ---- scene: replaces rand_init + create_world (main.cu:388,399) ------------------------------------------ */

@@ -14,7 +14,9 @@
  *   acceleration_structure.h:15 SPHERES_PER_LEAF <- -DRTO_SPL.  Image size / spp are locals of main() and become
  *   command-line arguments here.  No kernel or device function is modified.
  *
- * usage: ref_cuda_<variant> nx ny ns [--fb f.bin] [--spheres s.bin] [--camera c.bin] [--octree o.bin] [--reps R]
+ * usage: ref_cuda_<variant> nx ny ns[,ns2,...] [--fb f.bin] [--spheres s.bin] [--camera c.bin] [--octree o.bin] [--reps R]
+ * A comma-separated ns list renders every sample count in ONE process (create_world alone takes ~2 minutes at 100 k
+ * spheres: one thread device-news every material), one JSON line per count; --fb dumps the frame of the LAST count.
  */
 #define main reference_main_unused
 #include "main.cu"
@@ -66,7 +68,14 @@ static void dump(const char *path, const void *p, size_t bytes) {
 
 int main(int argc, char **argv) {
     if (argc < 4) { fprintf(stderr, "usage: %s nx ny ns [--fb f] [--spheres f] [--camera f] [--octree f] [--reps R]\n", argv[0]); return 1; }
-    const int nx = atoi(argv[1]), ny = atoi(argv[2]), ns = atoi(argv[3]);
+    const int nx = atoi(argv[1]), ny = atoi(argv[2]);
+    int ns_list[16], ns_count = 0;
+    for (const char *q = argv[3]; *q && ns_count < 16;) {
+        ns_list[ns_count++] = atoi(q);
+        while (*q && *q != ',') q++;
+        if (*q == ',') q++;
+    }
+    if (ns_count < 1 || ns_list[0] < 1) { fprintf(stderr, "bad ns list\n"); return 1; }
     const char *fb_path = 0, *sph_path = 0, *cam_path = 0, *oct_path = 0;
     int reps = 1;
     for (int a = 4; a + 1 < argc; a += 2) {
@@ -120,6 +129,15 @@ int main(int argc, char **argv) {
 
     dim3 blocks((nx + tx - 1) / tx, (ny + ty - 1) / ty);
     dim3 threads(tx, ty);
+    int use_octree = 0, fp16 = 0;
+#ifdef USE_OCTREE
+    use_octree = 1;
+#endif
+#ifdef USE_FP16
+    fp16 = 1;
+#endif
+    for (int k = 0; k < ns_count; k++) {
+    const int ns = ns_list[k];
     float best_render = 1e30f, best_init = 1e30f, sum_render = 0;
     for (int r = 0; r < reps; r++) {
         cudaEventRecord(e0);
@@ -137,6 +155,13 @@ int main(int argc, char **argv) {
         if (ms_render < best_render) best_render = ms_render;
         if (ms_init < best_init) best_init = ms_init;
         sum_render += ms_render;
+    }
+    printf("{\"impl\": \"ref_cuda\", \"n\": %d, \"spl\": %d, \"use_octree\": %d, \"fp16\": %d, \"nx\": %d, \"ny\": %d, \"ns\": %d, "
+           "\"reps\": %d, \"create_world_ms\": %.3f, \"octree_build_host_ms\": %.3f, \"octree_bytes\": %zu, "
+           "\"render_init_ms\": %.4f, \"render_ms\": %.4f, \"render_ms_mean\": %.4f, \"node_count\": %d, \"leaf_count\": %d}\n",
+           NUM_SPHERES, SPHERES_PER_LEAF, use_octree, fp16, nx, ny, ns, reps, ms_world, ms_build, sizeof(Octree),
+           best_init, best_render, sum_render / reps, octree->nodeCount, octree->leafCount);
+    fflush(stdout);
     }
 
     if (fb_path) dump(fb_path, fb, num_pixels * sizeof(vec3));
@@ -161,19 +186,6 @@ int main(int argc, char **argv) {
         dump(sph_path, h_f, sizeof(flat_sphere) * NUM_SPHERES);
         free(h_f); cudaFree(d_f); cudaFree(d_vt);
     }
-
-    int use_octree = 0, fp16 = 0;
-#ifdef USE_OCTREE
-    use_octree = 1;
-#endif
-#ifdef USE_FP16
-    fp16 = 1;
-#endif
-    printf("{\"impl\": \"ref_cuda\", \"n\": %d, \"spl\": %d, \"use_octree\": %d, \"fp16\": %d, \"nx\": %d, \"ny\": %d, \"ns\": %d, "
-           "\"reps\": %d, \"create_world_ms\": %.3f, \"octree_build_host_ms\": %.3f, \"octree_bytes\": %zu, "
-           "\"render_init_ms\": %.4f, \"render_ms\": %.4f, \"render_ms_mean\": %.4f, \"node_count\": %d, \"leaf_count\": %d}\n",
-           NUM_SPHERES, SPHERES_PER_LEAF, use_octree, fp16, nx, ny, ns, reps, ms_world, ms_build, sizeof(Octree),
-           best_init, best_render, sum_render / reps, octree->nodeCount, octree->leafCount);
 
     free_world<<<1, 1>>>(d_list, d_world, d_camera);
     checkCudaErrors(cudaDeviceSynchronize());

@@ -1,0 +1,282 @@
+// warp_model.cpp — ANALYSIS TOOL (not product, not test): a host model of how a 32-lane warp of k_render spends its loop
+// trips, built on the product's own __host__ __device__ traversal code (via tests/hostsim).  It replays the pixel chains of
+// whole 8x4 tiles in lock-step exactly as k_render schedules them and records, per closest-hit query, the "script" of the
+// flat walk loop (advance / candidate-pair trips, filter positives, exact tests).  From the scripts it derives the lane
+// occupancy of the present loop and of alternative organisations, so that kernel designs can be compared before any GPU
+// minute is spent.  Driver: profiles/warp_model.py.
+#include "../tests/hostsim/hostsim.cpp"
+
+#include <stdio.h>
+
+namespace {
+
+struct RayScript {
+    // one entry per visited voxel: number of references in it
+    std::vector<uint16_t> vox_counts;
+    int positives = 0;       // candidates with disc > 0
+    int filter_pass = 0;     // candidates the pre-filter lets through (exact test needed)
+    int exact_accept = 0;    // exact tests that improved the closest hit
+    int nprolog = 0;
+    bool grid_missed = false;
+    // per loop trip of the present flat loop: bit0 = advance executed, bits1-2 = candidates tested (0..2), bits3-4 = exact tests run
+    std::vector<uint8_t> trips;
+};
+
+// trace_walk<false> (rt_trace.cuh) with recording; `two` = candidates per trip
+static Hit walk_record(const SceneView &sc, const TreeView &tv, const vec3f o, const vec3f d, RayScript &rs, const int per_trip) {
+    Hit h;
+    h.t = kTMax; h.idx = -1;
+    RayPre r;
+    r.o = o; r.d = d;
+    r.a = dot3(d, d);
+    const float ia = rcp_trav(r.a);
+    { float t; if (sphere_test(sc.geom[0], o, d, r.a, kTMax, t)) { h.t = t; h.idx = 0; } }
+    rs.nprolog = tv.nprolog;
+    for (int k = 1; k < tv.nprolog; k++) {
+        const int idx = (int)tv.prolog[k];
+        float t;
+        const float4 s = sc.geom[idx];
+        if (maybe_hit(s, o, d, r.a, ia, h.t) && sphere_test(s, o, d, r.a, h.t, t)) { h.t = t; h.idx = idx; }
+    }
+    const GridView &g = tv.grid;
+    if (g.nx == 0) return h;
+    r.inv = mk(rcp_trav(d.x), rcp_trav(d.y), rcp_trav(d.z));
+    float te, tx;
+    if (!ray_box(r, g.org, g.hi, h.t * (1.0f + kTSlackRel) + kTSlackAbs, te, tx)) { rs.grid_missed = true; return h; }
+    int ix = (int)floorf((o.x + d.x * te - g.org[0]) * g.inv_vs[0]);
+    int iy = (int)floorf((o.y + d.y * te - g.org[1]) * g.inv_vs[1]);
+    int iz = (int)floorf((o.z + d.z * te - g.org[2]) * g.inv_vs[2]);
+    ix = imin(imax(ix, 0), g.nx - 1);
+    iy = imin(imax(iy, 0), g.ny - 1);
+    iz = imin(imax(iz, 0), g.nz - 1);
+    const int sx = d.x >= 0.0f ? 1 : -1, sy = d.y >= 0.0f ? 1 : -1, sz = d.z >= 0.0f ? 1 : -1;
+    float tmx = fabsf(d.x) > 0.0f ? (g.org[0] + (float)(ix + (sx > 0)) * g.vs[0] - o.x) * r.inv.x : kTMax;
+    float tmy = fabsf(d.y) > 0.0f ? (g.org[1] + (float)(iy + (sy > 0)) * g.vs[1] - o.y) * r.inv.y : kTMax;
+    float tmz = fabsf(d.z) > 0.0f ? (g.org[2] + (float)(iz + (sz > 0)) * g.vs[2] - o.z) * r.inv.z : kTMax;
+    const float dtx = fabsf(g.vs[0] * r.inv.x), dty = fabsf(g.vs[1] * r.inv.y), dtz = fabsf(g.vs[2] * r.inv.z);
+    uint32_t k, e;
+    { const uint2 v = g.vox[((size_t)(iz * g.ny + iy) * g.nx + ix)]; k = v.x; e = v.x + v.y; rs.vox_counts.push_back((uint16_t)v.y); }
+    int budget = g.nx + g.ny + g.nz + 4;
+    bool walking = true;
+    while (walking) {
+        uint8_t trip = 0;
+        if (k >= e) {
+            trip |= 1;
+            float t_in;
+            if (tmx <= tmy && tmx <= tmz) { t_in = tmx; ix += sx; tmx += dtx; walking = (unsigned)ix < (unsigned)g.nx; }
+            else if (tmy <= tmz)          { t_in = tmy; iy += sy; tmy += dty; walking = (unsigned)iy < (unsigned)g.ny; }
+            else                          { t_in = tmz; iz += sz; tmz += dtz; walking = (unsigned)iz < (unsigned)g.nz; }
+            if (t_in > h.t * (1.0f + kTSlackRel) + kTSlackAbs || t_in > tx * (1.0f + 1e-5f) + 1e-6f || --budget < 0) walking = false;
+            if (walking) {
+                const uint2 v = g.vox[((size_t)(iz * g.ny + iy) * g.nx + ix)];
+                k = v.x; e = v.x + v.y;
+                rs.vox_counts.push_back((uint16_t)v.y);
+            }
+        }
+        if (walking && k < e) {
+            int ntest = 0, nexact = 0;
+            const float bound = h.t;
+            for (int q = 0; q < per_trip && k < e; q++, k++) {
+                const float4 s = sc.geom[g.refs[k]];
+                ntest++;
+                const vec3f oc = mk(sub_(o.x, s.x), sub_(o.y, s.y), sub_(o.z, s.z));
+                const float b = dot3(oc, d), c = fma_(-s.w, s.w, dot3(oc, oc)), disc = fma_(b, b, -mul_(r.a, c));
+                if (disc > 0.0f) rs.positives++;
+                if (maybe_hit(s, o, d, r.a, ia, bound)) {
+                    rs.filter_pass++;
+                    nexact++;
+                    float t;
+                    if (sphere_test(s, o, d, r.a, h.t, t)) { h.t = t; h.idx = (int)g.refs[k]; rs.exact_accept++; }
+                }
+            }
+            trip |= (uint8_t)(ntest << 1) | (uint8_t)(nexact << 3);
+        }
+        rs.trips.push_back(trip);
+    }
+    return h;
+}
+
+struct Lane {
+    int pix = -1, pi = 0, pj = 0, s = 0, depth = 0;
+    xorwow rng;
+    vec3f o, d;
+};
+
+struct Acc {
+    // per-ray totals
+    double rays = 0, paths = 0, vox_visits = 0, vox_nonempty = 0, cands = 0, positives = 0, filter_pass = 0, exact_accept = 0, grid_missed = 0;
+    double trips = 0;
+    // present loop, lock-step
+    double outer = 0, active_lane_outer = 0;         // outer iterations (one closest-hit query per active lane), lanes with a pixel
+    double loop_trips = 0;                           // warp loop trips (max over lanes)
+    double trips_with_adv = 0, lanes_adv = 0, trips_with_test = 0, lanes_test = 0, trips_with_exact = 0, lanes_exact = 0;
+    // design B: voxel rounds with flattened candidates
+    double b_rounds = 0, b_chunks = 0, b_lanes_round = 0;
+    // design B2: rounds advance to the next NON-EMPTY voxel (empties skipped inside the advance)
+    double b2_rounds = 0, b2_chunks = 0, b2_max_adv = 0;
+    // histograms
+    double hist_vox[65] = {0}, hist_cands[257] = {0}, hist_trips[129] = {0};
+    double shade_hit = 0, shade_sky = 0;
+    double mat[3] = {0, 0, 0};
+};
+
+}  // namespace
+
+extern "C" int wm_run(const hs_sphere *sph, int n, const float *camera22, const void *blob, int spl, float density, int nx, int ny, int ns,
+                      int max_depth, int tile_first, int tile_step, int warps, int tiles_per_warp, int per_trip, double *out, int out_len) {
+    std::vector<float4> geom((size_t)n), matl((size_t)n);
+    std::vector<int> tag((size_t)n);
+    for (int i = 0; i < n; i++) {
+        geom[(size_t)i] = make_float4(sph[i].cx, sph[i].cy, sph[i].cz, sph[i].radius);
+        matl[(size_t)i] = make_float4(sph[i].ax, sph[i].ay, sph[i].az, sph[i].param);
+        tag[(size_t)i] = sph[i].mat;
+    }
+    SceneView sc;
+    sc.geom = geom.data(); sc.matl = matl.data(); sc.tag = tag.data(); sc.n = n;
+    HostTree T;
+    TreeView tv;
+    build_host_tree(geom, tag, static_cast<const int32_t *>(blob), spl, density, T);
+    view_of(T, tv);
+    fprintf(stderr, "grid %d x %d x %d, voxels %zu refs %zu, voxel size %.4f %.4f %.4f, prolog %d\n", tv.grid.nx, tv.grid.ny, tv.grid.nz, T.vox.size(),
+            T.refs.size(), tv.grid.vs[0], tv.grid.vs[1], tv.grid.vs[2], tv.nprolog);
+    CameraData cam;
+    memcpy(&cam, camera22, sizeof cam);
+    const int tiles_x = (nx + 7) / 8, tiles_y = (ny + 3) / 4;
+    Acc A;
+#pragma omp parallel
+    {
+        Acc a;
+#pragma omp for schedule(dynamic, 1)
+        for (int w = 0; w < warps; w++) {
+            Lane L[32];
+            uint32_t stock_next = 0, stock_end = 0;
+            int tiles_taken = 0;
+            const int base_tile = tile_first + w * tile_step;
+            while (true) {
+                // claim
+                for (int l = 0; l < 32; l++) {
+                    while (L[l].pix < 0) {
+                        if (stock_next >= stock_end) {
+                            if (tiles_taken >= tiles_per_warp) break;
+                            stock_next = (uint32_t)(base_tile + tiles_taken) * 32u;
+                            stock_end = stock_next + 32u;
+                            tiles_taken++;
+                        }
+                        const uint32_t item = stock_next++;
+                        const uint32_t tile = item >> 5, in = item & 31u;
+                        if ((int)tile >= tiles_x * tiles_y) continue;
+                        const int ty = (int)tile / tiles_x, tx_ = (int)tile - ty * tiles_x;
+                        const int i = tx_ * 8 + (int)(in & 7u), j = ty * 4 + (int)(in >> 3);
+                        if (i >= nx || j >= ny) continue;
+                        L[l].pi = i; L[l].pj = j; L[l].pix = j * nx + i; L[l].s = 0; L[l].depth = 0;
+                        xorwow_seed(L[l].rng, (unsigned long long)(long long)(1984 + L[l].pix));
+                    }
+                }
+                int nact = 0;
+                for (int l = 0; l < 32; l++) nact += L[l].pix >= 0;
+                if (!nact) break;
+                a.outer++;
+                a.active_lane_outer += nact;
+                RayScript rs[32];
+                vec3f att_dummy = mk(1, 1, 1);
+                (void)att_dummy;
+                Hit hs[32];
+                for (int l = 0; l < 32; l++) {
+                    if (L[l].pix < 0) continue;
+                    Lane &q = L[l];
+                    if (q.depth == 0) {
+                        const float u = div_(add_((float)q.pi, xorwow_uniform(q.rng)), (float)nx);
+                        const float v = div_(add_((float)q.pj, xorwow_uniform(q.rng)), (float)ny);
+                        camera_ray(cam, u, v, q.rng, q.o, q.d);
+                        a.paths++;
+                    }
+                    a.rays++;
+                    TraceCounters tcn{};
+                    hs[l] = trace_tree(sc, tv, &tv.planes[0][0], q.o, q.d, tcn);
+                    const Hit h2 = walk_record(sc, tv, q.o, q.d, rs[l], per_trip);
+                    if (h2.idx != hs[l].idx || h2.t != hs[l].t) { /* checked re-walk case: rare; keep trace_tree's answer */ }
+                    const RayScript &r = rs[l];
+                    a.vox_visits += r.vox_counts.size();
+                    int c = 0;
+                    for (uint16_t vc : r.vox_counts) { a.vox_nonempty += vc > 0; c += vc; }
+                    a.cands += c; a.positives += r.positives; a.filter_pass += r.filter_pass; a.exact_accept += r.exact_accept;
+                    a.grid_missed += r.grid_missed;
+                    a.trips += r.trips.size();
+                    a.hist_vox[std::min<size_t>(r.vox_counts.size(), 64)]++;
+                    a.hist_cands[std::min(c, 256)]++;
+                    a.hist_trips[std::min<size_t>(r.trips.size(), 128)]++;
+                }
+                // ---- present loop in lock-step ----
+                size_t tmax = 0;
+                for (int l = 0; l < 32; l++) tmax = std::max(tmax, rs[l].trips.size());
+                a.loop_trips += tmax;
+                for (size_t t = 0; t < tmax; t++) {
+                    int nadv = 0, ntest = 0, nex = 0;
+                    for (int l = 0; l < 32; l++) {
+                        if (t >= rs[l].trips.size()) continue;
+                        const uint8_t b = rs[l].trips[t];
+                        nadv += b & 1; ntest += ((b >> 1) & 3) > 0; nex += ((b >> 3) & 3) > 0;
+                    }
+                    a.trips_with_adv += nadv > 0; a.lanes_adv += nadv;
+                    a.trips_with_test += ntest > 0; a.lanes_test += ntest;
+                    a.trips_with_exact += nex > 0; a.lanes_exact += nex;
+                }
+                // ---- design B: one voxel per lane per round, candidates flattened over the warp ----
+                size_t vmax = 0;
+                for (int l = 0; l < 32; l++) vmax = std::max(vmax, rs[l].vox_counts.size());
+                a.b_rounds += vmax;
+                for (size_t t = 0; t < vmax; t++) {
+                    int tot = 0, lanes = 0;
+                    for (int l = 0; l < 32; l++) if (t < rs[l].vox_counts.size()) { tot += rs[l].vox_counts[t]; lanes++; }
+                    a.b_chunks += (tot + 31) / 32;
+                    a.b_lanes_round += lanes;
+                }
+                // ---- design B2: a round = next non-empty voxel of every lane ----
+                {
+                    std::vector<std::vector<std::pair<int, int>>> ne(32);   // (count, empties skipped before it)
+                    size_t rmax = 0;
+                    for (int l = 0; l < 32; l++) {
+                        int skipped = 0;
+                        for (uint16_t vc : rs[l].vox_counts) { if (vc) { ne[l].push_back({vc, skipped}); skipped = 0; } else skipped++; }
+                        if (skipped) ne[l].push_back({0, skipped});          // trailing empties until the walk ends
+                        rmax = std::max(rmax, ne[l].size());
+                    }
+                    a.b2_rounds += rmax;
+                    for (size_t t = 0; t < rmax; t++) {
+                        int tot = 0, madv = 0;
+                        for (int l = 0; l < 32; l++) if (t < ne[l].size()) { tot += ne[l][t].first; madv = std::max(madv, ne[l][t].second + 1); }
+                        a.b2_chunks += (tot + 31) / 32;
+                        a.b2_max_adv += madv;
+                    }
+                }
+                // ---- shade, exactly as k_render ----
+                for (int l = 0; l < 32; l++) {
+                    if (L[l].pix < 0) continue;
+                    Lane &q = L[l];
+                    const Hit h = hs[l];
+                    bool sample_done = false;
+                    if (h.idx >= 0) {
+                        a.shade_hit++;
+                        a.mat[std::min(std::max(tag[(size_t)h.idx], 0), 2)]++;
+                        vec3f hp, hn, at, dn;
+                        hit_point(geom[(size_t)h.idx], q.o, q.d, h.t, hp, hn);
+                        if (scatter(tag[(size_t)h.idx], matl[(size_t)h.idx], q.d, hp, hn, at, dn, q.rng)) {
+                            q.o = hp; q.d = dn; q.depth++;
+                            if (q.depth >= max_depth) sample_done = true;
+                        } else sample_done = true;
+                    } else { a.shade_sky++; sample_done = true; }
+                    if (sample_done) { q.depth = 0; q.s++; if (q.s >= ns) q.pix = -1; }
+                }
+            }
+        }
+#pragma omp critical
+        {
+            double *dst = reinterpret_cast<double *>(&A), *src = reinterpret_cast<double *>(&a);
+            for (size_t i = 0; i < sizeof(Acc) / sizeof(double); i++) dst[i] += src[i];
+        }
+    }
+    const size_t nd = sizeof(Acc) / sizeof(double);
+    if ((size_t)out_len < nd) return -(int)nd;
+    memcpy(out, &A, sizeof A);
+    return (int)nd;
+}
