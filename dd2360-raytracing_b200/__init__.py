@@ -38,10 +38,12 @@ SPHERE_DTYPE = np.dtype(
 ABI_SYMBOLS = [
     "rt_abi_version", "rt_create", "rt_destroy", "rt_last_error", "rt_set_stream", "rt_device_info",
     "rt_scene_generate", "rt_scene_generate_ex", "rt_scene_upload", "rt_scene_download", "rt_scene_size", "rt_camera_set", "rt_camera_get", "rt_camera_get_half",
-    "rt_octree_build", "rt_octree_build_ex", "rt_octree_reference_bytes", "rt_octree_export_reference", "rt_octree_debug_read", "rt_xorwow_state", "rt_debug_counters", "rt_trace_rays",
-    "rt_render_accumulate", "rt_finalize", "rt_render", "rt_render_to_host", "rt_format_ppm",
+    "rt_octree_build", "rt_octree_build_ex", "rt_octree_reference_bytes", "rt_octree_export_reference", "rt_octree_debug_read", "rt_xorwow_state", "rt_debug_counters", "rt_trace_rays", "rt_camera_get_rays", "rt_scatter_rays",
+    "rt_render_accumulate", "rt_render_progressive", "rt_finalize", "rt_finalize_n", "rt_render", "rt_render_to_host", "rt_format_ppm",
     "rt_ppm_format", "rt_ppm_read", "rt_render_to_ppm",
     "rt_ffma_peak", "rt_malloc", "rt_free", "rt_memcpy_to_host", "rt_synchronize", "rt_kernel_name",
+    "rt_comm_get_unique_id", "rt_comm_init_rank", "rt_comm_init_all", "rt_comm_attach", "rt_comm_destroy", "rt_comm_rank", "rt_comm_size",
+    "rt_group_start", "rt_group_end", "rt_reduce", "rt_reduce_scatter", "rt_broadcast",
 ]
 
 
@@ -117,8 +119,12 @@ def load_library(path: str | None = None) -> C.CDLL:
         "rt_xorwow_state": (i32, [C.c_uint64, C.c_uint64, vp]),
         "rt_debug_counters": (i32, [vp, vp]),
         "rt_trace_rays": (i32, [vp, i32, i32, vp, vp, vp, vp]),
+        "rt_camera_get_rays": (i32, [vp, i32, vp, vp, vp, vp, vp]),
+        "rt_scatter_rays": (i32, [vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
         "rt_render_accumulate": (i32, [vp, C.POINTER(RenderArgs), vp, C.POINTER(RenderStats)]),
+        "rt_render_progressive": (i32, [vp, C.POINTER(RenderArgs), vp, vp, i32, C.POINTER(RenderStats)]),
         "rt_finalize": (i32, [vp, vp, vp, i32, i32, i32]),
+        "rt_finalize_n": (i32, [vp, vp, vp, sz, i32]),
         "rt_render": (i32, [vp, C.POINTER(RenderArgs), vp, C.POINTER(RenderStats)]),
         "rt_render_to_host": (i32, [vp, C.POINTER(RenderArgs), vp, C.POINTER(RenderStats)]),
         "rt_format_ppm": (sz, [vp, i32, i32, vp, sz]),
@@ -130,6 +136,18 @@ def load_library(path: str | None = None) -> C.CDLL:
         "rt_free": (i32, [vp, vp]),
         "rt_memcpy_to_host": (i32, [vp, vp, vp, sz]),
         "rt_synchronize": (i32, [vp]),
+        "rt_comm_get_unique_id": (i32, [vp]),
+        "rt_comm_init_rank": (i32, [vp, vp, i32, i32]),
+        "rt_comm_init_all": (i32, [C.POINTER(vp), i32]),
+        "rt_comm_attach": (i32, [vp, vp, i32, i32]),
+        "rt_comm_destroy": (i32, [vp]),
+        "rt_comm_rank": (i32, [vp]),
+        "rt_comm_size": (i32, [vp]),
+        "rt_group_start": (i32, []),
+        "rt_group_end": (i32, []),
+        "rt_reduce": (i32, [vp, vp, sz, i32]),
+        "rt_reduce_scatter": (i32, [vp, vp, vp, sz]),
+        "rt_broadcast": (i32, [vp, vp, sz, i32]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -285,6 +303,28 @@ class RayTracer:
                  "rt_trace_rays")
         return idx, t
 
+    def camera_rays(self, s: np.ndarray, t: np.ndarray, states: np.ndarray):
+        """camera::get_ray for n (s, t) pairs; `states` [n, 6] uint32 is advanced in place.  Returns (org[n,3], dir[n,3])."""
+        s = np.ascontiguousarray(s, dtype=np.float32); t = np.ascontiguousarray(t, dtype=np.float32)
+        assert states.dtype == np.uint32 and states.flags.c_contiguous and states.shape == (len(s), 6)
+        org = np.zeros((len(s), 3), np.float32); d = np.zeros((len(s), 3), np.float32)
+        self._ck(self.L.rt_camera_get_rays(self._ctx, len(s), s.ctypes.data, t.ctypes.data, states.ctypes.data, org.ctypes.data, d.ctypes.data),
+                 "rt_camera_get_rays")
+        return org, d
+
+    def scatter_rays(self, idx: np.ndarray, org: np.ndarray, dirs: np.ndarray, t_hit: np.ndarray, states: np.ndarray):
+        """material::scatter for n hits; returns dict(p, normal, dir, atten, scattered); `states` advanced in place."""
+        idx = np.ascontiguousarray(idx, dtype=np.int32); org = np.ascontiguousarray(org, dtype=np.float32)
+        dirs = np.ascontiguousarray(dirs, dtype=np.float32); t_hit = np.ascontiguousarray(t_hit, dtype=np.float32)
+        n = len(idx)
+        assert states.dtype == np.uint32 and states.flags.c_contiguous and states.shape == (n, 6)
+        out = {k: np.zeros((n, 3), np.float32) for k in ("p", "normal", "dir", "atten")}
+        out["scattered"] = np.zeros(n, np.int32)
+        self._ck(self.L.rt_scatter_rays(self._ctx, n, idx.ctypes.data, org.ctypes.data, dirs.ctypes.data, t_hit.ctypes.data, states.ctypes.data,
+                                        out["p"].ctypes.data, out["normal"].ctypes.data, out["dir"].ctypes.data, out["atten"].ctypes.data,
+                                        out["scattered"].ctypes.data), "rt_scatter_rays")
+        return out
+
     # -- render (main.cu:424-429) --
     @staticmethod
     def args(nx, ny, ns, use_octree, max_depth=50, shard_mode=SHARD_NONE, shard_rank=0, shard_count=1,
@@ -331,8 +371,18 @@ class RayTracer:
                                              C.byref(st) if want_stats else None), "rt_render_accumulate")
         return st.as_dict() if want_stats else None
 
+    def render_progressive(self, args: RenderArgs, accum_dev_ptr: int, state_dev_ptr: int, first: bool, want_stats=True):
+        """args.ns MORE samples per pixel, continuing every pixel's stream and sum (render_progressive, main.cu:119-142)."""
+        st = RenderStats()
+        self._ck(self.L.rt_render_progressive(self._ctx, C.byref(args), C.c_void_p(accum_dev_ptr), C.c_void_p(state_dev_ptr), int(first),
+                                              C.byref(st) if want_stats else None), "rt_render_progressive")
+        return st.as_dict() if want_stats else None
+
     def finalize(self, accum_dev_ptr: int, fb_dev_ptr: int, nx, ny, ns):
         self._ck(self.L.rt_finalize(self._ctx, C.c_void_p(accum_dev_ptr), C.c_void_p(fb_dev_ptr), nx, ny, ns), "rt_finalize")
+
+    def finalize_n(self, accum_dev_ptr: int, fb_dev_ptr: int, count: int, ns: int):
+        self._ck(self.L.rt_finalize_n(self._ctx, C.c_void_p(accum_dev_ptr), C.c_void_p(fb_dev_ptr), count, ns), "rt_finalize_n")
 
     def ffma_peak_tflops(self) -> float:
         """Measured dense FP32 FFMA rate (TFLOP/s) of this GPU: the FP32 roofline denominator."""

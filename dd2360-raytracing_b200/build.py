@@ -68,7 +68,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     cli_src = os.path.join(CSRC, "raytracing_main.cpp")
     if os.path.exists(cli_src) and (force or _stale(CLI, [cli_src, LIB])):
         subprocess.run(["g++", "-O2", "-std=c++17", "-I", os.path.join(HERE, "..", "include"), cli_src, "-o", CLI,
-                        f"-L{HERE}", "-lrt_b200", f"-Wl,-rpath,$ORIGIN"], check=True, env=env)
+                        f"-L{HERE}", "-lrt_b200", "-lpthread", f"-Wl,-rpath,$ORIGIN"], check=True, env=env)
     return LIB
 
 

@@ -2,7 +2,9 @@
 // There is no CPU fallback anywhere in this library: every compute entry point launches CUDA kernels.
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 #include <math.h>
+#include <nccl.h>          // types and prototypes only: the functions are resolved with dlopen (see NcclApi)
 #include <stdarg.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -64,7 +66,13 @@ struct rt_context {
     uint32_t *skip_tables = nullptr;
     uint32_t *seed_states = nullptr;
     size_t seed_states_words = 0;
+    // multi-GPU (rt_comm_*): this context's rank in an NCCL communicator
+    ncclComm_t comm = nullptr;
+    bool comm_owned = false;
+    int comm_rank = 0, comm_size = 1;
 };
+
+extern "C" int rt_comm_destroy(rt_context *ctx);
 
 static const std::vector<uint32_t> &host_skip_tables() {
     static const std::vector<uint32_t> t = make_skip_tables();      // derived once per process (a few ms)
@@ -135,6 +143,7 @@ extern "C" void rt_destroy(rt_context *ctx) {
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    rt_comm_destroy(ctx);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
@@ -429,7 +438,12 @@ extern "C" size_t rt_octree_debug_read(rt_context *ctx, int which, void *host, s
 }
 
 // ---- render -----------------------------------------------------------------------------------------------------
-static int do_render(rt_context *ctx, const rt_render_args *a, float *out_dev, bool finalize, rt_render_stats *stats) {
+struct ProgressiveIO {
+    uint32_t *state = nullptr;     // 6 words per pixel, device
+    bool first = true;
+};
+static int do_render(rt_context *ctx, const rt_render_args *a, float *out_dev, bool finalize, rt_render_stats *stats,
+                     const ProgressiveIO *prog = nullptr) {
     if (!ctx || !a || !out_dev) return fail(ctx, RT_ERR_INVALID, "render: null argument");
     if (a->nx < 1 || a->ny < 1 || a->ns < 1) return fail(ctx, RT_ERR_INVALID, "render: bad nx/ny/ns");
     if (ctx->n < 1) return fail(ctx, RT_ERR_STATE, "render: no scene (rt_scene_generate / rt_scene_upload first)");
@@ -437,6 +451,7 @@ static int do_render(rt_context *ctx, const rt_render_args *a, float *out_dev, b
     if (a->seed_mode != RT_SEED_HEAD && a->seed_mode != RT_SEED_UPSTREAM) return fail(ctx, RT_ERR_INVALID, "render: unknown seed_mode");
     if (a->precision != RT_PREC_FP32 && a->precision != RT_PREC_FP16) return fail(ctx, RT_ERR_INVALID, "render: unknown precision");
     const bool fp16 = a->precision == RT_PREC_FP16;
+    if (fp16 && prog) return fail(ctx, RT_ERR_UNSUPPORTED, "render: progressive rendering is FP32 only");
     if (fp16 && a->shard_mode != RT_SHARD_NONE)
         return fail(ctx, RT_ERR_UNSUPPORTED, "render: USE_FP16 frames are rendered whole (RT_SHARD_NONE): the half accumulator does not split");
     if (a->use_octree && ctx->octree->built && ctx->octree->fp16 != fp16)
@@ -481,17 +496,18 @@ static int do_render(rt_context *ctx, const rt_render_args *a, float *out_dev, b
     p.tile_first = 0; p.tile_stride = 1;
     long long owned = ntiles;
     const size_t fb_bytes = (size_t)a->nx * a->ny * 3 * sizeof(float);
+    const bool continuing = prog && !prog->first;
     if (a->shard_mode == RT_SHARD_TILES && count > 1) {
         p.tile_first = rank; p.tile_stride = count;
         owned = (ntiles - rank + count - 1) / count;
-        CK(cudaMemsetAsync(out_dev, 0, fb_bytes, ctx->stream));       // pixels of other shards stay 0 so shards add up
+        if (!continuing) CK(cudaMemsetAsync(out_dev, 0, fb_bytes, ctx->stream));       // pixels of other shards stay 0 so shards add up
     } else if (a->shard_mode == RT_SHARD_SPP && count > 1) {
         p.ns_local = a->ns / count + (rank < a->ns % count ? 1 : 0);
         // shard g draws from streams seeded 1984 + pixel_index + g*num_pixels: distinct seeds, the reference's own
         // convention for independent streams (main.cu:91-93); g = 0 is the reference stream
         p.seed_offset = (unsigned long long)rank * (unsigned long long)a->nx * (unsigned long long)a->ny;
         if (p.ns_local == 0) {
-            CK(cudaMemsetAsync(out_dev, 0, fb_bytes, ctx->stream));
+            if (!continuing) CK(cudaMemsetAsync(out_dev, 0, fb_bytes, ctx->stream));
             if (stats) memset(stats, 0, sizeof *stats);
             return RT_OK;
         }
@@ -512,7 +528,7 @@ static int do_render(rt_context *ctx, const rt_render_args *a, float *out_dev, b
     CK(cudaMemsetAsync(ctx->counters, 0, 32 * 8, ctx->stream));
     int blocks = 0;
     int launches = 1;
-    if (a->seed_mode == RT_SEED_UPSTREAM) {
+    if (a->seed_mode == RT_SEED_UPSTREAM && !continuing) {
         const size_t npix = (size_t)a->nx * a->ny;
         if (!ctx->skip_tables) {
             const std::vector<uint32_t> &t = host_skip_tables();
@@ -527,8 +543,14 @@ static int do_render(rt_context *ctx, const rt_render_args *a, float *out_dev, b
         }
         p.seed_states = ctx->seed_states;
     }
+    if (prog) {
+        p.state_out = prog->state;
+        p.accumulate = continuing ? 1 : 0;
+    }
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
-    if (p.seed_states) {   // render_init (main.cu:424): inside the timed region, as in the reference
+    if (continuing) {
+        p.seed_states = prog->state;                  // every pixel resumes its own stream
+    } else if (p.seed_states) {   // render_init (main.cu:424): inside the timed region, as in the reference
         // spp shard g draws from subsequences pixel_index + g * num_pixels (g = 0: the reference's streams)
         CK(launch_seed_upstream(ctx->seed_states, (size_t)a->nx * a->ny, 1984ull, p.seed_offset, ctx->skip_tables, ctx->stream));
         launches = 2;
@@ -604,16 +626,31 @@ extern "C" int rt_debug_counters(rt_context *ctx, uint64_t out[32]) {
     return RT_OK;
 }
 
+// device scratch of one API call, released on every exit path
+struct Scratch {
+    std::vector<void *> ptrs;
+    ~Scratch() { for (void *p : ptrs) cudaFree(p); }
+    template <typename T>
+    cudaError_t get(T *&out, size_t count) {
+        void *p = nullptr;
+        const cudaError_t e = cudaMalloc(&p, count * sizeof(T) + 16);
+        if (e == cudaSuccess) ptrs.push_back(p);
+        out = static_cast<T *>(p);
+        return e;
+    }
+};
+
 // test hook: closest hit of caller-supplied rays (host arrays of 3 floats per ray)
 extern "C" int rt_trace_rays(rt_context *ctx, int use_octree, int n, const float *org, const float *dir, int *out_idx, float *out_t) {
     if (!ctx || n < 1 || !org || !dir || !out_idx || !out_t) return fail(ctx, RT_ERR_INVALID, "rt_trace_rays: bad arguments");
     if (ctx->n < 1) return fail(ctx, RT_ERR_STATE, "rt_trace_rays: no scene");
     if (use_octree && !ctx->octree->built) return fail(ctx, RT_ERR_STATE, "rt_trace_rays: no octree built");
     CK(cudaSetDevice(ctx->device));
+    Scratch sc;
     float *d_o = nullptr, *d_d = nullptr, *d_t = nullptr;
     int *d_i = nullptr;
-    CK(cudaMalloc(&d_o, (size_t)n * 12)); CK(cudaMalloc(&d_d, (size_t)n * 12));
-    CK(cudaMalloc(&d_t, (size_t)n * 4)); CK(cudaMalloc(&d_i, (size_t)n * 4));
+    CK(sc.get(d_o, (size_t)n * 3)); CK(sc.get(d_d, (size_t)n * 3));
+    CK(sc.get(d_t, (size_t)n)); CK(sc.get(d_i, (size_t)n));
     CK(cudaMemcpyAsync(d_o, org, (size_t)n * 12, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(d_d, dir, (size_t)n * 12, cudaMemcpyHostToDevice, ctx->stream));
     RenderLaunch p;
@@ -625,7 +662,59 @@ extern "C" int rt_trace_rays(rt_context *ctx, int use_octree, int n, const float
     CK(cudaMemcpyAsync(out_idx, d_i, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaMemcpyAsync(out_t, d_t, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    cudaFree(d_o); cudaFree(d_d); cudaFree(d_t); cudaFree(d_i);
+    return RT_OK;
+}
+
+// camera::get_ray (camera.h:45-49) for n (s, t) pairs: each draws its lens sample from ITS OWN XORWOW state (6 words, in/out)
+extern "C" int rt_camera_get_rays(rt_context *ctx, int n, const float *s, const float *t, uint32_t *states6, float *org, float *dir) {
+    if (!ctx || n < 1 || !s || !t || !states6 || !org || !dir) return fail(ctx, RT_ERR_INVALID, "rt_camera_get_rays: bad arguments");
+    if (!ctx->have_camera) return fail(ctx, RT_ERR_STATE, "rt_camera_get_rays: no camera set (rt_camera_set)");
+    CK(cudaSetDevice(ctx->device));
+    Scratch sc;
+    float *d_s = nullptr, *d_t = nullptr, *d_o = nullptr, *d_d = nullptr;
+    uint32_t *d_st = nullptr;
+    CK(sc.get(d_s, (size_t)n)); CK(sc.get(d_t, (size_t)n)); CK(sc.get(d_o, (size_t)n * 3)); CK(sc.get(d_d, (size_t)n * 3)); CK(sc.get(d_st, (size_t)n * 6));
+    CK(cudaMemcpyAsync(d_s, s, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_t, t, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_st, states6, (size_t)n * 24, cudaMemcpyHostToDevice, ctx->stream));
+    CK(launch_camera_rays(ctx->cam_host, n, d_s, d_t, d_st, d_o, d_d, ctx->stream));
+    CK(cudaMemcpyAsync(org, d_o, (size_t)n * 12, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(dir, d_d, (size_t)n * 12, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(states6, d_st, (size_t)n * 24, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return RT_OK;
+}
+
+// material::scatter (material.h:55-113) + the hit record of sphere::hit (sphere.h:30-33) for n (ray, sphere, t) triples
+extern "C" int rt_scatter_rays(rt_context *ctx, int n, const int *sphere_idx, const float *org, const float *dir, const float *t_hit,
+                               uint32_t *states6, float *out_p, float *out_normal, float *out_dir, float *out_atten, int *scattered) {
+    if (!ctx || n < 1 || !sphere_idx || !org || !dir || !t_hit || !states6 || !out_p || !out_normal || !out_dir || !out_atten || !scattered)
+        return fail(ctx, RT_ERR_INVALID, "rt_scatter_rays: bad arguments");
+    if (ctx->n < 1) return fail(ctx, RT_ERR_STATE, "rt_scatter_rays: no scene");
+    CK(cudaSetDevice(ctx->device));
+    Scratch sc;
+    int *d_i = nullptr, *d_sc = nullptr;
+    float *d_o = nullptr, *d_d = nullptr, *d_t = nullptr, *d_p = nullptr, *d_n = nullptr, *d_od = nullptr, *d_a = nullptr;
+    uint32_t *d_st = nullptr;
+    CK(sc.get(d_i, (size_t)n)); CK(sc.get(d_sc, (size_t)n)); CK(sc.get(d_o, (size_t)n * 3)); CK(sc.get(d_d, (size_t)n * 3)); CK(sc.get(d_t, (size_t)n));
+    CK(sc.get(d_p, (size_t)n * 3)); CK(sc.get(d_n, (size_t)n * 3)); CK(sc.get(d_od, (size_t)n * 3)); CK(sc.get(d_a, (size_t)n * 3)); CK(sc.get(d_st, (size_t)n * 6));
+    CK(cudaMemcpyAsync(d_i, sphere_idx, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_o, org, (size_t)n * 12, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_d, dir, (size_t)n * 12, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_t, t_hit, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_st, states6, (size_t)n * 24, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemsetAsync(d_p, 0, (size_t)n * 12, ctx->stream)); CK(cudaMemsetAsync(d_n, 0, (size_t)n * 12, ctx->stream));
+    CK(cudaMemsetAsync(d_od, 0, (size_t)n * 12, ctx->stream)); CK(cudaMemsetAsync(d_a, 0, (size_t)n * 12, ctx->stream));
+    SceneView sv;
+    sv.geom = ctx->geom; sv.matl = ctx->matl; sv.tag = ctx->tag; sv.n = ctx->n;
+    CK(launch_scatter_rays(sv, n, d_i, d_o, d_d, d_t, d_st, d_p, d_n, d_od, d_a, d_sc, ctx->stream));
+    CK(cudaMemcpyAsync(out_p, d_p, (size_t)n * 12, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(out_normal, d_n, (size_t)n * 12, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(out_dir, d_od, (size_t)n * 12, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(out_atten, d_a, (size_t)n * 12, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(scattered, d_sc, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(states6, d_st, (size_t)n * 24, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
     return RT_OK;
 }
 
@@ -637,10 +726,27 @@ extern "C" int rt_render(rt_context *ctx, const rt_render_args *args, float *fb_
     return do_render(ctx, args, fb_dev, true, stats);
 }
 
+extern "C" int rt_render_progressive(rt_context *ctx, const rt_render_args *args, float *accum_dev, uint32_t *rng_state_dev, int first,
+                                     rt_render_stats *stats) {
+    if (!rng_state_dev) return fail(ctx, RT_ERR_INVALID, "rt_render_progressive: null state buffer");
+    ProgressiveIO io;
+    io.state = rng_state_dev;
+    io.first = first != 0;
+    return do_render(ctx, args, accum_dev, false, stats, &io);
+}
+
 extern "C" int rt_finalize(rt_context *ctx, const float *accum_dev, float *fb_dev, int nx, int ny, int ns) {
     if (!ctx || !accum_dev || !fb_dev || nx < 1 || ny < 1 || ns < 1) return fail(ctx, RT_ERR_INVALID, "rt_finalize: bad arguments");
     CK(cudaSetDevice(ctx->device));
     CK(launch_finalize(accum_dev, fb_dev, nx, ny, ns, ctx->stream));
+    return RT_OK;
+}
+
+extern "C" int rt_finalize_n(rt_context *ctx, const float *accum_dev, float *fb_dev, size_t count, int ns) {
+    if (!ctx || !accum_dev || !fb_dev || ns < 1) return fail(ctx, RT_ERR_INVALID, "rt_finalize_n: bad arguments");
+    if (count == 0) return RT_OK;
+    CK(cudaSetDevice(ctx->device));
+    CK(launch_finalize_n(accum_dev, fb_dev, count, ns, ctx->stream));
     return RT_OK;
 }
 
@@ -783,5 +889,145 @@ extern "C" int rt_synchronize(rt_context *ctx) {
     if (!ctx) return RT_ERR_INVALID;
     CK(cudaSetDevice(ctx->device));
     CK(cudaStreamSynchronize(ctx->stream));
+    return RT_OK;
+}
+
+// ---- multi-GPU: one context per GPU, one NCCL communicator over NVLink ------------------------------------------------
+// The path has exactly one exchange: the ranks' LINEAR radiance buffers are summed before /ns, sqrt and the
+// output switch (main.cu:424-453).  NCCL is resolved at run time (dlopen) so that librt_b200.so has no link-time
+// dependency and shares the NCCL already loaded in the process (torch's, in the Python host).
+namespace {
+struct NcclApi {
+    void *handle = nullptr;
+    decltype(&ncclGetUniqueId) GetUniqueId = nullptr;
+    decltype(&ncclCommInitRank) CommInitRank = nullptr;
+    decltype(&ncclCommInitAll) CommInitAll = nullptr;
+    decltype(&ncclCommDestroy) CommDestroy = nullptr;
+    decltype(&ncclReduce) Reduce = nullptr;
+    decltype(&ncclReduceScatter) ReduceScatter = nullptr;
+    decltype(&ncclBroadcast) Broadcast = nullptr;
+    decltype(&ncclGroupStart) GroupStart = nullptr;
+    decltype(&ncclGroupEnd) GroupEnd = nullptr;
+    decltype(&ncclGetErrorString) GetErrorString = nullptr;
+    bool ok = false;
+};
+NcclApi &nccl_api() {
+    static NcclApi api = [] {
+        NcclApi a;
+        for (const char *name : {"libnccl.so.2", "libnccl.so"}) {
+            a.handle = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+            if (a.handle) break;
+        }
+        if (!a.handle) return a;
+#define RT_NCCL_SYM(f) a.f = reinterpret_cast<decltype(a.f)>(dlsym(a.handle, "nccl" #f))
+        RT_NCCL_SYM(GetUniqueId); RT_NCCL_SYM(CommInitRank); RT_NCCL_SYM(CommInitAll); RT_NCCL_SYM(CommDestroy); RT_NCCL_SYM(Reduce);
+        RT_NCCL_SYM(ReduceScatter); RT_NCCL_SYM(Broadcast); RT_NCCL_SYM(GroupStart); RT_NCCL_SYM(GroupEnd); RT_NCCL_SYM(GetErrorString);
+#undef RT_NCCL_SYM
+        a.ok = a.GetUniqueId && a.CommInitRank && a.CommInitAll && a.CommDestroy && a.Reduce && a.ReduceScatter && a.Broadcast &&
+               a.GroupStart && a.GroupEnd && a.GetErrorString;
+        return a;
+    }();
+    return api;
+}
+int nccl_fail(rt_context *ctx, ncclResult_t r, const char *what) {
+    return fail(ctx, RT_ERR_STATE, "NCCL error %d at %s '%s'", (int)r, what, nccl_api().GetErrorString ? nccl_api().GetErrorString(r) : "?");
+}
+}  // namespace
+#define NK(call)                                               \
+    do {                                                       \
+        ncclResult_t r_ = (call);                              \
+        if (r_ != ncclSuccess) return nccl_fail(ctx, r_, #call); \
+    } while (0)
+#define NEED_NCCL(ctx) \
+    if (!nccl_api().ok) return fail(ctx, RT_ERR_UNSUPPORTED, "libnccl.so.2 not found (or too old): multi-GPU entry points are unavailable")
+
+static_assert(RT_COMM_ID_BYTES == sizeof(ncclUniqueId), "RT_COMM_ID_BYTES must match ncclUniqueId");
+
+extern "C" int rt_comm_get_unique_id(void *id) {
+    rt_context *ctx = nullptr;
+    if (!id) return RT_ERR_INVALID;
+    NEED_NCCL(ctx);
+    NK(nccl_api().GetUniqueId(static_cast<ncclUniqueId *>(id)));
+    return RT_OK;
+}
+
+extern "C" int rt_comm_init_rank(rt_context *ctx, const void *id, int nranks, int rank) {
+    if (!ctx || !id || nranks < 1 || rank < 0 || rank >= nranks) return fail(ctx, RT_ERR_INVALID, "rt_comm_init_rank: bad arguments");
+    NEED_NCCL(ctx);
+    if (ctx->comm) return fail(ctx, RT_ERR_STATE, "rt_comm_init_rank: the context already has a communicator");
+    CK(cudaSetDevice(ctx->device));
+    ncclUniqueId uid;
+    memcpy(&uid, id, sizeof uid);
+    NK(nccl_api().CommInitRank(&ctx->comm, nranks, uid, rank));
+    ctx->comm_owned = true; ctx->comm_rank = rank; ctx->comm_size = nranks;
+    return RT_OK;
+}
+
+extern "C" int rt_comm_init_all(rt_context *const *ctxs, int n) {
+    rt_context *ctx = (ctxs && n > 0) ? ctxs[0] : nullptr;
+    if (!ctx || n > 64) return fail(ctx, RT_ERR_INVALID, "rt_comm_init_all: bad arguments");
+    NEED_NCCL(ctx);
+    int devs[64];
+    ncclComm_t comms[64];
+    for (int i = 0; i < n; i++) {
+        if (!ctxs[i] || ctxs[i]->comm) return fail(ctx, RT_ERR_STATE, "rt_comm_init_all: null context, or one that already has a communicator");
+        devs[i] = ctxs[i]->device;
+    }
+    NK(nccl_api().CommInitAll(comms, n, devs));
+    for (int i = 0; i < n; i++) { ctxs[i]->comm = comms[i]; ctxs[i]->comm_owned = true; ctxs[i]->comm_rank = i; ctxs[i]->comm_size = n; }
+    return RT_OK;
+}
+
+extern "C" int rt_comm_attach(rt_context *ctx, void *nccl_comm, int nranks, int rank) {
+    if (!ctx || !nccl_comm || nranks < 1 || rank < 0 || rank >= nranks) return fail(ctx, RT_ERR_INVALID, "rt_comm_attach: bad arguments");
+    NEED_NCCL(ctx);
+    if (ctx->comm) return fail(ctx, RT_ERR_STATE, "rt_comm_attach: the context already has a communicator");
+    ctx->comm = static_cast<ncclComm_t>(nccl_comm);
+    ctx->comm_owned = false; ctx->comm_rank = rank; ctx->comm_size = nranks;
+    return RT_OK;
+}
+
+extern "C" int rt_comm_destroy(rt_context *ctx) {
+    if (!ctx) return RT_ERR_INVALID;
+    if (ctx->comm && ctx->comm_owned) {
+        cudaSetDevice(ctx->device);
+        cudaStreamSynchronize(ctx->stream);
+        nccl_api().CommDestroy(ctx->comm);
+    }
+    ctx->comm = nullptr; ctx->comm_owned = false; ctx->comm_rank = 0; ctx->comm_size = 1;
+    return RT_OK;
+}
+
+extern "C" int rt_comm_rank(const rt_context *ctx) { return ctx ? ctx->comm_rank : 0; }
+extern "C" int rt_comm_size(const rt_context *ctx) { return ctx ? ctx->comm_size : 1; }
+
+extern "C" int rt_group_start(void) { return nccl_api().ok && nccl_api().GroupStart() == ncclSuccess ? RT_OK : RT_ERR_STATE; }
+extern "C" int rt_group_end(void) { return nccl_api().ok && nccl_api().GroupEnd() == ncclSuccess ? RT_OK : RT_ERR_STATE; }
+
+extern "C" int rt_reduce(rt_context *ctx, float *accum_dev, size_t count, int root) {
+    if (!ctx || !accum_dev) return fail(ctx, RT_ERR_INVALID, "rt_reduce: null argument");
+    if (!ctx->comm) return ctx->comm_size == 1 ? RT_OK : fail(ctx, RT_ERR_STATE, "rt_reduce: no communicator (rt_comm_init_rank / rt_comm_init_all)");
+    CK(cudaSetDevice(ctx->device));
+    NK(nccl_api().Reduce(accum_dev, accum_dev, count, ncclFloat, ncclSum, root, ctx->comm, ctx->stream));
+    return RT_OK;
+}
+
+extern "C" int rt_reduce_scatter(rt_context *ctx, const float *accum_dev, float *slice_dev, size_t slice_count) {
+    if (!ctx || !accum_dev || !slice_dev) return fail(ctx, RT_ERR_INVALID, "rt_reduce_scatter: null argument");
+    CK(cudaSetDevice(ctx->device));
+    if (!ctx->comm) {
+        if (ctx->comm_size != 1) return fail(ctx, RT_ERR_STATE, "rt_reduce_scatter: no communicator");
+        if (slice_dev != accum_dev) CK(cudaMemcpyAsync(slice_dev, accum_dev, slice_count * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+        return RT_OK;
+    }
+    NK(nccl_api().ReduceScatter(accum_dev, slice_dev, slice_count, ncclFloat, ncclSum, ctx->comm, ctx->stream));
+    return RT_OK;
+}
+
+extern "C" int rt_broadcast(rt_context *ctx, void *dev, size_t bytes, int root) {
+    if (!ctx || !dev) return fail(ctx, RT_ERR_INVALID, "rt_broadcast: null argument");
+    if (!ctx->comm) return ctx->comm_size == 1 ? RT_OK : fail(ctx, RT_ERR_STATE, "rt_broadcast: no communicator");
+    CK(cudaSetDevice(ctx->device));
+    NK(nccl_api().Broadcast(dev, dev, bytes, ncclChar, root, ctx->comm, ctx->stream));
     return RT_OK;
 }

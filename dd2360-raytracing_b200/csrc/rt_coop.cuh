@@ -31,14 +31,20 @@ namespace coop {
 
 constexpr unsigned kFull = 0xffffffffu;
 constexpr uint32_t kPrologFlag = 0x80000000u;    // ring reference: index into the prolog list instead of the voxel lists
-constexpr int kRing = 64;                        // >= 31 (left over) + 32 (one chunk's pushes)
+constexpr int kRing = 96;                        // >= 31 (left over) + 64 (one chunk's pushes, two candidates per lane)
+
+struct __align__(16) RayMeta {
+    int koff;        // first reference of the lane's current voxel - ITEMS * its offset in the flat item list
+    int kend;        // one past the last reference of that voxel
+    float bound;     // t of best[] (what the pre-filter and the walk prune against)
+    int pad;
+};
 
 struct __align__(16) WarpShared {
     float4 ro[32];                   // ray origin, a = dot(d, d)
     float4 rd[32];                   // ray direction, 1/a (approximate: pre-filter only)
+    RayMeta meta[32];
     unsigned long long best[32];     // closest hit so far: float bits of t << 32 | sphere index (0xffffffff: none)
-    float bound[32];                 // t of best[] (what the pre-filter and the walk prune against)
-    int koff[32];                    // first reference of the lane's current voxel - its offset in the flat item list
     uint32_t slot[32];               // chunk position of a segment start -> owner lane
     uint2 ring[kRing];               // {owner lane, reference}
 };
@@ -47,8 +53,13 @@ __device__ __forceinline__ unsigned long long pack_hit(const float t, const uint
     return (unsigned long long)__float_as_uint(t) << 32 | idx;
 }
 
-// Exact test of up to 32 queued candidates, one per lane, folded into the owners' keys.  Entries [first, first + n).
+// Exact test of up to 32 queued candidates, one per lane, folded into the owners' records.  Entries [first, first + n).
+// The lanes whose candidates belong to the same ray find each other with MATCH.ANY and reduce (t, index) with two REDUX.MIN;
+// one lane per ray then updates the record with plain loads and stores — no shared-memory atomics (a 64-bit atomicMin is a
+// compare-and-swap loop in shared memory: 7.6 % of the stall samples of the first version of this kernel, profiles r02c).
 __device__ __forceinline__ void drain(WarpShared &ws, const SceneView &sc, const TreeView &tv, const unsigned lane, const int first, const int n) {
+    uint32_t owner = 0x100u | lane;          // a lane without a hit is a group of its own
+    uint32_t tb = 0xffffffffu, idx = 0xffffffffu;
     if ((int)lane < n) {
         const uint2 e = ws.ring[first + (int)lane];
         const float4 ro = ws.ro[e.x], rd = ws.rd[e.x];
@@ -57,31 +68,55 @@ __device__ __forceinline__ void drain(WarpShared &ws, const SceneView &sc, const
         const float4 s = pro ? __ldg(tv.prolog_geom + k) : __ldg(tv.grid.ref_geom + k);
         float t;
         if (sphere_test(s, mk(ro.x, ro.y, ro.z), mk(rd.x, rd.y, rd.z), ro.w, kTMax, t)) {
-            const uint32_t idx = pro ? __ldg(tv.prolog + k) : __ldg(tv.grid.refs + k);
-            atomicMin(&ws.best[e.x], pack_hit(t, idx));
+            idx = pro ? __ldg(tv.prolog + k) : __ldg(tv.grid.refs + k);
+            tb = __float_as_uint(t);
+            owner = e.x;
         }
+    }
+    const unsigned peers = __match_any_sync(kFull, owner);
+    const uint32_t tmin = __reduce_min_sync(peers, tb);
+    const uint32_t imin = __reduce_min_sync(peers, tb == tmin ? idx : 0xffffffffu);
+    if (tb != 0xffffffffu && (int)lane == __ffs(peers) - 1) {
+        const unsigned long long key = (unsigned long long)tmin << 32 | imin;
+        if (key < ws.best[owner]) ws.best[owner] = key;
     }
     __syncwarp();
 }
 
-// Append the lanes with `pass` to the ring; drains 32 entries when that many are queued.  Warp-uniform `count`.
-__device__ __forceinline__ void push(WarpShared &ws, const SceneView &sc, const TreeView &tv, const unsigned lane, const bool pass,
-                                     const uint32_t owner, const uint32_t ref, int &count) {
-    const unsigned m = __ballot_sync(kFull, pass);
-    if (!m) return;
-    if (pass) ws.ring[count + __popc(m & ((1u << lane) - 1u))] = make_uint2(owner, ref);
-    count += __popc(m);
+// after a drain: every lane re-reads its own ray's closest hit into the record the pre-filter prunes against
+__device__ __forceinline__ float refresh_bound(WarpShared &ws, const unsigned lane) {
+    const float t = __uint_as_float((uint32_t)(ws.best[lane] >> 32));
+    ws.meta[lane].bound = t;
+    return t;
+}
+
+// Append the lanes with pass0 / pass1 (two candidates per lane: references ref and ref + 1) to the ring; drains while 32 or
+// more are queued.  Warp-uniform `count`.
+__device__ __forceinline__ void push2(WarpShared &ws, const SceneView &sc, const TreeView &tv, const unsigned lane, const bool pass0,
+                                      const bool pass1, const uint32_t owner, const uint32_t ref, int &count) {
+    const unsigned m0 = __ballot_sync(kFull, pass0), m1 = __ballot_sync(kFull, pass1);
+    if (!(m0 | m1)) return;
+    const unsigned lt = (1u << lane) - 1u;
+    const int c0 = __popc(m0);
+    if (pass0) ws.ring[count + __popc(m0 & lt)] = make_uint2(owner, ref);
+    if (pass1) ws.ring[count + c0 + __popc(m1 & lt)] = make_uint2(owner, ref + 1u);
+    count += c0 + __popc(m1);
     __syncwarp();
     if (count >= 32) {
-        drain(ws, sc, tv, lane, count - 32, 32);      // the newest 32; what is left stays at the front
-        count -= 32;
-        ws.bound[lane] = __uint_as_float((uint32_t)(ws.best[lane] >> 32));
+        do {
+            drain(ws, sc, tv, lane, count - 32, 32);      // the newest 32; what is left stays at the front
+            count -= 32;
+        } while (count >= 32);
+        refresh_bound(ws, lane);
         __syncwarp();
     }
 }
 
 // Closest hit for the rays of the whole warp (lane `has` a ray or idles along).  Every lane of the warp must call.
+// ITEMS = candidates per lane and chunk step (1 or 2: with 2 a lane takes two consecutive references of one voxel list,
+// so the owner lookup and the ray fetch are paid once per pair and two geometry loads are in flight).
 // Returns the minimum over ALL candidates (the visibility rule is applied by the caller, as in trace_tree).
+template <int ITEMS>
 __device__ __forceinline__ Hit coop_trace(WarpShared &ws, const SceneView &sc, const TreeView &tv, const unsigned lane, const bool has,
                                           const vec3f o, const vec3f d, TraceCounters &tc) {
     const float a = dot3(d, d);
@@ -98,21 +133,20 @@ __device__ __forceinline__ Hit coop_trace(WarpShared &ws, const SceneView &sc, c
             if (sphere_test(__ldg(sc.geom), o, d, a, kTMax, t)) { best_t = t; idx = 0u; }
         }
         ws.best[lane] = pack_hit(best_t, idx);
-        ws.bound[lane] = best_t;
+        ws.meta[lane].bound = best_t;
     }
     __syncwarp();
     int count = 0;
     for (int k = 1; k < tv.nprolog; k++) {   // big spheres: one pre-filter per lane, exact tests through the ring
         const float4 s = __ldg(tv.prolog_geom + k);
         if (has) RT_COUNT(sphere_tests);
-        push(ws, sc, tv, lane, has && maybe_hit(s, o, d, a, ia, ws.bound[lane]), lane, kPrologFlag | (uint32_t)k, count);
+        push2(ws, sc, tv, lane, has && maybe_hit(s, o, d, a, ia, ws.meta[lane].bound), false, lane, kPrologFlag | (uint32_t)k, count);
     }
     if (count) {
         drain(ws, sc, tv, lane, 0, count);
         count = 0;
     }
-    best_t = __uint_as_float((uint32_t)(ws.best[lane] >> 32));
-    ws.bound[lane] = best_t;
+    best_t = refresh_bound(ws, lane);
 
     // ---- 3D-DDA set-up, per lane (as trace_walk) ----
     const GridView &g = tv.grid;
@@ -165,8 +199,8 @@ __device__ __forceinline__ Hit coop_trace(WarpShared &ws, const SceneView &sc, c
         }
         if (!__any_sync(kFull, walking)) break;
 
-        // ---- lay the lanes' reference ranges end to end ----
-        const uint32_t mine = walking ? cnt : 0u;
+        // ---- lay the lanes' reference ranges end to end, in units of ITEMS references ----
+        const uint32_t mine = walking ? (cnt + (uint32_t)(ITEMS - 1)) / (uint32_t)ITEMS : 0u;
         uint32_t incl = mine;
 #pragma unroll
         for (int off = 1; off < 32; off <<= 1) {
@@ -175,7 +209,8 @@ __device__ __forceinline__ Hit coop_trace(WarpShared &ws, const SceneView &sc, c
         }
         const uint32_t total = __shfl_sync(kFull, incl, 31);
         const uint32_t excl = incl - mine;
-        ws.koff[lane] = (int)k - (int)excl;
+        ws.meta[lane].koff = (int)k - ITEMS * (int)excl;
+        ws.meta[lane].kend = (int)(k + cnt);
         __syncwarp();
 
         for (uint32_t base = 0; base < total; base += 32u) {
@@ -190,21 +225,28 @@ __device__ __forceinline__ Hit coop_trace(WarpShared &ws, const SceneView &sc, c
             const bool valid = item < total;
             const uint32_t owner = ws.slot[31 - __clz(starts & (0xffffffffu >> (31u - lane)))];   // bit 0 is always a start
             const float4 ro = ws.ro[owner], rd = ws.rd[owner];
-            const uint32_t ref = (uint32_t)(ws.koff[owner] + (int)item);
-            bool pass = false;
+            const RayMeta mt = ws.meta[owner];
+            const uint32_t ref = (uint32_t)(mt.koff + ITEMS * (int)item);
+            bool pass0 = false, pass1 = false;
             if (valid) {
+                const vec3f oo = mk(ro.x, ro.y, ro.z), dd = mk(rd.x, rd.y, rd.z);
+                const float4 s0 = __ldg(g.ref_geom + ref);
+                if (ITEMS == 2) {
+                    const float4 s1 = __ldg(g.ref_geom + ref + 1);     // (one past a list's end is the next list's first entry, or the slack element)
+                    RT_COUNT(sphere_tests);
+                    pass1 = (int)ref + 1 < mt.kend && maybe_hit(s1, oo, dd, ro.w, rd.w, mt.bound);
+                }
                 RT_COUNT(sphere_tests);
-                pass = maybe_hit(__ldg(g.ref_geom + ref), mk(ro.x, ro.y, ro.z), mk(rd.x, rd.y, rd.z), ro.w, rd.w, ws.bound[owner]);
+                pass0 = maybe_hit(s0, oo, dd, ro.w, rd.w, mt.bound);
             }
             __syncwarp();                       // slot[] is rewritten by the next chunk
-            push(ws, sc, tv, lane, pass, owner, ref, count);
+            push2(ws, sc, tv, lane, pass0, pass1, owner, ref, count);
         }
         if (count) {
             drain(ws, sc, tv, lane, 0, count);
             count = 0;
         }
-        best_t = __uint_as_float((uint32_t)(ws.best[lane] >> 32));
-        ws.bound[lane] = best_t;
+        best_t = refresh_bound(ws, lane);
         cnt = 0u;                               // every published range was consumed: the advance loop steps on
         __syncwarp();
     }
@@ -216,9 +258,10 @@ __device__ __forceinline__ Hit coop_trace(WarpShared &ws, const SceneView &sc, c
 }
 
 // hitTree semantics on top of coop_trace: the visibility rule on the winner (as trace_tree), the rare failures re-walked per lane
+template <int ITEMS>
 __device__ __forceinline__ Hit coop_trace_tree(WarpShared &ws, const SceneView &sc, const TreeView &tv, const float *planes, const unsigned lane,
                                                const bool has, const vec3f o, const vec3f d, TraceCounters &tc) {
-    Hit h = coop_trace(ws, sc, tv, lane, has, o, d, tc);
+    Hit h = coop_trace<ITEMS>(ws, sc, tv, lane, has, o, d, tc);
     if (has && h.idx > 0 && tv.check_visibility && !visible_fast(tv, planes, __ldg(sc.geom + h.idx), o, d, h.t)) {
         int last_ok = -1;
         if (!sphere_visible(tv.vis, planes, h.idx, o, d, last_ok, tc)) h = trace_walk<true>(sc, tv, planes, o, d, tc);
@@ -226,7 +269,7 @@ __device__ __forceinline__ Hit coop_trace_tree(WarpShared &ws, const SceneView &
     return h;
 }
 
-template <int MINB>
+template <int MINB, int ITEMS>
 __global__ void __launch_bounds__(kRenderThreads, MINB) k_render_coop(const __grid_constant__ RenderLaunch p) {
     __shared__ WarpShared wsh[kRenderThreads / 32];
     WarpShared &ws = wsh[threadIdx.x >> 5];
@@ -260,6 +303,10 @@ __global__ void __launch_bounds__(kRenderThreads, MINB) k_render_coop(const __gr
                     pix = pj * p.nx + pi;
                     s = 0; depth = 0;
                     col = mk(0, 0, 0);
+                    if (p.accumulate) {          // progressive: continue the pixel's sum exactly where the last call left it
+                        const float *acc = p.out + (size_t)pix * 3;
+                        col = mk(acc[0], acc[1], acc[2]);
+                    }
                     pixel_stream(p, pix, rng);
                 }
             }
@@ -276,7 +323,7 @@ __global__ void __launch_bounds__(kRenderThreads, MINB) k_render_coop(const __gr
         }
         if (has) nrays++;
         __syncwarp();
-        const Hit h = coop_trace_tree(ws, sc, p.tree, &p.tree.planes[0][0], lane, has, o, d, tc);
+        const Hit h = coop_trace_tree<ITEMS>(ws, sc, p.tree, &p.tree.planes[0][0], lane, has, o, d, tc);
         if (has) {   // ---- one iteration of color()'s loop (main.cu:47-73) ----
             bool sample_done = false;
             vec3f contrib = mk(0, 0, 0);
@@ -311,6 +358,10 @@ __global__ void __launch_bounds__(kRenderThreads, MINB) k_render_coop(const __gr
                         out[2] = sqrt_(mul_(col.z, inv_ns));
                     } else {
                         out[0] = col.x; out[1] = col.y; out[2] = col.z;
+                    }
+                    if (p.state_out) {           // main.cu:136: rand_state[pixel_index] = local_rand_state
+                        uint2 *so = reinterpret_cast<uint2 *>(p.state_out + (size_t)pix * 6);
+                        so[0] = make_uint2(rng.d, rng.v0); so[1] = make_uint2(rng.v1, rng.v2); so[2] = make_uint2(rng.v3, rng.v4);
                     }
                     pix = -1;
                 }
@@ -348,13 +399,13 @@ __global__ void __launch_bounds__(kRenderThreads) k_trace_rays_coop(const __grid
     const vec3f d = has ? mk(dir[3 * i], dir[3 * i + 1], dir[3 * i + 2]) : mk(0, 0, 1);
     TraceCounters tc;
     tc.sphere_tests = tc.node_tests = tc.voxel_steps = 0;
-    const Hit h = coop_trace_tree(wsh[threadIdx.x >> 5], p.scene, p.tree, &p.tree.planes[0][0], threadIdx.x & 31u, has, o, d, tc);
+    const Hit h = coop_trace_tree<2>(wsh[threadIdx.x >> 5], p.scene, p.tree, &p.tree.planes[0][0], threadIdx.x & 31u, has, o, d, tc);
     if (has) { out_idx[i] = h.idx; out_t[i] = h.t; }
 }
 
-template <int MINB>
+template <int MINB, int ITEMS>
 static cudaError_t launch_coop(const RenderLaunch &p, int sm_count, cudaStream_t st, int *blocks_out) {
-    auto kern = k_render_coop<MINB>;
+    auto kern = k_render_coop<MINB, ITEMS>;
     int per_sm = 0;
     cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kRenderThreads, 0);
     if (e != cudaSuccess) return e;

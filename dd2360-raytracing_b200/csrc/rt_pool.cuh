@@ -156,7 +156,9 @@ __device__ __forceinline__ void body_cand(const Ctx<NC> c, const RenderLaunch &p
     const float4 s = __ldg(p.scene.geom + idx);
     float t;
     RT_COUNT(sphere_tests);
-    if (sphere_test(s, o, d, a, ht, t)) { c.sf(F_HT, t); c.su(F_HIDX, (uint32_t)idx); }
+    if (sphere_test(s, o, d, a, tie_bound(ht), t) && (t < ht || (uint32_t)idx < c.u(F_HIDX))) {   // ties: the smaller index (rt_trace.cuh)
+        c.sf(F_HT, t); c.su(F_HIDX, (uint32_t)idx);
+    }
     cm &= cm - 1u;                                   // clear the lowest flagged position
     if (cm & 15u) { c.su(F_CM, cm); return; }        // more flagged candidates in this chunk: stay in CAND
     k += cm >> 4;

@@ -189,6 +189,10 @@ __global__ void __launch_bounds__(kRenderThreads, 6) k_render(const __grid_const
                     pix = pj * p.nx + pi;
                     s = 0; depth = 0;
                     col = mk(0, 0, 0);
+                    if (p.accumulate) {          // progressive: continue the pixel's sum exactly where the last call left it
+                        const float *acc = p.out + (size_t)pix * 3;
+                        col = mk(acc[0], acc[1], acc[2]);
+                    }
                     pixel_stream(p, pix, rng);
                 }
             }
@@ -242,6 +246,10 @@ __global__ void __launch_bounds__(kRenderThreads, 6) k_render(const __grid_const
                         out[2] = sqrt_(mul_(col.z, inv_ns));
                     } else {
                         out[0] = col.x; out[1] = col.y; out[2] = col.z;
+                    }
+                    if (p.state_out) {           // main.cu:136: rand_state[pixel_index] = local_rand_state
+                        uint2 *so = reinterpret_cast<uint2 *>(p.state_out + (size_t)pix * 6);
+                        so[0] = make_uint2(rng.d, rng.v0); so[1] = make_uint2(rng.v1, rng.v2); so[2] = make_uint2(rng.v3, rng.v4);
                     }
                     pix = -1;
                 }
@@ -356,17 +364,70 @@ cudaError_t launch_trace_rays(const RenderLaunch &p, bool octree, const float *o
     return cudaGetLastError();
 }
 
+// camera::get_ray (camera.h:45-49) and material::scatter (material.h:55-113) for caller-supplied inputs, evaluated by the same
+// device functions the render kernels inline — the class-surface entry points of include/rt_dropin.h and a per-call parity hook.
+__global__ void k_camera_rays(const CameraData cam, int n, const float *__restrict__ s, const float *__restrict__ t, uint32_t *__restrict__ states,
+                              float *__restrict__ org, float *__restrict__ dir) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    xorwow rng;
+    uint32_t *st = states + (size_t)i * 6;
+    rng.d = st[0]; rng.v0 = st[1]; rng.v1 = st[2]; rng.v2 = st[3]; rng.v3 = st[4]; rng.v4 = st[5];
+    vec3f o, d;
+    camera_ray(cam, s[i], t[i], rng, o, d);
+    org[3 * i] = o.x; org[3 * i + 1] = o.y; org[3 * i + 2] = o.z;
+    dir[3 * i] = d.x; dir[3 * i + 1] = d.y; dir[3 * i + 2] = d.z;
+    st[0] = rng.d; st[1] = rng.v0; st[2] = rng.v1; st[3] = rng.v2; st[4] = rng.v3; st[5] = rng.v4;
+}
+cudaError_t launch_camera_rays(const CameraData &cam, int n, const float *s, const float *t, uint32_t *states, float *org, float *dir,
+                               cudaStream_t st) {
+    k_camera_rays<<<(n + 127) / 128, 128, 0, st>>>(cam, n, s, t, states, org, dir);
+    return cudaGetLastError();
+}
+
+// in: ray (org, dir), the sphere it hit and the ray parameter of the hit.  out: hit point = scattered origin, normal,
+// scattered direction, attenuation, and whether the ray goes on (metal absorbs: material.h:72)
+__global__ void k_scatter_rays(const SceneView sc, int n, const int *__restrict__ sphere_idx, const float *__restrict__ org,
+                               const float *__restrict__ dir, const float *__restrict__ t_hit, uint32_t *__restrict__ states,
+                               float *__restrict__ out_p, float *__restrict__ out_n, float *__restrict__ out_dir, float *__restrict__ out_att,
+                               int *__restrict__ scattered) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int idx = sphere_idx[i];
+    if (idx < 0 || idx >= sc.n || sc.tag[idx] < 0) { scattered[i] = -1; return; }
+    xorwow rng;
+    uint32_t *st = states + (size_t)i * 6;
+    rng.d = st[0]; rng.v0 = st[1]; rng.v1 = st[2]; rng.v2 = st[3]; rng.v3 = st[4]; rng.v4 = st[5];
+    const vec3f o = mk(org[3 * i], org[3 * i + 1], org[3 * i + 2]), d = mk(dir[3 * i], dir[3 * i + 1], dir[3 * i + 2]);
+    vec3f hp, hn, att, dn = mk(0.f, 0.f, 0.f);
+    hit_point(sc.geom[idx], o, d, t_hit[i], hp, hn);
+    const bool go = scatter(sc.tag[idx], sc.matl[idx], d, hp, hn, att, dn, rng);
+    out_p[3 * i] = hp.x; out_p[3 * i + 1] = hp.y; out_p[3 * i + 2] = hp.z;
+    out_n[3 * i] = hn.x; out_n[3 * i + 1] = hn.y; out_n[3 * i + 2] = hn.z;
+    out_dir[3 * i] = dn.x; out_dir[3 * i + 1] = dn.y; out_dir[3 * i + 2] = dn.z;
+    out_att[3 * i] = att.x; out_att[3 * i + 1] = att.y; out_att[3 * i + 2] = att.z;
+    scattered[i] = go ? 1 : 0;
+    st[0] = rng.d; st[1] = rng.v0; st[2] = rng.v1; st[3] = rng.v2; st[4] = rng.v3; st[5] = rng.v4;
+}
+cudaError_t launch_scatter_rays(const SceneView &sc, int n, const int *sphere_idx, const float *org, const float *dir, const float *t_hit,
+                                uint32_t *states, float *out_p, float *out_n, float *out_dir, float *out_att, int *scattered, cudaStream_t st) {
+    k_scatter_rays<<<(n + 127) / 128, 128, 0, st>>>(sc, n, sphere_idx, org, dir, t_hit, states, out_p, out_n, out_dir, out_att, scattered);
+    return cudaGetLastError();
+}
+
 // fb = sqrt(accum * (1/ns)) (main.cu:111-114), for frames assembled from shards
 __global__ void k_finalize(const float *__restrict__ accum, float *__restrict__ fb, size_t n3, float inv_ns) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n3) fb[i] = __fsqrt_rn(__fmul_rn(accum[i], inv_ns));
 }
 
-cudaError_t launch_finalize(const float *accum, float *fb, int nx, int ny, int ns, cudaStream_t st) {
-    const size_t n3 = (size_t)nx * ny * 3;
+cudaError_t launch_finalize_n(const float *accum, float *fb, size_t n3, int ns, cudaStream_t st) {
     const float inv_ns = (float)(1.0 / (double)(float)ns);
     k_finalize<<<(unsigned)((n3 + 255) / 256), 256, 0, st>>>(accum, fb, n3, inv_ns);
     return cudaGetLastError();
+}
+cudaError_t launch_finalize(const float *accum, float *fb, int nx, int ny, int ns, cudaStream_t st) {
+    return launch_finalize_n(accum, fb, (size_t)nx * ny * 3, ns, st);
 }
 
 template <bool OCTREE, bool GEOM_SMEM>
@@ -398,7 +459,8 @@ cudaError_t launch_render(const RenderLaunch &p, bool octree, int sm_count, size
     if (octree) {
         // the pooled kernel packs depth into 8 bits and the sample number into 24 (rt_pool.cuh F_SD): outside that range the
         // other kernels render the frame
-        const bool pool_ok = p.max_depth <= 255 && p.ns_local < (1 << 24);
+        // ... and it has no progressive state carry (state_out / accumulate)
+        const bool pool_ok = p.max_depth <= 255 && p.ns_local < (1 << 24) && !p.state_out && !p.accumulate;
         which = kKernelPool;
         switch (pool_ok ? p.variant : -1) {          // A/B measurement variants; all produce the same image
             case 10: return pool::launch_pool<96, 4>(p, sm_count, st, blocks_out);
@@ -411,18 +473,23 @@ cudaError_t launch_render(const RenderLaunch &p, bool octree, int sm_count, size
         }
         which = kKernelCoop;
         switch (p.variant) {
-            case 40: return coop::launch_coop<6>(p, sm_count, st, blocks_out);
-            case 41: return coop::launch_coop<5>(p, sm_count, st, blocks_out);
-            case 42: return coop::launch_coop<4>(p, sm_count, st, blocks_out);
-            case 43: return coop::launch_coop<8>(p, sm_count, st, blocks_out);
+            case 40: return coop::launch_coop<6, 2>(p, sm_count, st, blocks_out);
+            case 41: return coop::launch_coop<5, 2>(p, sm_count, st, blocks_out);
+            case 42: return coop::launch_coop<4, 2>(p, sm_count, st, blocks_out);
+            case 43: return coop::launch_coop<8, 2>(p, sm_count, st, blocks_out);
+            case 44: return coop::launch_coop<6, 1>(p, sm_count, st, blocks_out);     // one candidate per lane and chunk step
             default: break;
         }
-        // measured on B200 (profiles/README.md, profiles/sweep_pool_threshold.py at 4K): pooled / pixel-per-lane speed
-        // 0.87x at 100 k spheres, 1.07x at 300 k, ~1.5x at 1 M — the pooled kernel pays off once candidate lists are
-        // long (at 1200x800 the crossover sits in the same place: k_render ahead at 100 k, the pool at 300 k)
+        // automatic choice by scene size (measured on B200, profiles/README.md): the pixel-per-lane walk for small scenes (short
+        // candidate lists, many empty voxels), the warp-cooperative kernel from kCoopMinSpheres on, the pooled kernel from
+        // kPoolMinSpheres on; variant 1 forces the pixel-per-lane walk
         if (p.variant != 1 && pool_ok && p.scene.n >= kPoolMinSpheres) {
             which = kKernelPool;
             return pool::launch_pool<64, 6>(p, sm_count, st, blocks_out);
+        }
+        if (p.variant != 1 && p.scene.n >= kCoopMinSpheres) {
+            which = kKernelCoop;
+            return coop::launch_coop<6, 2>(p, sm_count, st, blocks_out);
         }
         which = kKernelLane;
         return launch_variant<true, false>(p, 0, sm_count, st, blocks_out);

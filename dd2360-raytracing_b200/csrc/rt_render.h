@@ -11,6 +11,7 @@ namespace rt {
 constexpr int kRenderThreads = 128;
 constexpr int kListGridMinSpheres = 256;   // flat-list mode: scenes at least this large are answered through the grid
 constexpr int kPoolMinSpheres = 200000;  // octree mode: scenes at least this large use the pooled kernel (rt_pool.cuh)
+constexpr int kCoopMinSpheres = 20000;   // ... and scenes at least this large the warp-cooperative kernel (rt_coop.cuh)
 
 struct RenderLaunch {
     SceneView scene;
@@ -24,7 +25,11 @@ struct RenderLaunch {
     int tile_first, tile_stride;   // this shard owns tiles tile_first + k*tile_stride
     uint32_t total_items;    // owned tiles * 32
     unsigned long long seed_offset;   // added to the per-pixel seed 1984 + pixel_index (spp shards)
-    const uint32_t *seed_states;      // RT_SEED_UPSTREAM: 6 words {d, v0..v4} per pixel from k_seed_upstream; else nullptr
+    const uint32_t *seed_states;      // 6 words {d, v0..v4} per pixel to START from (RT_SEED_UPSTREAM: from k_seed_upstream; progressive
+                                      // continuation: the states the previous call stored); nullptr = seed in the kernel (HEAD)
+    uint32_t *state_out;              // progressive rendering (main.cu:119-142): every pixel's stream state is stored here when its
+                                      // samples of this call are done (same layout); nullptr otherwise
+    int accumulate;                   // 1: a pixel's sum CONTINUES from the value in `out` (fb += col, main.cu:141, in one-shot order)
     uint32_t max_rounds;     // pool kernel watchdog: scheduling rounds per warp before it gives up (host reports an error)
     int tune_sticky, tune_sticky_min;   // pool kernel: TEST chunks per scheduling round, and the lane count that keeps it going
     int tune_test_min;       // pool kernel: TEST is only scheduled ahead of fuller-enough other states once this many contexts wait in it
@@ -41,6 +46,10 @@ cudaError_t launch_render(const RenderLaunch &p, bool octree, int sm_count, size
                           int *blocks_out, int *kernel_out);
 cudaError_t launch_trace_rays(const RenderLaunch &p, bool octree, const float *org, const float *dir, int n, int *out_idx,
                               float *out_t, cudaStream_t st);
+cudaError_t launch_camera_rays(const CameraData &cam, int n, const float *s, const float *t, uint32_t *states, float *org, float *dir,
+                               cudaStream_t st);
+cudaError_t launch_scatter_rays(const SceneView &sc, int n, const int *sphere_idx, const float *org, const float *dir, const float *t_hit,
+                                uint32_t *states, float *out_p, float *out_n, float *out_dir, float *out_att, int *scattered, cudaStream_t st);
 // render_init with the upstream seeding curand_init(1984, pixel_index + subsequence_base, 0) (main.cu:90)
 cudaError_t launch_seed_upstream(uint32_t *states, size_t npix, unsigned long long seed, unsigned long long subsequence_base,
                                  const uint32_t *tables, cudaStream_t st);
@@ -72,5 +81,6 @@ struct PpmWorkspace {
 cudaError_t ppm_format_device(PpmWorkspace &ws, const float *fb, int nx, int ny, cudaStream_t st, size_t *len_out);
 void ppm_free(PpmWorkspace &ws);
 cudaError_t launch_finalize(const float *accum, float *fb, int nx, int ny, int ns, cudaStream_t st);
+cudaError_t launch_finalize_n(const float *accum, float *fb, size_t count, int ns, cudaStream_t st);
 
 }  // namespace rt

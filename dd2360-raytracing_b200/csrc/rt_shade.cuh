@@ -108,8 +108,17 @@ RT_HD bool scatter(const int tag, const float4 m, const vec3f d_in, const vec3f 
         ni_over_nt = div_(1.0f, ref_idx);
         cosine = div_(-ddn, sqrt_(dot3(d_in, d_in)));
     }
-    if (refract(d_in, outward, ni_over_nt, refracted)) reflect_prob = schlick(cosine, ref_idx);
-    else reflect_prob = 1.0f;
+    if (refract(d_in, outward, ni_over_nt, refracted)) {
+        reflect_prob = schlick(cosine, ref_idx);
+    } else {
+        reflect_prob = 1.0f;
+        // material.h:88 leaves `refracted` uninitialised and :109 reads it when total internal reflection meets
+        // curand_uniform == 1.0 (the draw is in (0, 1]; ~3e-8 per such event — config 3 at full size has one, pixel (2070, 687)).
+        // The reference's sm_100 build then uses what its registers hold; read off its SASS (render, dielectric::scatter at
+        // 0x4f10, select at 0x6c90): (v.y, v.z, unit_vector(v).y) with v = r_in.direction().  Reproduced so that the frame
+        // matches the reference's to the last pixel; with zeros instead that pixel turns NaN.
+        refracted = mk(d_in.y, d_in.z, div_(d_in.y, sqrt_(dot3(d_in, d_in))));
+    }
     d_out = (xorwow_uniform(rng) < reflect_prob) ? reflected : refracted;
     return true;
 }

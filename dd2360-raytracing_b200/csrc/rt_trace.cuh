@@ -14,6 +14,8 @@
 // reference's quirks exactly: spheres dropped on bucket overflow, spheres outside the root box, hits the line test
 // never reaches.  All pruning is conservative (margins below), so the minimum is unchanged.
 #pragma once
+#include <string.h>
+
 #include "rt_shade.cuh"
 
 namespace rt {
@@ -44,9 +46,24 @@ struct TraceCounters {
 #define RT_COUNT(field) ((void)0)
 #endif
 
-// Ties: two DIFFERENT spheres with bit-identical t keep whichever is tested first, here as in the reference
-// (strict '<').  Voxel reference lists are sorted at build time, so the outcome is deterministic run to run;
-// it could differ from the reference's pick only for such exact ties, which the generated scenes do not produce.
+// Ties: two DIFFERENT spheres with bit-identical t.  The reference keeps whichever it tests first (strict '<'): the ground,
+// then cells in child order, leaf lists in ascending sphere index — for spheres that share their level-3 cells (the generated
+// scenes: radius 0.1 against 2.75-wide cells) that is the SMALLER INDEX.  BASELINE config 3 at full size has ~170 such
+// pixels (1e9 rays against 7-fold overlapping spheres); the frame of the reference's CUDA build settles the rule
+// (tests/golden/ref_cuda/manifest_full.json): every kernel here resolves ties to the smaller index, whatever its test order.
+// tie_bound(t) is the next float above t, so that sphere_test's strict `root < t_max` lets an equal root through.
+RT_HD float tie_bound(const float t) {
+#if defined(__CUDA_ARCH__)
+    return __uint_as_float(__float_as_uint(t) + 1u);
+#else
+    uint32_t u;
+    memcpy(&u, &t, 4);
+    u += 1u;
+    float r;
+    memcpy(&r, &u, 4);
+    return r;
+#endif
+}
 
 // ---- flat list: every sphere, SoA float4, warp-uniform address (broadcast) ------------------------------------
 template <typename GeomPtr>
@@ -223,7 +240,7 @@ RT_HD Hit trace_walk(const SceneView &sc, const TreeView &tv, const float *plane
         float t;
         RT_COUNT(sphere_tests);
         const float4 s = RT_LDG(sc.geom + idx);
-        if (maybe_hit(s, o, d, r.a, ia, h.t) && sphere_test(s, o, d, r.a, h.t, t) &&
+        if (maybe_hit(s, o, d, r.a, ia, h.t) && sphere_test(s, o, d, r.a, tie_bound(h.t), t) && (t < h.t || idx < h.idx) &&
             (!CHECKED || sphere_visible(tv.vis, planes, idx, o, d, last_ok, tc))) {
             h.t = t; h.idx = idx;
         }
@@ -287,14 +304,14 @@ RT_HD Hit trace_walk(const SceneView &sc, const TreeView &tv, const float *plane
             const bool m0 = maybe_hit(s0, o, d, r.a, ia, h.t), m1 = two & maybe_hit(s1, o, d, r.a, ia, h.t);
             float t;
             RT_COUNT(sphere_tests);
-            if (m0 && sphere_test(s0, o, d, r.a, h.t, t)) {
+            if (m0 && sphere_test(s0, o, d, r.a, tie_bound(h.t), t)) {
                 const int idx = (int)RT_LDG(g.refs + k);
-                if (!CHECKED || sphere_visible(tv.vis, planes, idx, o, d, last_ok, tc)) { h.t = t; h.idx = idx; }
+                if ((t < h.t || idx < h.idx) && (!CHECKED || sphere_visible(tv.vis, planes, idx, o, d, last_ok, tc))) { h.t = t; h.idx = idx; }
             }
             if (two) RT_COUNT(sphere_tests);
-            if (m1 && sphere_test(s1, o, d, r.a, h.t, t)) {
+            if (m1 && sphere_test(s1, o, d, r.a, tie_bound(h.t), t)) {
                 const int idx = (int)RT_LDG(g.refs + k + 1);
-                if (!CHECKED || sphere_visible(tv.vis, planes, idx, o, d, last_ok, tc)) { h.t = t; h.idx = idx; }
+                if ((t < h.t || idx < h.idx) && (!CHECKED || sphere_visible(tv.vis, planes, idx, o, d, last_ok, tc))) { h.t = t; h.idx = idx; }
             }
             k += two ? 2u : 1u;
         }

@@ -152,12 +152,32 @@ int rt_debug_counters(rt_context *ctx, uint64_t out[32]);
 /* test hook: closest hit (sphere index or -1, and t) of n caller-supplied rays — hitTree / hitable_list::hit per ray */
 int rt_trace_rays(rt_context *ctx, int use_octree, int n, const float *org, const float *dir, int *out_idx, float *out_t);
 
+/* camera::get_ray(s, t, &rand_state) (camera.h:45-49) for n (s, t) pairs, each drawing its lens sample from its own XORWOW
+ * state (6 words {d, v0..v4}, host array, updated in place; start one with rt_xorwow_state); org / dir: 3 floats per ray.
+ * Evaluated on the GPU by the device function the render kernels inline. */
+int rt_camera_get_rays(rt_context *ctx, int n, const float *s, const float *t, uint32_t *states6, float *org, float *dir);
+/* material::scatter (material.h:55-113) with the hit record sphere::hit fills (sphere.h:30-33), for n (ray, sphere, t):
+ * out_p = hit point = origin of the scattered ray, out_normal, out_dir = scattered direction, out_atten = attenuation,
+ * scattered = 1 / 0 (metal absorbs, material.h:72) / -1 (not a defined sphere).  States as in rt_camera_get_rays. */
+int rt_scatter_rays(rt_context *ctx, int n, const int *sphere_idx, const float *org, const float *dir, const float *t_hit,
+                    uint32_t *states6, float *out_p, float *out_normal, float *out_dir, float *out_atten, int *scattered);
+
 /* ---- render: replaces render_init + render (main.cu:424-429) ---------------------------------------------- */
 /* Renders this rank's shard into `accum_dev` (device pointer, nx*ny*3 floats): LINEAR radiance sums (before
  * /ns and sqrt), zero where the shard owns nothing, so that shards add up (main.cu:119-142 semantics). */
 int rt_render_accumulate(rt_context *ctx, const rt_render_args *args, float *accum_dev, rt_render_stats *stats);
+/* Progressive rendering — render_progressive (main.cu:119-142) with its state carry: every call traces args->ns MORE samples
+ * per pixel, resuming each pixel's XORWOW stream where the previous call stored it (rng_state_dev: 6 words {d, v0..v4} per
+ * pixel, nx*ny*24 bytes of device memory owned by the caller; main.cu:136) and continuing each pixel's sum from the value
+ * in accum_dev in the order a one-shot render adds its samples (main.cu:141).  k calls of m samples therefore leave, bit for
+ * bit, the linear sums (and stream states) of one k*m-sample rt_render_accumulate.  first != 0 starts the streams
+ * (args->seed_mode) and overwrites accum_dev.  Dump a frame at any point with rt_finalize(.., samples so far).  FP32 only. */
+int rt_render_progressive(rt_context *ctx, const rt_render_args *args, float *accum_dev, uint32_t *rng_state_dev, int first,
+                          rt_render_stats *stats);
 /* fb = sqrt(accum * (1/ns)) per channel (main.cu:111-114); in place allowed */
 int rt_finalize(rt_context *ctx, const float *accum_dev, float *fb_dev, int nx, int ny, int ns);
+/* the same on `count` consecutive floats: a rank's slice of the frame after rt_reduce_scatter */
+int rt_finalize_n(rt_context *ctx, const float *accum_dev, float *fb_dev, size_t count, int ns);
 /* Whole frame on one GPU straight into the reference's fb layout (device pointer, vec3 per pixel). */
 int rt_render(rt_context *ctx, const rt_render_args *args, float *fb_dev, rt_render_stats *stats);
 /* Same with a HOST destination: render + device->host copy (what the reference does through managed memory). */
@@ -174,6 +194,31 @@ size_t rt_format_ppm(const float *fb_host, int nx, int ny, char *buf, size_t cap
 int rt_ppm_format(rt_context *ctx, const float *fb_dev, int nx, int ny, size_t *len_out);
 int rt_ppm_read(rt_context *ctx, char *buf_host, size_t cap);
 int rt_render_to_ppm(rt_context *ctx, const rt_render_args *args, rt_render_stats *stats, size_t *len_out);
+
+/* ---- multi-GPU: one context per GPU, NCCL over NVLink ---------------------------------------------------------
+ * The reference is single-GPU; this wraps the one exchange a sharded frame needs, between render (main.cu:427) and the
+ * output switch (main.cu:435-453): the ranks' LINEAR radiance buffers (rt_render_accumulate with RT_SHARD_TILES or
+ * RT_SHARD_SPP) are summed, then /ns, sqrt and the PPM writer run on the sum.  All calls are asynchronous on the context's
+ * stream.  NCCL is looked up at run time (libnccl.so.2); without it these entry points return RT_ERR_UNSUPPORTED.
+ *   one process per GPU : rank 0 calls rt_comm_get_unique_id, ships the 128 bytes to the others, all call rt_comm_init_rank;
+ *   one process, n GPUs : rt_comm_init_all over n contexts, and collectives bracketed by rt_group_start / rt_group_end;
+ *   caller-owned NCCL   : rt_comm_attach(ctx, ncclComm_t, nranks, rank). */
+#define RT_COMM_ID_BYTES 128
+int rt_comm_get_unique_id(void *id_out);
+int rt_comm_init_rank(rt_context *ctx, const void *id, int nranks, int rank);
+int rt_comm_init_all(rt_context *const *ctxs, int n);
+int rt_comm_attach(rt_context *ctx, void *nccl_comm, int nranks, int rank);
+int rt_comm_destroy(rt_context *ctx);
+int rt_comm_rank(const rt_context *ctx);
+int rt_comm_size(const rt_context *ctx);
+int rt_group_start(void);
+int rt_group_end(void);
+/* sum of `count` floats over the ranks, in place, result on `root` */
+int rt_reduce(rt_context *ctx, float *accum_dev, size_t count, int root);
+/* sum over the ranks of accum_dev[nranks * slice_count]; rank r receives elements [r * slice_count, (r+1) * slice_count) —
+ * every rank then finalises (and formats, and copies out) its own slice of the frame in parallel */
+int rt_reduce_scatter(rt_context *ctx, const float *accum_dev, float *slice_dev, size_t slice_count);
+int rt_broadcast(rt_context *ctx, void *dev, size_t bytes, int root);
 
 /* ---- measurement: dense FP32 FFMA rate of this GPU (2 flop per FFMA), the denominator of the FP32 roofline -------- */
 int rt_ffma_peak(rt_context *ctx, float *tflops, float *kernel_ms);

@@ -60,6 +60,28 @@ __global__ void rto_camera_dump(camera **cam, float *out22) {
     out22[21] = float(c.lens_radius);
 }
 
+/* The body of the reference's render kernel (main.cu:96-117) for a LIST of pixels instead of the whole frame: same device
+ * functions (camera::get_ray, color), same per-pixel stream (the state render_init left in rand_state[pixel_index]), same
+ * accumulation; the running linear sum `col` is written out after every sample, so a frame of the full-size configuration can
+ * be compared pixel by pixel and sample by sample without tracing all of it.  Test infrastructure, like the rest of this file. */
+__global__ void rto_render_pixels(const int *pix_ij, int npix, int max_x, int max_y, int ns, camera **cam, hitable **world,
+                                  curandState *rand_state, Octree *d_octree, sphere (*d_list)[NUM_SPHERES], float *prefix) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= npix) return;
+    int i = pix_ij[2 * k], j = pix_ij[2 * k + 1];
+    if (i < 0 || j < 0 || i >= max_x || j >= max_y) return;
+    int pixel_index = j * max_x + i;
+    curandState local_rand_state = rand_state[pixel_index];
+    vec3 col(0, 0, 0);
+    for (int s = 0; s < ns; s++) {
+        real_t u = real_t(i + curand_uniform(&local_rand_state)) / real_t(max_x);
+        real_t v = real_t(j + curand_uniform(&local_rand_state)) / real_t(max_y);
+        ray r = (*cam)->get_ray(u, v, &local_rand_state);
+        col += color(r, world, &local_rand_state, d_octree, d_list);
+        for (int c = 0; c < 3; c++) prefix[((size_t)k * ns + s) * 3 + c] = float(col[c]);
+    }
+}
+
 static void dump(const char *path, const void *p, size_t bytes) {
     FILE *f = fopen(path, "wb");
     if (!f || fwrite(p, 1, bytes, f) != bytes) { fprintf(stderr, "cannot write %s\n", path); exit(2); }
@@ -76,7 +98,7 @@ int main(int argc, char **argv) {
         if (*q == ',') q++;
     }
     if (ns_count < 1 || ns_list[0] < 1) { fprintf(stderr, "bad ns list\n"); return 1; }
-    const char *fb_path = 0, *sph_path = 0, *cam_path = 0, *oct_path = 0;
+    const char *fb_path = 0, *sph_path = 0, *cam_path = 0, *oct_path = 0, *pix_path = 0, *pix_out = 0;
     int reps = 1;
     for (int a = 4; a + 1 < argc; a += 2) {
         if (!strcmp(argv[a], "--fb")) fb_path = argv[a + 1];
@@ -84,6 +106,8 @@ int main(int argc, char **argv) {
         else if (!strcmp(argv[a], "--camera")) cam_path = argv[a + 1];
         else if (!strcmp(argv[a], "--octree")) oct_path = argv[a + 1];
         else if (!strcmp(argv[a], "--reps")) reps = atoi(argv[a + 1]);
+        else if (!strcmp(argv[a], "--pixels")) pix_path = argv[a + 1];       /* text file: "i j" per line */
+        else if (!strcmp(argv[a], "--pixels-out")) pix_out = argv[a + 1];    /* npix * ns * 3 floats: running sums per sample */
     }
     const int tx = 8, ty = 8;                                     /* main.cu:351-352 */
     const size_t num_pixels = (size_t)nx * ny;
@@ -136,6 +160,38 @@ int main(int argc, char **argv) {
 #ifdef USE_FP16
     fp16 = 1;
 #endif
+    if (pix_path && pix_out) {      /* pixel-list mode: no full frame is traced */
+        FILE *pf = fopen(pix_path, "r");
+        if (!pf) { fprintf(stderr, "cannot read %s\n", pix_path); return 2; }
+        int cap = 1024, npix = 0, *h_ij = (int *)malloc(sizeof(int) * 2 * cap);
+        while (fscanf(pf, "%d %d", &h_ij[2 * npix], &h_ij[2 * npix + 1]) == 2) {
+            if (++npix == cap) { cap *= 2; h_ij = (int *)realloc(h_ij, sizeof(int) * 2 * cap); }
+        }
+        fclose(pf);
+        const int ns = ns_list[0];
+        int *d_ij;
+        float *d_prefix;
+        checkCudaErrors(cudaMalloc(&d_ij, sizeof(int) * 2 * (npix + 1)));
+        checkCudaErrors(cudaMalloc(&d_prefix, sizeof(float) * 3 * (size_t)ns * (npix + 1)));
+        checkCudaErrors(cudaMemset(d_prefix, 0, sizeof(float) * 3 * (size_t)ns * (npix + 1)));
+        checkCudaErrors(cudaMemcpy(d_ij, h_ij, sizeof(int) * 2 * npix, cudaMemcpyHostToDevice));
+        render_init<<<blocks, threads>>>(nx, ny, d_rand_state);
+        checkCudaErrors(cudaDeviceSynchronize());
+        cudaEventRecord(e0);
+        rto_render_pixels<<<(npix + 31) / 32, 32>>>(d_ij, npix, nx, ny, ns, d_camera, d_world, d_rand_state, d_octree, d_list, d_prefix);
+        cudaEventRecord(e1);
+        checkCudaErrors(cudaGetLastError());
+        checkCudaErrors(cudaDeviceSynchronize());
+        cudaEventElapsedTime(&ms_render, e0, e1);
+        float *h_prefix = (float *)malloc(sizeof(float) * 3 * (size_t)ns * (npix + 1));
+        checkCudaErrors(cudaMemcpy(h_prefix, d_prefix, sizeof(float) * 3 * (size_t)ns * npix, cudaMemcpyDeviceToHost));
+        dump(pix_out, h_prefix, sizeof(float) * 3 * (size_t)ns * npix);
+        printf("{\"impl\": \"ref_cuda\", \"mode\": \"pixels\", \"n\": %d, \"spl\": %d, \"use_octree\": %d, \"fp16\": %d, \"nx\": %d, \"ny\": %d, "
+               "\"ns\": %d, \"pixels\": %d, \"render_ms\": %.3f, \"create_world_ms\": %.3f}\n",
+               NUM_SPHERES, SPHERES_PER_LEAF, use_octree, fp16, nx, ny, ns, npix, ms_render, ms_world);
+        ns_count = 0;
+        free(h_prefix); free(h_ij); cudaFree(d_ij); cudaFree(d_prefix);
+    }
     for (int k = 0; k < ns_count; k++) {
     const int ns = ns_list[k];
     float best_render = 1e30f, best_init = 1e30f, sum_render = 0;

@@ -206,8 +206,18 @@ static int SUF(scatter)(const rto_sphere *s, v3 d_in, v3 p, v3 n, v3 *atten, v3 
         }
         if (SUF(refract)(d_in, outward, ni_over_nt, &refracted))
             reflect_prob = SUF(schlick)(cosine, ref_idx);
-        else
+        else {
             reflect_prob = 1.0f;
+#if RTO_FMA
+            /* material.h:88 leaves `refracted` UNINITIALISED and material.h:109 reads it when total internal reflection meets
+             * curand_uniform == 1.0 (the draw is in (0, 1]; p ~ 3e-8 per such event; BASELINE config 3 at full size has one:
+             * pixel (2070, 687), sample 36).  What the reference's sm_100 build then uses is whatever its registers hold — read off
+             * the SASS of `render` (cuobjdump, nvcc 12.9 -O3 -arch=sm_100; dielectric::scatter at 0x4f10, the select at 0x6c90):
+             * refracted = (R16, R2, R17) = (v.y, v.z, unit_vector(v).y), v = r_in.direction().  The host build of the reference
+             * leaves other garbage there; this oracle's host mode keeps zero. */
+            refracted = V3(d_in.y, d_in.z, d_in.y / sqrtf(SUF(dot3)(d_in, d_in)));
+#endif
+        }
         if (xorwow_uniform(rng) < reflect_prob) *d_out = reflected;
         else *d_out = refracted;
         return 1;

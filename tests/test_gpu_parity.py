@@ -506,24 +506,34 @@ def test_pooled_and_plain_kernels_agree_at_4k(rt):
     assert torch.equal(fbs[0][0], fbs[1][0]) and torch.equal(fbs[0][0], fbs[2][0]) and fbs[0][1] == fbs[1][1] == fbs[2][1]
 
 
-def test_config3_full_size_nan_pixel_and_its_neighbours_match_the_oracle(rt, O):
-    """BASELINE config 3 at FULL size (3840x2160, 64 spp, 1.04e9 rays): the frame has exactly one non-finite pixel —
-    (i, j) = (2070, 687) turns NaN at sample 36, where a degenerate scatter direction reaches unit_vector — and the
-    oracle, i.e. the reference's arithmetic, produces the same NaN; the finite pixels of its row neighbourhood are bit-identical."""
+def test_config3_full_size_frame_is_the_reference_cuda_frame(rt, pkg, O, golden_dir):
+    """BASELINE config 3 at FULL size (3840x2160, 64 spp, 1.04e9 rays) against the frame the reference's own CUDA build wrote
+    on a B200 (tests/golden/gen_ref_cuda_full.sh; 178 s there): sha256 of the float framebuffer and of the integer PPM values,
+    and the committed 1/16 x 1/16 subsample pixel by pixel.  Two things this pins that small frames never reach:
+    * exact ties between DIFFERENT spheres (bit-identical t; ~170 pixels of this frame): the reference keeps the sphere with the
+      smaller index (same level-3 cell, leaf lists in ascending order);
+    * pixel (2070, 687), sample 36: total internal reflection meets curand_uniform == 1.0, the reference reads its uninitialised
+      `refracted` (material.h:88,109) — the value its sm_100 build has there is reproduced (rt_shade.cuh), so the pixel is finite as
+      in the reference's frame (with zeros it would be NaN).  The oracle's window around it agrees bit for bit."""
+    import sys
     import torch
+    sys.path.insert(0, golden_dir)
+    from digest_frame import digest, subsample16
+    man = json.load(open(os.path.join(golden_dir, "ref_cuda", "manifest_full.json")))["frames"]["C3_3840x2160x64"]
     nx, ny, ns, n, spl = 3840, 2160, 64, 100000, 300
     rt.create_world(n, 0.1)
     rt.build_octree(spl)
     fb = torch.empty((ny, nx, 3), dtype=torch.float32, device="cuda")
     st = rt.render_device(rt.args(nx, ny, ns, True), fb.data_ptr())
-    bad = torch.nonzero(~torch.isfinite(fb).all(dim=2)).tolist()
-    assert bad == [[687, 2070]] and st["paths"] == nx * ny * ns
+    frame = fb.cpu().numpy()
+    assert torch.isfinite(fb).all() and st["paths"] == nx * ny * ns
+    gsub = np.load(os.path.join(golden_dir, "ref_cuda", man["subsample"]))
+    assert np.array_equal(subsample16(frame).view(np.uint32), gsub.view(np.uint32))
+    d = digest(frame)
+    assert d["sha256_raw"] == man["sha256_raw"], (d, st)
+    assert d["sha256_i32_ppm_order"] == man["sha256_i32_ppm_order"]
     sph, _ = O.create_world(n)
     blob, _ = O.build_octree(sph, spl)
     i0, i1, j = 2064, 2077, 687
     ref, _, _ = O.render(sph, O.camera(nx, ny, O.ARITH_DEVICE), O.make_params(nx, ny, ns, True, spl, O.ARITH_DEVICE, window=(i0, i1, j, j + 1)), blob)
-    got = fb[j, i0:i1].cpu().numpy()
-    want = ref[j, i0:i1]
-    nan = np.isnan(want)
-    assert np.array_equal(np.isnan(got), nan) and nan[2070 - i0].all() and nan.sum() == 3       # (NaN payload bits differ CPU/GPU)
-    assert np.array_equal(got.view(np.uint32)[~nan], want.view(np.uint32)[~nan])
+    assert np.array_equal(frame[j, i0:i1].view(np.uint32), ref[j, i0:i1].view(np.uint32))
