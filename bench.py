@@ -34,10 +34,12 @@ CONFIGS = {
 FP16_CONFIGS = {"C4"}
 # CPU sample of the workload: every CPU_STRIDE-th pixel in x and y of the full frame, all ns samples
 CPU_STRIDE = {"C1": (4, 4), "C2": (2, 2), "C3": (16, 16), "C4": (96, 96), "C5": (96, 96)}
-# reference CUDA build on the same B200 (oracle/_ref/ref_cuda_*, measured with tests/golden/gen_ref_cuda.sh);
-# kept next to the number for context — the driver computes its own ratios
-REF_CUDA_MS = {"C1": 42.19, "C2": 325.12, "C3": 177654.47,
-               "C4": 16 * 3489.82}        # C4: measured at 4 spp (3 489.8 ms), scaled to 64 spp
+# The reference's own CUDA build (oracle/_ref/ref_cuda_*: its kernels recompiled for sm_100).  `ref_cuda_leg` runs it LIVE on
+# this box at REF_CUDA_LIVE_SPP samples (its create_world alone takes ~2 minutes at 100 k spheres: one thread device-news every
+# material); the full 64-spp frame takes 3 minutes more, so that number is quoted from the committed record of
+# tests/golden/gen_ref_cuda_full.sh (tests/golden/ref_cuda/manifest_full.json: render time per sample count, clocks under load).
+REF_CUDA_BIN = {"C3": "ref_cuda_n100000_oct_spl300", "C4": "ref_cuda_n100000_oct_spl300_fp16"}
+REF_CUDA_LIVE_SPP = 4
 
 
 class ClockSampler(threading.Thread):
@@ -111,6 +113,44 @@ def cpu_reference_sample(cfg: str, threads: int = 0):
     return ctr["rays"] / dt / 1e6, {"cores": cores, "kind": kind, "sample": sample, "seconds": dt, "rays": ctr["rays"]}
 
 
+def ref_cuda_leg(cfg: str, rays_at_live_spp: float, rays_full: float, budget_s: float):
+    """Mrays/s of the reference's CUDA build on this box.  Live: REF_CUDA_LIVE_SPP samples per pixel of the same frame (clocks
+    sampled while it runs).  Recorded: the committed timing of the full sample count.  Rays are counted by this repo's kernel
+    for the same frame and sample count (identical sample chains, so identical ray counts)."""
+    n, spl, octree, nx, ny, ns, _ = CONFIGS[cfg]
+    out = {"binary": "oracle/_ref/" + REF_CUDA_BIN.get(cfg, "")}
+    try:
+        man = json.load(open(os.path.join(ROOT, "tests", "golden", "ref_cuda", "manifest_full.json")))["timing"].get(cfg)
+        if man:
+            full = [r for r in man["runs"] if r["ns"] == ns]
+            out["recorded"] = {"runs": man["runs"], "clocks": man["clocks"], "source": "tests/golden/ref_cuda/manifest_full.json"}
+            if full and rays_full:
+                out["recorded"]["ms_per_frame"] = full[0]["render_ms"]
+                out["recorded"]["mrays_s"] = rays_full / full[0]["render_ms"] / 1e3
+    except Exception as e:
+        out["recorded"] = {"error": str(e)}
+    exe = os.path.join(ROOT, "oracle", "_ref", REF_CUDA_BIN.get(cfg, "missing"))
+    if not os.path.exists(exe):
+        out["live"] = {"error": "binary not built (make -C oracle ref_cuda needs /root/reference)"}
+        return out
+    if budget_s < 150:
+        out["live"] = {"skipped": f"only {budget_s:.0f} s of the bench's time budget left; the run needs ~130 s"}
+        return out
+    sampler = ClockSampler(int(os.environ.get("LOCAL_RANK", "0")))
+    sampler.start()
+    try:
+        r = subprocess.run([exe, str(nx), str(ny), str(REF_CUDA_LIVE_SPP)], capture_output=True, text=True, timeout=min(budget_s, 240))
+        rec = json.loads(r.stdout.strip().splitlines()[-1])
+        out["live"] = {"spp": REF_CUDA_LIVE_SPP, "render_ms": rec["render_ms"], "create_world_ms": rec["create_world_ms"],
+                       "mrays_s": rays_at_live_spp / rec["render_ms"] / 1e3 if rays_at_live_spp else None,
+                       "note": "render_init + render of the reference (main.cu:424-429), cudaEvent-timed; its per-sample cost grows with "
+                               "the sample count (see recorded.runs), so the 64-spp ratio is larger than this one"}
+    except Exception as e:
+        out["live"] = {"error": str(e)[:200]}
+    out["live_clocks"] = sampler.stop()
+    return out
+
+
 def run_reference_arm(args):
     """--impl reference: the reference's CPU implementation of the path, all host threads, bounded sample per step."""
     rank = int(os.environ.get("RANK", "0"))
@@ -137,13 +177,24 @@ def run_reference_arm(args):
     return 0
 
 
-def measure_e2e(pkg, mg, rt, torch, dist, dev, rank, world, mode, prec, n, spl, octree, nx, ny, ns, accum, fb, steps):
+def measure_e2e(pkg, mg, rt, torch, dist, dev, rank, world, mode, prec, n, spl, octree, nx, ny, ns, frame, fb, steps):
     """The same metric through the public API with HOST buffers, all N ranks taking part: host->device copy of the sphere
-    descriptors, GPU octree build, (sharded) render, the reduce, device->host copy of the frame into pinned memory on
-    rank 0.  Wall clock around barriers; max over ranks by construction (rank 0 waits for the reduce)."""
+    descriptors, GPU octree build, (sharded) render, the reduce-scatter, /ns + sqrt of each rank's slice and its device->host copy
+    into ONE pinned host frame (N = 1: rt_render_to_host; N > 1: a POSIX shared-memory frame every rank maps and page-locks, so the
+    N slices cross PCIe in parallel).  Wall clock around barriers: max over ranks by construction."""
     import ctypes as C
     spheres = rt.spheres()
-    host_fb = torch.empty((ny, nx, 3), dtype=torch.float32).pin_memory() if rank == 0 else None
+    host, host_fb = None, None
+    if world == 1:
+        host_fb = torch.empty((ny, nx, 3), dtype=torch.float32).pin_memory()
+    else:
+        name = f"rt_b200_frame_{os.environ.get('MASTER_PORT', '0')}_{os.getppid()}"
+        if rank == 0:
+            host = mg.SharedHostFrame(name, nx * ny * 12, True, torch)
+        dist.barrier()
+        if rank != 0:
+            host = mg.SharedHostFrame(name, nx * ny * 12, False, torch)
+        frame.attach_host(host)
     rays, secs = 0.0, 0.0
     for k in range(steps + 1):
         if world > 1:
@@ -159,9 +210,7 @@ def measure_e2e(pkg, mg, rt, torch, dist, dev, rank, world, mode, prec, n, spl, 
             rt._ck(rt.L.rt_render_to_host(rt._ctx, C.byref(a), C.c_void_p(host_fb.data_ptr()), C.byref(stt)), "rt_render_to_host")
             r = float(stt.rays)
         else:
-            st = mg.render_sharded(rt, accum, fb, nx, ny, ns, bool(octree), rank, world, mode, dist, want_stats=True)
-            if rank == 0:
-                host_fb.copy_(fb, non_blocking=False)
+            st = mg.render_sharded(rt, frame, ns, bool(octree), mode, dist, want_stats=True, to_host=True)
             r = float(st["rays"])
         torch.cuda.synchronize()
         if world > 1:
@@ -174,9 +223,30 @@ def measure_e2e(pkg, mg, rt, torch, dist, dev, rank, world, mode, prec, n, spl, 
         if k > 0:                      # the first pass warms the allocations
             rays += r
             secs += dt
+    check = None
+    if world > 1:
+        # what the N-GPU run left in the host frame, against the 1-GPU frame of the same config rendered on rank 0
+        if rank == 0:
+            got = host.array.reshape(ny, nx, 3).copy()
+            one = torch.empty((ny, nx, 3), dtype=torch.float32, device=dev)
+            rt.render_device(rt.args(nx, ny, ns, octree, precision=prec), one.data_ptr())
+            ref = one.cpu().numpy()
+            import numpy as np
+            fin = np.isfinite(got).all(axis=2) & np.isfinite(ref).all(axis=2)
+            mse = float(((np.clip(got[fin], 0, 1) - np.clip(ref[fin], 0, 1)) ** 2).mean())
+            check = {"sharding": "tiles" if mode == pkg.SHARD_TILES else "spp",
+                     "identical_to_1gpu_frame": bool(np.array_equal(got.view(np.uint32), ref.view(np.uint32))),
+                     "pixels_identical": float((got.view(np.uint32) == ref.view(np.uint32)).all(axis=2).mean()),
+                     "mean_radiance": float(got[fin].mean()), "mean_radiance_1gpu": float(ref[fin].mean()),
+                     "psnr_db_vs_1gpu": None if mse == 0 else float(10 * np.log10(1.0 / mse)),
+                     "expect": "tiles: bit-identical; spp: same mean radiance, PSNR bounded by Monte-Carlo noise (independent streams)"}
+        dist.barrier()
+        frame.attach_host(None)
+        host.close()
     return {"value": rays / secs / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": int(n * 36) * world,
-            "d2h_bytes_per_step": int(nx * ny * 12 + 40), "ms_per_step": 1e3 * secs / steps,
-            "includes": "per rank: scene upload + GPU octree build + render of its shard; one reduce; frame copy to pinned host memory on rank 0"}
+            "d2h_bytes_per_step": int(nx * ny * 12 + 40), "ms_per_step": 1e3 * secs / steps, "frame_check": check,
+            "includes": "per rank: scene upload + GPU octree build + render of its shard; one reduce-scatter; /ns + sqrt and the copy of every "
+                        "rank's slice into one pinned host frame"}
 
 
 def main():
@@ -188,6 +258,9 @@ def main():
     ap.add_argument("--config", default="C3", choices=sorted(CONFIGS))
     ap.add_argument("--shard", default="spp", choices=["tiles", "spp"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ref-cuda", action="store_true", help="skip the live run of the reference's CUDA build (~130 s, N = 1 only)")
+    ap.add_argument("--time-budget", type=float, default=330.0, help="seconds the whole bench may take; the reference-CUDA leg is skipped "
+                                                                       "when less than 150 s of it are left")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -221,15 +294,15 @@ def main():
     rt.create_world(n, 0.1, prec)
     bst = rt.build_octree(spl, prec) if octree else None
     rt.set_camera(nx, ny)
-    accum = torch.empty((ny, nx, 3), dtype=torch.float32, device=dev)
-    fb = torch.empty_like(accum) if rank == 0 else accum
+    frame = mg.ShardedFrame(torch, dev, nx, ny, rank, world) if world > 1 else None
+    fb = torch.empty((ny, nx, 3), dtype=torch.float32, device=dev) if world == 1 else None
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
     mode = pkg.SHARD_TILES if args.shard == "tiles" else pkg.SHARD_SPP
 
     def step(want_stats):
         if world == 1:
             return rt.render_device(rt.args(nx, ny, ns, octree, precision=prec), fb.data_ptr(), want_stats=want_stats)
-        return mg.render_sharded(rt, accum, fb, nx, ny, ns, bool(octree), rank, world, mode, dist, want_stats=want_stats)
+        return mg.render_sharded(rt, frame, ns, bool(octree), mode, dist, want_stats=want_stats)
 
     def barrier():
         if world > 1:
@@ -243,7 +316,8 @@ def main():
     if rank == 0:
         sampler.start()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    rays_local, kernel_ms = 0, []
+    rays_local, kernel_ms, kernel_name = 0, [], None
+    t_bench0 = time.perf_counter()
     barrier()
     for k in range(args.steps):
         flush.zero_()                                  # L2 flush between timed iterations (untimed)
@@ -252,6 +326,7 @@ def main():
         ev[k][1].record(stream)
         rays_local += st["rays"]
         kernel_ms.append(st["kernel_ms"])
+        kernel_name = st["kernel"]
     barrier()
     clocks = sampler.stop() if rank == 0 else None
     step_ms = [a.elapsed_time(b) for a, b in ev]
@@ -264,14 +339,14 @@ def main():
         total_ms, total_rays = float(tmax[0]), float(tsum[1])
     else:
         total_ms, total_rays = float(t[0]), float(t[1])
-    e2e_result = measure_e2e(pkg, mg, rt, torch, dist, dev, rank, world, mode, prec, n, spl, octree, nx, ny, ns, accum, fb, args.steps)
+    e2e_result = measure_e2e(pkg, mg, rt, torch, dist, dev, rank, world, mode, prec, n, spl, octree, nx, ny, ns, frame, fb, args.steps)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return 0
 
     value = total_rays / (total_ms * 1e-3) / 1e6
-    launches_per_step = 1 if world == 1 else 2          # render (+ finalize on rank 0); the reduce is NCCL's kernel
+    launches_per_step = 1 if world == 1 else 2          # render + finalize of the rank's slice; the reduce-scatter is NCCL's kernel
     line = {"metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f16" if prec == pkg.PREC_FP16 else "f32", "data": "synthetic",
@@ -281,14 +356,13 @@ def main():
                            "spp: rank g traces ns/N samples of every pixel from its own XORWOW streams (g = 0: the reference's); a valid "
                            "frame of the same quality, not bit-identical to the 1-GPU frame.  --shard tiles is bit-identical (tests) but "
                            "keeps every pixel's whole sample chain on one GPU, so the longest chain bounds the frame time"),
-                       "collective": None if world == 1 else "one NCCL reduce-sum of the linear radiance buffer per frame",
+                       "collective": None if world == 1 else "one NCCL reduce-scatter (sum) of the linear radiance buffer per frame; every rank "
+                                                             "finalises its own slice",
                        "l2": "flushed between timed steps (256 MiB memset, untimed); each step times one whole frame",
                        "rays_per_frame": total_rays / args.steps, "octree_build_ms": bst["build_ms"] if bst else None},
             "clocks": clocks, "gpu_launches": launches_per_step * args.steps,
             "kernel_ms_per_step": sum(kernel_ms) / len(kernel_ms)}
-    if args.config in REF_CUDA_MS:
-        line["ref_cuda_build_same_b200"] = {"ms_per_frame": REF_CUDA_MS[args.config],
-                                            "source": "tests/golden/ref_cuda/manifest.json (oracle/_ref/ref_cuda_*, sm_100 recompile)"}
+    line["kernel"] = kernel_name
 
     # ---- end to end through the public API with HOST buffers: every rank uploads the sphere descriptors and rebuilds the
     #      octree, renders its shard, the shards are reduced, rank 0 copies the frame to pinned host memory ----
@@ -313,7 +387,7 @@ def main():
         if os.path.exists(pj):
             traffic = json.load(open(pj)).get(args.config, {}).get("dram_bytes_per_launch")
         line["roofline"] = {"bound": "fp32", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                            "traffic": traffic, "kernel": "k_render_pool<64,6>" if (octree and n >= 200000) else "k_render", "flop_per_ray": flop_per_ray,
+                            "traffic": traffic, "kernel": kernel_name, "flop_per_ray": flop_per_ray,
                             "sphere_tests_per_ray": S, "node_tests_per_ray": B,
                             "peak_source": "measured here: dense FFMA microbenchmark (rt_ffma_peak); MEASURED_PEAKS.json has no FP32 figure",
                             "note": "FP32 issue is the bounding unit (SURVEY §8d); HBM traffic is the 12 B/pixel frame only"}
@@ -352,6 +426,15 @@ def main():
                                     "sample": info["sample"], "seconds": info["seconds"]}
         except Exception as e:
             line["cpu_baseline"] = {"error": str(e)}
+    # ---- the bar north_star sets: the reference's own CUDA build on this box ----
+    if world == 1 and args.config in REF_CUDA_BIN and not args.no_ref_cuda:
+        try:
+            probe = torch.empty((ny, nx, 3), dtype=torch.float32, device=dev)
+            r4 = rt.render_device(rt.args(nx, ny, REF_CUDA_LIVE_SPP, octree, precision=prec), probe.data_ptr())["rays"]
+            del probe
+            line["ref_cuda"] = ref_cuda_leg(args.config, float(r4), total_rays / args.steps, args.time_budget - (time.perf_counter() - t_bench0))
+        except Exception as e:
+            line["ref_cuda"] = {"error": str(e)[:200]}
     print(json.dumps(line), flush=True)
     rt.close()
     if world > 1:

@@ -24,7 +24,7 @@
 //   sphere::hit(t_max) accepts root1 if t_min < root1 < t_max, else root2 if t_min < root2 < t_max; root2 >= root1 (the
 //   rounding of (-b -+ sq)/a is monotone, a > 0), hence  hit(t_max) = [acc < t_max] with acc = root1 if root1 > t_min,
 //   else root2 if root2 > t_min — exactly what sphere_test(.., t_max = FLT_MAX, ..) returns.
-// Ties (two DIFFERENT spheres with bit-identical t) go to the smaller sphere index, independent of scheduling.
+// Ties (two DIFFERENT spheres with bit-identical t) are detected here and ranked in the reference's test order by finish_hit.
 #pragma once
 
 namespace coop {
@@ -36,7 +36,8 @@ constexpr int kRing = 96;                        // >= 31 (left over) + 64 (one 
 struct __align__(16) RayMeta {
     int koff;        // first reference of the lane's current voxel - ITEMS * its offset in the flat item list
     int kend;        // one past the last reference of that voxel
-    float bound;     // t of best[] (what the pre-filter and the walk prune against)
+    float bound;     // what the pre-filter and the walk prune against: an upper bound of the ray's closest hit — the exact t of
+                     // best_t, or less: the certain-hit bound of a candidate still waiting in the ring (maybe_hit_ub)
     int pad;
 };
 
@@ -44,22 +45,23 @@ struct __align__(16) WarpShared {
     float4 ro[32];                   // ray origin, a = dot(d, d)
     float4 rd[32];                   // ray direction, 1/a (approximate: pre-filter only)
     RayMeta meta[32];
-    unsigned long long best[32];     // closest hit so far: float bits of t << 32 | sphere index (0xffffffff: none)
+    uint32_t best_t[32];             // closest hit so far: float bits of t (positive floats order like their bits) ...
+    uint32_t best_i[32];             // ... and its sphere index (0xffffffff: none); provisional among equal t (the smallest seen)
+    uint32_t tie[32];                // 1: two DIFFERENT spheres share best_t — finish_hit ranks them in the reference's order
     uint32_t slot[32];               // chunk position of a segment start -> owner lane
     uint2 ring[kRing];               // {owner lane, reference}
 };
 
-__device__ __forceinline__ unsigned long long pack_hit(const float t, const uint32_t idx) {
-    return (unsigned long long)__float_as_uint(t) << 32 | idx;
-}
-
-// Exact test of up to 32 queued candidates, one per lane, folded into the owners' records.  Entries [first, first + n).
-// The lanes whose candidates belong to the same ray find each other with MATCH.ANY and reduce (t, index) with two REDUX.MIN;
-// one lane per ray then updates the record with plain loads and stores — no shared-memory atomics (a 64-bit atomicMin is a
-// compare-and-swap loop in shared memory: 7.6 % of the stall samples of the first version of this kernel, profiles r02c).
-__device__ __forceinline__ void drain(WarpShared &ws, const SceneView &sc, const TreeView &tv, const unsigned lane, const int first, const int n) {
-    uint32_t owner = 0x100u | lane;          // a lane without a hit is a group of its own
-    uint32_t tb = 0xffffffffu, idx = 0xffffffffu;
+// Exact test of up to 32 queued candidates, one per lane, folded into the owners' (t, index) records: minimum t, and among
+// bit-identical t the smallest sphere index.  Two native 32-bit shared-memory atomics (ATOMS.MIN) instead of one 64-bit
+// atomicMin, which is a compare-and-swap loop in shared memory (7.6 % of the stall samples of the first version of this
+// kernel, profiles r02c); MATCH.ANY + REDUX per owner group was tried and is far slower (it serialises over the distinct
+// owners: 34.0 instead of 21.9 ms per 8-spp frame).  Every lane is also the OWNER of ray `lane`: between the two atomics it resets the
+// index of its own record if this drain lowered its t.  Entries [first, first + n).  Returns the owner's new t.
+__device__ __forceinline__ float drain(WarpShared &ws, const SceneView &sc, const TreeView &tv, const unsigned lane, const int first, const int n) {
+    const uint32_t before = ws.best_t[lane];
+    __syncwarp();                                               // (no lane's atomic may overtake another lane's read of `before`)
+    uint32_t owner = 0, tb = 0xffffffffu, idx = 0xffffffffu;
     if ((int)lane < n) {
         const uint2 e = ws.ring[first + (int)lane];
         const float4 ro = ws.ro[e.x], rd = ws.rd[e.x];
@@ -71,23 +73,23 @@ __device__ __forceinline__ void drain(WarpShared &ws, const SceneView &sc, const
             idx = pro ? __ldg(tv.prolog + k) : __ldg(tv.grid.refs + k);
             tb = __float_as_uint(t);
             owner = e.x;
+            atomicMin(&ws.best_t[owner], tb);
         }
     }
-    const unsigned peers = __match_any_sync(kFull, owner);
-    const uint32_t tmin = __reduce_min_sync(peers, tb);
-    const uint32_t imin = __reduce_min_sync(peers, tb == tmin ? idx : 0xffffffffu);
-    if (tb != 0xffffffffu && (int)lane == __ffs(peers) - 1) {
-        const unsigned long long key = (unsigned long long)tmin << 32 | imin;
-        if (key < ws.best[owner]) ws.best[owner] = key;
+    __syncwarp();
+    const uint32_t now = ws.best_t[lane];
+    if (now != before) {                                        // a closer hit: whatever was recorded belongs to the old t
+        ws.best_i[lane] = 0xffffffffu;
+        ws.tie[lane] = 0u;
     }
     __syncwarp();
-}
-
-// after a drain: every lane re-reads its own ray's closest hit into the record the pre-filter prunes against
-__device__ __forceinline__ float refresh_bound(WarpShared &ws, const unsigned lane) {
-    const float t = __uint_as_float((uint32_t)(ws.best[lane] >> 32));
-    ws.meta[lane].bound = t;
-    return t;
+    if (tb != 0xffffffffu && ws.best_t[owner] == tb) {
+        const uint32_t old = atomicMin(&ws.best_i[owner], idx);
+        if (old != 0xffffffffu && old != idx) ws.tie[owner] = 1u;       // same root, another sphere (rt_trace.cuh "Ties")
+    }
+    ws.meta[lane].bound = fminf(ws.meta[lane].bound, __uint_as_float(now));     // (the bound may already be lower: certain hits not drained yet)
+    __syncwarp();
+    return __uint_as_float(now);
 }
 
 // Append the lanes with pass0 / pass1 (two candidates per lane: references ref and ref + 1) to the ring; drains while 32 or
@@ -107,18 +109,17 @@ __device__ __forceinline__ void push2(WarpShared &ws, const SceneView &sc, const
             drain(ws, sc, tv, lane, count - 32, 32);      // the newest 32; what is left stays at the front
             count -= 32;
         } while (count >= 32);
-        refresh_bound(ws, lane);
-        __syncwarp();
     }
 }
 
 // Closest hit for the rays of the whole warp (lane `has` a ray or idles along).  Every lane of the warp must call.
 // ITEMS = candidates per lane and chunk step (1 or 2: with 2 a lane takes two consecutive references of one voxel list,
 // so the owner lookup and the ray fetch are paid once per pair and two geometry loads are in flight).
-// Returns the minimum over ALL candidates (the visibility rule is applied by the caller, as in trace_tree).
+// Returns the minimum over ALL candidates and whether two different spheres tied for it (finish_hit settles ties and the
+// visibility rule, as in trace_tree).
 template <int ITEMS>
 __device__ __forceinline__ Hit coop_trace(WarpShared &ws, const SceneView &sc, const TreeView &tv, const unsigned lane, const bool has,
-                                          const vec3f o, const vec3f d, TraceCounters &tc) {
+                                          const vec3f o, const vec3f d, TraceCounters &tc, bool &tie) {
     const float a = dot3(d, d);
     const float ia = rcp_trav(a);
     __syncwarp();
@@ -132,7 +133,9 @@ __device__ __forceinline__ Hit coop_trace(WarpShared &ws, const SceneView &sc, c
             RT_COUNT(sphere_tests);
             if (sphere_test(__ldg(sc.geom), o, d, a, kTMax, t)) { best_t = t; idx = 0u; }
         }
-        ws.best[lane] = pack_hit(best_t, idx);
+        ws.best_t[lane] = __float_as_uint(best_t);
+        ws.best_i[lane] = idx;
+        ws.tie[lane] = 0u;
         ws.meta[lane].bound = best_t;
     }
     __syncwarp();
@@ -140,13 +143,12 @@ __device__ __forceinline__ Hit coop_trace(WarpShared &ws, const SceneView &sc, c
     for (int k = 1; k < tv.nprolog; k++) {   // big spheres: one pre-filter per lane, exact tests through the ring
         const float4 s = __ldg(tv.prolog_geom + k);
         if (has) RT_COUNT(sphere_tests);
-        push2(ws, sc, tv, lane, has && maybe_hit(s, o, d, a, ia, ws.meta[lane].bound), false, lane, kPrologFlag | (uint32_t)k, count);
+        float ub;
+        const bool pass = has && maybe_hit_ub(s, o, d, a, ia, ws.meta[lane].bound, ub);
+        if (pass && ub < ws.meta[lane].bound) ws.meta[lane].bound = ub;        // (the lane's own record: no other lane touches it here)
+        push2(ws, sc, tv, lane, pass, false, lane, kPrologFlag | (uint32_t)k, count);
     }
-    if (count) {
-        drain(ws, sc, tv, lane, 0, count);
-        count = 0;
-    }
-    best_t = refresh_bound(ws, lane);
+    best_t = ws.meta[lane].bound;           // from here on `best_t` is the pruning bound; exact values live in ws.best_t / best_i
 
     // ---- 3D-DDA set-up, per lane (as trace_walk) ----
     const GridView &g = tv.grid;
@@ -231,29 +233,36 @@ __device__ __forceinline__ Hit coop_trace(WarpShared &ws, const SceneView &sc, c
             if (valid) {
                 const vec3f oo = mk(ro.x, ro.y, ro.z), dd = mk(rd.x, rd.y, rd.z);
                 const float4 s0 = __ldg(g.ref_geom + ref);
+                float ub0, ub1 = kTMax;
                 if (ITEMS == 2) {
                     const float4 s1 = __ldg(g.ref_geom + ref + 1);     // (one past a list's end is the next list's first entry, or the slack element)
                     RT_COUNT(sphere_tests);
-                    pass1 = (int)ref + 1 < mt.kend && maybe_hit(s1, oo, dd, ro.w, rd.w, mt.bound);
+                    pass1 = maybe_hit_ub(s1, oo, dd, ro.w, rd.w, mt.bound, ub1) && (int)ref + 1 < mt.kend;
+                    if (!pass1) ub1 = kTMax;
                 }
                 RT_COUNT(sphere_tests);
-                pass0 = maybe_hit(s0, oo, dd, ro.w, rd.w, mt.bound);
+                pass0 = maybe_hit_ub(s0, oo, dd, ro.w, rd.w, mt.bound, ub0);
+                // a certain hit lowers the owner's pruning bound at once (native shared-memory atomic on the float's bits: roots
+                // are positive); its exact evaluation waits in the ring until 32 candidates are queued
+                const float ub = fminf(ub0, ub1);
+                if (ub < mt.bound) atomicMin(reinterpret_cast<uint32_t *>(&ws.meta[owner].bound), __float_as_uint(ub));
             }
             __syncwarp();                       // slot[] is rewritten by the next chunk
             push2(ws, sc, tv, lane, pass0, pass1, owner, ref, count);
         }
-        if (count) {
-            drain(ws, sc, tv, lane, 0, count);
-            count = 0;
-        }
-        best_t = refresh_bound(ws, lane);
-        cnt = 0u;                               // every published range was consumed: the advance loop steps on
         __syncwarp();
+        best_t = ws.meta[lane].bound;           // no exact evaluation at the end of a round: the certain-hit bounds steer the walk
+        cnt = 0u;                               // every published range was consumed: the advance loop steps on
     }
-    const unsigned long long key = ws.best[lane];
+    while (count > 0) {                         // what is still queued: the last exact evaluations of this trace
+        const int n = count < 32 ? count : 32;
+        drain(ws, sc, tv, lane, count - n, n);
+        count -= n;
+    }
     Hit h;
-    h.t = __uint_as_float((uint32_t)(key >> 32));
-    h.idx = (int)(uint32_t)key;                 // 0xffffffff -> -1
+    h.t = __uint_as_float(ws.best_t[lane]);
+    h.idx = (int)ws.best_i[lane];               // 0xffffffff -> -1
+    tie = ws.tie[lane] != 0u;
     return h;
 }
 
@@ -261,11 +270,9 @@ __device__ __forceinline__ Hit coop_trace(WarpShared &ws, const SceneView &sc, c
 template <int ITEMS>
 __device__ __forceinline__ Hit coop_trace_tree(WarpShared &ws, const SceneView &sc, const TreeView &tv, const float *planes, const unsigned lane,
                                                const bool has, const vec3f o, const vec3f d, TraceCounters &tc) {
-    Hit h = coop_trace<ITEMS>(ws, sc, tv, lane, has, o, d, tc);
-    if (has && h.idx > 0 && tv.check_visibility && !visible_fast(tv, planes, __ldg(sc.geom + h.idx), o, d, h.t)) {
-        int last_ok = -1;
-        if (!sphere_visible(tv.vis, planes, h.idx, o, d, last_ok, tc)) h = trace_walk<true>(sc, tv, planes, o, d, tc);
-    }
+    bool tie = false;
+    Hit h = coop_trace<ITEMS>(ws, sc, tv, lane, has, o, d, tc, tie);
+    if (has) h = finish_hit(sc, tv, planes, o, d, h, tie, tc);
     return h;
 }
 

@@ -42,6 +42,7 @@ enum : int {
     NF
 };
 constexpr uint32_t kPrologBit = 0x80000000u;
+constexpr uint32_t kTieBit = 0x40000000u;    // F_HIDX of a hit (>= 0): two different spheres share the closest root; body_end ranks them
 constexpr int kChunk = 4;
 constexpr int kSticky = 4;        // TEST: chunks a lane may run back to back on one context before the warp re-schedules
 constexpr int kStickyMin = 20;    // ... as long as this many lanes are still testing
@@ -72,13 +73,6 @@ struct Ctx {
 __device__ __forceinline__ float rcp_fast(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 
 // (the conservative root pre-filter `maybe_hit` lives in rt_trace.cuh: the pixel-per-lane kernel uses it too)
-
-// the careful re-walk (winner not visible) is rare: out of line, so it costs the bodies no registers
-__device__ __noinline__ Hit rewalk_checked(const SceneView &sc, const TreeView &tv, const float *planes, const vec3f o, const vec3f d) {
-    TraceCounters tc;
-    tc.sphere_tests = tc.node_tests = tc.voxel_steps = 0;
-    return trace_walk<true>(sc, tv, planes, o, d, tc);
-}
 
 template <int NC>
 __device__ __forceinline__ void begin_walk(const Ctx<NC> c, const RenderLaunch &p) {
@@ -156,8 +150,10 @@ __device__ __forceinline__ void body_cand(const Ctx<NC> c, const RenderLaunch &p
     const float4 s = __ldg(p.scene.geom + idx);
     float t;
     RT_COUNT(sphere_tests);
-    if (sphere_test(s, o, d, a, tie_bound(ht), t) && (t < ht || (uint32_t)idx < c.u(F_HIDX))) {   // ties: the smaller index (rt_trace.cuh)
-        c.sf(F_HT, t); c.su(F_HIDX, (uint32_t)idx);
+    if (sphere_test(s, o, d, a, tie_bound(ht), t)) {
+        const uint32_t hraw = c.u(F_HIDX);
+        if (t < ht) { c.sf(F_HT, t); c.su(F_HIDX, (uint32_t)idx); }
+        else if ((int)hraw >= 0 && (hraw & ~kTieBit) != (uint32_t)idx) c.su(F_HIDX, hraw | kTieBit);   // same root, another sphere (rt_trace.cuh "Ties")
     }
     cm &= cm - 1u;                                   // clear the lowest flagged position
     if (cm & 15u) { c.su(F_CM, cm); return; }        // more flagged candidates in this chunk: stay in CAND
@@ -239,15 +235,17 @@ __device__ __forceinline__ void body_step(const Ctx<NC> c, const RenderLaunch &p
 template <int NC>
 __device__ __forceinline__ void body_end(const Ctx<NC> c, const RenderLaunch &p, const float *planes, TraceCounters &tc) {
     int hidx = c.i(F_HIDX);
-    if (hidx > 0 && p.tree.check_visibility) {       // the ground sphere (index 0) is tested unconditionally by the reference
-        const vec3f o = c.v3(F_OX), d = c.v3(F_DX);
-        int last_ok = -1;
-        if (!visible_fast(p.tree, planes, __ldg(p.scene.geom + hidx), o, d, c.f(F_HT)) && !sphere_visible(p.tree.vis, planes, hidx, o, d, last_ok, tc)) {
-            const Hit h = rewalk_checked(p.scene, p.tree, planes, o, d);
-            c.sf(F_HT, h.t);
-            c.su(F_HIDX, (uint32_t)h.idx);
-            hidx = h.idx;
+    if (hidx >= 0) {
+        const bool tie = ((uint32_t)hidx & kTieBit) != 0u;
+        Hit h;
+        h.t = c.f(F_HT); h.idx = (int)((uint32_t)hidx & ~kTieBit);
+        // ties, then the reference's visibility rule on the winner (rt_trace.cuh finish_hit); the rare failures redo the walk per lane
+        if (tie || (h.idx > 0 && p.tree.check_visibility)) {
+            const Hit w = finish_hit(p.scene, p.tree, planes, c.v3(F_OX), c.v3(F_DX), h, tie, tc);
+            if (w.idx != hidx || w.t != h.t) { c.sf(F_HT, w.t); c.su(F_HIDX, (uint32_t)w.idx); }
+            h = w;
         }
+        hidx = h.idx;
     }
     c.set_state(hidx < 0 ? S_SAMPLE : (__ldg(p.scene.tag + hidx) == 2 /* RT_MAT_DIELECTRIC */ ? S_DIEL : S_DIFF));
 }

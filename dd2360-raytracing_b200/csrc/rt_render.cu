@@ -480,13 +480,9 @@ cudaError_t launch_render(const RenderLaunch &p, bool octree, int sm_count, size
             case 44: return coop::launch_coop<6, 1>(p, sm_count, st, blocks_out);     // one candidate per lane and chunk step
             default: break;
         }
-        // automatic choice by scene size (measured on B200, profiles/README.md): the pixel-per-lane walk for small scenes (short
-        // candidate lists, many empty voxels), the warp-cooperative kernel from kCoopMinSpheres on, the pooled kernel from
-        // kPoolMinSpheres on; variant 1 forces the pixel-per-lane walk
-        if (p.variant != 1 && pool_ok && p.scene.n >= kPoolMinSpheres) {
-            which = kKernelPool;
-            return pool::launch_pool<64, 6>(p, sm_count, st, blocks_out);
-        }
+        // automatic choice by scene size (measured on B200, profiles/README.md r02f): the pixel-per-lane walk for small scenes
+        // (short candidate lists, many empty voxels: C2 2.3 vs 3.4 ms), the warp-cooperative kernel from kCoopMinSpheres on
+        // (C3 +8 %, C5 +19 % over the pooled kernel, which stays available as variants 10-15); variant 1 forces the per-lane walk
         if (p.variant != 1 && p.scene.n >= kCoopMinSpheres) {
             which = kKernelCoop;
             return coop::launch_coop<6, 2>(p, sm_count, st, blocks_out);

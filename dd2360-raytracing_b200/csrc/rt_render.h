@@ -10,8 +10,7 @@ namespace rt {
 
 constexpr int kRenderThreads = 128;
 constexpr int kListGridMinSpheres = 256;   // flat-list mode: scenes at least this large are answered through the grid
-constexpr int kPoolMinSpheres = 200000;  // octree mode: scenes at least this large use the pooled kernel (rt_pool.cuh)
-constexpr int kCoopMinSpheres = 20000;   // ... and scenes at least this large the warp-cooperative kernel (rt_coop.cuh)
+constexpr int kCoopMinSpheres = 20000;   // octree mode: scenes at least this large use the warp-cooperative kernel (rt_coop.cuh)
 
 struct RenderLaunch {
     SceneView scene;

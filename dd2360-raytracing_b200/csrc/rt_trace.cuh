@@ -46,11 +46,13 @@ struct TraceCounters {
 #define RT_COUNT(field) ((void)0)
 #endif
 
-// Ties: two DIFFERENT spheres with bit-identical t.  The reference keeps whichever it tests first (strict '<'): the ground,
-// then cells in child order, leaf lists in ascending sphere index — for spheres that share their level-3 cells (the generated
-// scenes: radius 0.1 against 2.75-wide cells) that is the SMALLER INDEX.  BASELINE config 3 at full size has ~170 such
-// pixels (1e9 rays against 7-fold overlapping spheres); the frame of the reference's CUDA build settles the rule
-// (tests/golden/ref_cuda/manifest_full.json): every kernel here resolves ties to the smaller index, whatever its test order.
+// Ties: two DIFFERENT spheres with bit-identical t (~170 pixels of BASELINE config 3 at full size: 1e9 rays against 7-fold
+// overlapping spheres).  The reference keeps whichever it tests FIRST (strict '<'): the ground sphere, then the level-3 cells
+// in child order (= ascending 9-bit Morton id) whose boxes the ray's line crosses, each cell's leaf lists in ascending sphere
+// index.  A tied sphere's place in that order is tie_key() = (first crossed cell that stores it, its index); the frame of the
+// reference's CUDA build settles it (tests/golden/ref_cuda/manifest_full.json: with "smaller index wins" 21 pixels of that
+// frame differ, with this rule none).  The closest-hit kernels only DETECT a tie (a candidate whose root equals the current
+// minimum but whose index differs) and leave the decision to resolve_ties(): one more walk for ~1e-7 of the rays.
 // tie_bound(t) is the next float above t, so that sphere_test's strict `root < t_max` lets an equal root through.
 RT_HD float tie_bound(const float t) {
 #if defined(__CUDA_ARCH__)
@@ -138,6 +140,28 @@ RT_HD bool maybe_hit(const float4 s, const vec3f o, const vec3f d, const float a
     return (disc > 0.0f) & !reject;
 }
 
+// The same pre-filter, and — when the estimates make a hit CERTAIN — an upper bound of the root sphere_test will accept:
+// root1 surely above kTMin (accepted: root1 <= t1 + eps), or root1 surely below kTMin and root2 surely above it (accepted:
+// root2 <= t2 + eps).  FLT_MAX otherwise (no hit, or the estimates straddle kTMin).  The closest hit of the ray is then at most
+// `ub`, whatever the exact evaluation returns: the cooperative kernel prunes against it long before it evaluates exactly.
+RT_HD bool maybe_hit_ub(const float4 s, const vec3f o, const vec3f d, const float a, const float ia, const float t_max, float &ub) {
+    const vec3f oc = mk(sub_(o.x, s.x), sub_(o.y, s.y), sub_(o.z, s.z));
+    const float b = dot3(oc, d);
+    const float c = fma_(-s.w, s.w, dot3(oc, oc));
+    const float disc = fma_(b, b, -mul_(a, c));
+    const float sa = sqrt_trav(fmaxf(disc, 0.0f));
+    const float t1 = (-b - sa) * ia, t2 = (sa - b) * ia;
+    const float eps = (fabsf(b) + sa) * ia * 1e-5f;
+    const float lo1 = t1 - eps, hi1 = t1 + eps, lo2 = t2 - eps, hi2 = t2 + eps;
+    const bool reject = (lo1 > t_max) | (hi2 < kTMin) | ((hi1 < kTMin) & (lo2 > t_max));
+    const bool pass = (disc > 0.0f) & !reject;
+    float u = kTMax;
+    if (lo1 > kTMin) u = hi1;
+    else if ((hi1 < kTMin) & (lo2 > kTMin)) u = hi2;
+    ub = pass ? u : kTMax;
+    return pass;
+}
+
 struct RayPre {
     vec3f o, d, inv;    // inv = 1/d (IEEE; +-inf for zero components)
     float a;            // dot(d,d)
@@ -190,6 +214,29 @@ bool sphere_visible(const VisView vis, const float *planes, const int idx, const
     return false;
 }
 
+// Place of sphere `idx` in the reference's test order among spheres that tie (see "Ties" above): the first level-3 cell in child
+// order that stores it and that the ray's line crosses, then the index; 0 for the ground sphere (tested before the tree),
+// 0xffffffff when no such cell exists (the reference never tests it: not a candidate).  Flat-list mode: list order = index.
+RT_HD uint32_t tie_key(const TreeView &tv, const float *planes, const int idx, const vec3f o, const vec3f d, TraceCounters &tc) {
+    if (idx <= 0) return 0u;
+    if (!tv.check_visibility) return (uint32_t)idx;
+    uint32_t best = 0xffffffffu;
+    const uint32_t b = RT_LDG(tv.vis.ent_off + idx), e = RT_LDG(tv.vis.ent_off + idx + 1);
+    for (uint32_t k = b; k < e; k++) {
+        const int c = (int)RT_LDG(tv.vis.ent_cell + k);
+        if (c & kEntDropped) continue;
+        const uint32_t key = (uint32_t)c << 22 | (uint32_t)idx;
+        if (key >= best) continue;
+        int ix, iy, iz;
+        cell_xyz(c, ix, iy, iz);
+        RT_COUNT(node_tests);
+        if (ref_line_test(o, d, planes[ix], planes[kPlanes + iy], planes[2 * kPlanes + iz], planes[ix + 1], planes[kPlanes + iy + 1],
+                          planes[2 * kPlanes + iz + 1]))
+            best = key;
+    }
+    return best;
+}
+
 // A sufficient condition for the rule above that needs no division and no list: the hit point P = o + t*d lies on the
 // ray's line, so if P is strictly inside some level-3 cell that stores the sphere, the line crosses that cell and the
 // reference's slab test passes — PROVIDED the margins absorb its float rounding.  With P inside [lo + m, hi - m] per
@@ -218,13 +265,40 @@ RT_HD bool visible_fast(const TreeView &tv, const float *planes, const float4 s,
     return ok;
 }
 
-// One pass over the candidates.  CHECKED = true applies the visibility rule to every candidate before it may become
-// the closest hit (always exact); CHECKED = false takes the plain minimum over all candidates.
-template <bool CHECKED>
+// One pass over the candidates.
+//   kWalkMin     : the plain minimum over all candidates; *tie is set when two different spheres share that minimum;
+//   kWalkChecked : the visibility rule on every candidate before it may become the closest hit, ties by tie_key (always exact);
+//   kWalkTies    : among the candidates whose accepted root is exactly t_tie, the first in the reference's order (idx -1: none).
+enum : int { kWalkMin = 0, kWalkChecked = 1, kWalkTies = 2 };
+
+// the candidate (t, idx) against the closest hit so far, per mode; key_h: tie_key of h.idx in kWalkTies (0xffffffff: none yet)
+template <int MODE>
+RT_HD void walk_accept(const TreeView &tv, const float *planes, const vec3f o, const vec3f d, const float t, const int idx, Hit &h,
+                       uint32_t &key_h, bool *tie, int &last_ok, TraceCounters &tc) {
+    if (MODE == kWalkMin) {
+        if (t < h.t) { h.t = t; h.idx = idx; if (tie) *tie = false; }
+        else if (idx != h.idx && tie) *tie = true;                       // equal root, another sphere: resolve_ties decides
+    } else if (MODE == kWalkChecked) {
+        if (t < h.t) {
+            if (sphere_visible(tv.vis, planes, idx, o, d, last_ok, tc)) { h.t = t; h.idx = idx; }
+        } else if (idx != h.idx) {
+            if (tie_key(tv, planes, idx, o, d, tc) < tie_key(tv, planes, h.idx, o, d, tc)) h.idx = idx;
+        }
+    } else {
+        if (t == h.t && idx != h.idx) {
+            const uint32_t key = tie_key(tv, planes, idx, o, d, tc);
+            if (key < key_h) { key_h = key; h.idx = idx; }
+        }
+    }
+}
+
+template <int MODE>
 RT_HD Hit trace_walk(const SceneView &sc, const TreeView &tv, const float *planes, const vec3f o, const vec3f d,
-                    TraceCounters &tc) {
+                    TraceCounters &tc, const float t_tie = 0.0f, bool *tie = nullptr) {
     Hit h;
-    h.t = kTMax; h.idx = -1;
+    h.t = MODE == kWalkTies ? t_tie : kTMax; h.idx = -1;
+    uint32_t key_h = 0xffffffffu;
+    if (tie) *tie = false;
     RayPre r;
     r.o = o; r.d = d;
     r.a = dot3(d, d);
@@ -232,7 +306,10 @@ RT_HD Hit trace_walk(const SceneView &sc, const TreeView &tv, const float *plane
     {   // ground sphere first, unconditionally (:322-332)
         float t;
         RT_COUNT(sphere_tests);
-        if (sphere_test(RT_LDG(sc.geom), o, d, r.a, kTMax, t)) { h.t = t; h.idx = 0; }
+        if (sphere_test(RT_LDG(sc.geom), o, d, r.a, kTMax, t)) {
+            if (MODE != kWalkTies) { h.t = t; h.idx = 0; }
+            else if (t == t_tie) { h.idx = 0; key_h = 0u; }
+        }
     }
     int last_ok = -1;
     for (int k = 1; k < tv.nprolog; k++) {   // big spheres: tested directly (prolog[0] is the ground sphere)
@@ -240,10 +317,8 @@ RT_HD Hit trace_walk(const SceneView &sc, const TreeView &tv, const float *plane
         float t;
         RT_COUNT(sphere_tests);
         const float4 s = RT_LDG(sc.geom + idx);
-        if (maybe_hit(s, o, d, r.a, ia, h.t) && sphere_test(s, o, d, r.a, tie_bound(h.t), t) && (t < h.t || idx < h.idx) &&
-            (!CHECKED || sphere_visible(tv.vis, planes, idx, o, d, last_ok, tc))) {
-            h.t = t; h.idx = idx;
-        }
+        if (maybe_hit(s, o, d, r.a, ia, h.t) && sphere_test(s, o, d, r.a, tie_bound(h.t), t))
+            walk_accept<MODE>(tv, planes, o, d, t, idx, h, key_h, tie, last_ok, tc);
     }
     const GridView &g = tv.grid;
     if (g.nx == 0) return h;
@@ -304,34 +379,57 @@ RT_HD Hit trace_walk(const SceneView &sc, const TreeView &tv, const float *plane
             const bool m0 = maybe_hit(s0, o, d, r.a, ia, h.t), m1 = two & maybe_hit(s1, o, d, r.a, ia, h.t);
             float t;
             RT_COUNT(sphere_tests);
-            if (m0 && sphere_test(s0, o, d, r.a, tie_bound(h.t), t)) {
-                const int idx = (int)RT_LDG(g.refs + k);
-                if ((t < h.t || idx < h.idx) && (!CHECKED || sphere_visible(tv.vis, planes, idx, o, d, last_ok, tc))) { h.t = t; h.idx = idx; }
-            }
+            if (m0 && sphere_test(s0, o, d, r.a, tie_bound(h.t), t))
+                walk_accept<MODE>(tv, planes, o, d, t, (int)RT_LDG(g.refs + k), h, key_h, tie, last_ok, tc);
             if (two) RT_COUNT(sphere_tests);
-            if (m1 && sphere_test(s1, o, d, r.a, tie_bound(h.t), t)) {
-                const int idx = (int)RT_LDG(g.refs + k + 1);
-                if ((t < h.t || idx < h.idx) && (!CHECKED || sphere_visible(tv.vis, planes, idx, o, d, last_ok, tc))) { h.t = t; h.idx = idx; }
-            }
+            if (m1 && sphere_test(s1, o, d, r.a, tie_bound(h.t), t))
+                walk_accept<MODE>(tv, planes, o, d, t, (int)RT_LDG(g.refs + k + 1), h, key_h, tie, last_ok, tc);
             k += two ? 2u : 1u;
         }
     }
     return h;
 }
 
-// acceleration_structure.h:319-342 hitTree, re-organised (see the header comment).
-// Invisible candidates are rare (hits outside the root box, spheres dropped on bucket overflow), so: take the
-// minimum over ALL candidates first; if that sphere is visible it is also the minimum over the visible ones and
-// we are done — one visibility test per ray, made where the warp has reconverged.  Otherwise redo the walk with the
-// rule applied to every candidate.
-RT_HD Hit trace_tree(const SceneView &sc, const TreeView &tv, const float *planes, const vec3f o, const vec3f d,
+// What every closest-hit kernel does with its minimum over ALL candidates (h, and whether two different spheres tied for it):
+// ties go through one more walk that ranks the tied spheres in the reference's test order; then the reference's visibility rule
+// ("some cell that stores the sphere is crossed by the ray's line") on the winner — invisible candidates are rare (hits outside
+// the root box, spheres dropped on bucket overflow), so it is evaluated once, where the warp has reconverged, and only a
+// failure redoes the walk with the rule (and the tie order) applied to every candidate.
+// (the two rare continuations — ranking tied spheres, redoing the walk with the rule on every candidate — are out of line so
+// that they cost the kernels no registers)
+#if defined(__CUDA_ARCH__)
+__device__ __noinline__
+#else
+inline
+#endif
+Hit finish_hit_slow(const SceneView &sc, const TreeView &tv, const float *planes, const vec3f o, const vec3f d, Hit h, const bool tie,
                     TraceCounters &tc) {
-    Hit h = trace_walk<false>(sc, tv, planes, o, d, tc);
+    if (tie) {
+        const Hit w = trace_walk<kWalkTies>(sc, tv, planes, o, d, tc, h.t);
+        if (w.idx >= 0) {                     // (tie_key found a crossed cell that stores it: visible)
+            h.idx = w.idx;
+            return h;
+        }
+    }                                         // none of the tied spheres is visible, or the winner is not:
+    return trace_walk<kWalkChecked>(sc, tv, planes, o, d, tc);
+}
+
+RT_HD Hit finish_hit(const SceneView &sc, const TreeView &tv, const float *planes, const vec3f o, const vec3f d, const Hit h, const bool tie,
+                    TraceCounters &tc) {
+    if (tie) return finish_hit_slow(sc, tv, planes, o, d, h, true, tc);
     if (h.idx > 0 && tv.check_visibility && !visible_fast(tv, planes, RT_LDG(sc.geom + h.idx), o, d, h.t)) {
         int last_ok = -1;                    // (the ground sphere, index 0, is tested unconditionally by the reference)
-        if (!sphere_visible(tv.vis, planes, h.idx, o, d, last_ok, tc)) h = trace_walk<true>(sc, tv, planes, o, d, tc);
+        if (!sphere_visible(tv.vis, planes, h.idx, o, d, last_ok, tc)) return finish_hit_slow(sc, tv, planes, o, d, h, false, tc);
     }
     return h;
+}
+
+// acceleration_structure.h:319-342 hitTree, re-organised (see the header comment): candidates from the grid walk, then finish_hit.
+RT_HD Hit trace_tree(const SceneView &sc, const TreeView &tv, const float *planes, const vec3f o, const vec3f d,
+                    TraceCounters &tc) {
+    bool tie = false;
+    const Hit h = trace_walk<kWalkMin>(sc, tv, planes, o, d, tc, 0.0f, &tie);
+    return finish_hit(sc, tv, planes, o, d, h, tie, tc);
 }
 
 }  // namespace rt

@@ -280,7 +280,7 @@ def test_dropin_octree_hit_scatter_and_get_ray_members(rt, pkg, O, tmp_path):
         assert [np.float32(float.fromhex(x)) for x in f[9:12]] == list(sc["atten"][q])
         assert [np.float32(float.fromhex(x)) for x in f[12:15]] == list(sc["dir"][q])
         nrm = np.array([float.fromhex(x) for x in f[5:8]])
-        assert abs(np.linalg.norm(nrm) - 1.0) < 1e-4
+        assert abs(np.linalg.norm(nrm) - 1.0) < 2e-3      # (the ground sphere: (p - c) / 1000 in float)
     # get_ray
     rt.set_camera(1200, 800)
     gs = np.stack([pkg.xorwow_state(1984 + k, 0) for k in range(G)]).astype(np.uint32)
