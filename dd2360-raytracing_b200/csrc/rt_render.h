@@ -10,7 +10,7 @@ namespace rt {
 
 constexpr int kRenderThreads = 128;
 constexpr int kListGridMinSpheres = 256;   // flat-list mode: scenes at least this large are answered through the grid
-constexpr int kCoopMinSpheres = 20000;   // octree mode: scenes at least this large use the warp-cooperative kernel (rt_coop.cuh)
+constexpr int kCoopMinSpheres = 40000;   // octree mode: scenes at least this large use the warp-cooperative kernel (rt_coop.cuh)
 
 struct RenderLaunch {
     SceneView scene;
