@@ -41,7 +41,7 @@ ABI_SYMBOLS = [
     "rt_octree_build", "rt_octree_build_ex", "rt_octree_reference_bytes", "rt_octree_export_reference", "rt_octree_debug_read", "rt_xorwow_state", "rt_debug_counters", "rt_trace_rays", "rt_camera_get_rays", "rt_scatter_rays",
     "rt_render_accumulate", "rt_render_progressive", "rt_finalize", "rt_finalize_n", "rt_render", "rt_render_to_host", "rt_format_ppm",
     "rt_ppm_format", "rt_ppm_read", "rt_render_to_ppm",
-    "rt_ffma_peak", "rt_malloc", "rt_free", "rt_memcpy_to_host", "rt_synchronize", "rt_kernel_name",
+    "rt_ffma_peak", "rt_hfma2_peak", "rt_malloc", "rt_free", "rt_memcpy_to_host", "rt_synchronize", "rt_kernel_name",
     "rt_comm_get_unique_id", "rt_comm_init_rank", "rt_comm_init_all", "rt_comm_attach", "rt_comm_destroy", "rt_comm_rank", "rt_comm_size",
     "rt_group_start", "rt_group_end", "rt_reduce", "rt_reduce_scatter", "rt_broadcast",
 ]
@@ -132,6 +132,7 @@ def load_library(path: str | None = None) -> C.CDLL:
         "rt_ppm_read": (i32, [vp, vp, sz]),
         "rt_render_to_ppm": (i32, [vp, C.POINTER(RenderArgs), C.POINTER(RenderStats), C.POINTER(sz)]),
         "rt_ffma_peak": (i32, [vp, C.POINTER(f32), C.POINTER(f32)]),
+        "rt_hfma2_peak": (i32, [vp, C.POINTER(f32), C.POINTER(f32)]),
         "rt_malloc": (i32, [vp, sz, C.POINTER(vp)]),
         "rt_free": (i32, [vp, vp]),
         "rt_memcpy_to_host": (i32, [vp, vp, vp, sz]),
@@ -383,6 +384,12 @@ class RayTracer:
 
     def finalize_n(self, accum_dev_ptr: int, fb_dev_ptr: int, count: int, ns: int):
         self._ck(self.L.rt_finalize_n(self._ctx, C.c_void_p(accum_dev_ptr), C.c_void_p(fb_dev_ptr), count, ns), "rt_finalize_n")
+
+    def hfma2_peak_tflops(self) -> float:
+        """Measured dense packed-half HFMA2 rate (TFLOP/s, 4 flop per instruction): the USE_FP16 roofline denominator."""
+        t, ms = C.c_float(), C.c_float()
+        self._ck(self.L.rt_hfma2_peak(self._ctx, C.byref(t), C.byref(ms)), "rt_hfma2_peak")
+        return float(t.value)
 
     def ffma_peak_tflops(self) -> float:
         """Measured dense FP32 FFMA rate (TFLOP/s) of this GPU: the FP32 roofline denominator."""

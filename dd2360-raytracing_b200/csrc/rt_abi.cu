@@ -486,6 +486,10 @@ static int do_render(rt_context *ctx, const rt_render_args *a, float *out_dev, b
         list_grid = true;
     }
     p.cam = ctx->cam_host;                        // per-context camera, by value in the launch parameters
+    {
+        const OctreeBuilder *acc = list_grid ? ctx->list_accel : ctx->octree;
+        p.coop_items = (a->use_octree || list_grid) && acc->total_voxels > 0 && acc->total_refs / acc->total_voxels >= 40 ? 4 : 2;
+    }
     p.nx = a->nx; p.ny = a->ny;
     p.ns_total = a->ns;
     p.ns_local = a->ns;
@@ -860,6 +864,45 @@ extern "C" int rt_ffma_peak(rt_context *ctx, float *tflops, float *ms_out) {
         if (rep > 0 && ms < best) best = ms;
     }
     const double flops = 2.0 * 8 * 16 * (double)iters * blocks * threads;
+    *tflops = (float)(flops / (best * 1e-3) / 1e12);
+    if (ms_out) *ms_out = best;
+    return RT_OK;
+}
+
+// the same for packed half arithmetic: dense HFMA2 rate (2 lanes x 2 flop per instruction), the roofline denominator of USE_FP16
+__global__ void __launch_bounds__(256) k_hfma2_peak(float *out, int iters, float a, float b) {
+    const __half2 a2 = __float2half2_rn(a), b2 = __float2half2_rn(b);
+    __half2 x[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) x[k] = __float2half2_rn((float)(threadIdx.x & 7) * 0.125f + (float)k);
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int u = 0; u < 16; u++) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) x[k] = __hfma2(x[k], a2, b2);
+        }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; k++) s += __low2float(x[k]) + __high2float(x[k]);
+    if (s == 12345.678f) out[0] = s;   // keeps the chain alive, never true in practice
+}
+
+extern "C" int rt_hfma2_peak(rt_context *ctx, float *tflops, float *ms_out) {
+    if (!ctx || !tflops) return RT_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    const int blocks = ctx->prop.multiProcessorCount * 8, threads = 256, iters = 4096;
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; rep++) {
+        CK(cudaEventRecord(ctx->ev0, ctx->stream));
+        k_hfma2_peak<<<blocks, threads, 0, ctx->stream>>>(reinterpret_cast<float *>(ctx->counters), iters, 0.999f, 1e-3f);
+        CK(cudaEventRecord(ctx->ev1, ctx->stream));
+        CK(cudaEventSynchronize(ctx->ev1));
+        float ms = 0;
+        cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+        if (rep > 0 && ms < best) best = ms;
+    }
+    const double flops = 4.0 * 8 * 16 * (double)iters * blocks * threads;
     *tflops = (float)(flops / (best * 1e-3) / 1e12);
     if (ms_out) *ms_out = best;
     return RT_OK;

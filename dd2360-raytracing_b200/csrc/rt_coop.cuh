@@ -31,7 +31,7 @@ namespace coop {
 
 constexpr unsigned kFull = 0xffffffffu;
 constexpr uint32_t kPrologFlag = 0x80000000u;    // ring reference: index into the prolog list instead of the voxel lists
-constexpr int kRing = 96;                        // >= 31 (left over) + 64 (one chunk's pushes, two candidates per lane)
+constexpr int kRing = 160;                       // >= 31 (left over) + 128 (one chunk's pushes at four candidates per lane)
 
 struct __align__(16) RayMeta {
     int koff;        // first reference of the lane's current voxel - ITEMS * its offset in the flat item list
@@ -92,29 +92,32 @@ __device__ __forceinline__ float drain(WarpShared &ws, const SceneView &sc, cons
     return __uint_as_float(now);
 }
 
-// Append the lanes with pass0 / pass1 (two candidates per lane: references ref and ref + 1) to the ring; drains while 32 or
-// more are queued.  Warp-uniform `count`.
-__device__ __forceinline__ void push2(WarpShared &ws, const SceneView &sc, const TreeView &tv, const unsigned lane, const bool pass0,
-                                      const bool pass1, const uint32_t owner, const uint32_t ref, int &count) {
-    const unsigned m0 = __ballot_sync(kFull, pass0), m1 = __ballot_sync(kFull, pass1);
-    if (!(m0 | m1)) return;
+// Append the candidates flagged in `pass` (bit j: reference ref + j passed the pre-filter; N candidates per lane) to the ring by
+// ballot/popc ranking — the warp is converged, `count` is a warp-uniform register, no atomics; drains while 32 or more are
+// queued.  (Claiming slots with a shared-memory atomicAdd under the lanes' own predicates measured 3 % slower, profiles r02k.)
+template <int N>
+__device__ __forceinline__ void push_n(WarpShared &ws, const SceneView &sc, const TreeView &tv, const unsigned lane, const uint32_t pass,
+                                       const uint32_t owner, const uint32_t ref, int &count) {
+    if (!__any_sync(kFull, pass != 0u)) return;
     const unsigned lt = (1u << lane) - 1u;
-    const int c0 = __popc(m0);
-    if (pass0) ws.ring[count + __popc(m0 & lt)] = make_uint2(owner, ref);
-    if (pass1) ws.ring[count + c0 + __popc(m1 & lt)] = make_uint2(owner, ref + 1u);
-    count += c0 + __popc(m1);
+#pragma unroll
+    for (int j = 0; j < N; j++) {
+        const bool pj = (pass >> j) & 1u;
+        const unsigned m = __ballot_sync(kFull, pj);
+        if (pj) ws.ring[count + __popc(m & lt)] = make_uint2(owner, ref + (uint32_t)j);
+        count += __popc(m);
+    }
     __syncwarp();
-    if (count >= 32) {
-        do {
-            drain(ws, sc, tv, lane, count - 32, 32);      // the newest 32; what is left stays at the front
-            count -= 32;
-        } while (count >= 32);
+    while (count >= 32) {
+        drain(ws, sc, tv, lane, count - 32, 32);      // the newest 32; what is left stays at the front
+        count -= 32;
     }
 }
 
 // Closest hit for the rays of the whole warp (lane `has` a ray or idles along).  Every lane of the warp must call.
-// ITEMS = candidates per lane and chunk step (1 or 2: with 2 a lane takes two consecutive references of one voxel list,
-// so the owner lookup and the ray fetch are paid once per pair and two geometry loads are in flight).
+// ITEMS = candidates per lane and chunk step (1, 2 or 4: a lane takes that many consecutive references of one voxel list, so the
+// owner lookup and the ray fetch are paid once per group and the geometry loads are in flight together; 2 is the default,
+// 4 pays off once lists are long — BASELINE config 5 has 71 references per voxel).
 // Returns the minimum over ALL candidates and whether two different spheres tied for it (finish_hit settles ties and the
 // visibility rule, as in trace_tree).
 template <int ITEMS>
@@ -146,7 +149,7 @@ __device__ __forceinline__ Hit coop_trace(WarpShared &ws, const SceneView &sc, c
         float ub;
         const bool pass = has && maybe_hit_ub(s, o, d, a, ia, ws.meta[lane].bound, ub);
         if (pass && ub < ws.meta[lane].bound) ws.meta[lane].bound = ub;        // (the lane's own record: no other lane touches it here)
-        push2(ws, sc, tv, lane, pass, false, lane, kPrologFlag | (uint32_t)k, count);
+        push_n<1>(ws, sc, tv, lane, pass ? 1u : 0u, lane, kPrologFlag | (uint32_t)k, count);
     }
     best_t = ws.meta[lane].bound;           // from here on `best_t` is the pruning bound; exact values live in ws.best_t / best_i
 
@@ -229,26 +232,26 @@ __device__ __forceinline__ Hit coop_trace(WarpShared &ws, const SceneView &sc, c
             const float4 ro = ws.ro[owner], rd = ws.rd[owner];
             const RayMeta mt = ws.meta[owner];
             const uint32_t ref = (uint32_t)(mt.koff + ITEMS * (int)item);
-            bool pass0 = false, pass1 = false;
+            uint32_t pass = 0u;
             if (valid) {
                 const vec3f oo = mk(ro.x, ro.y, ro.z), dd = mk(rd.x, rd.y, rd.z);
-                const float4 s0 = __ldg(g.ref_geom + ref);
-                float ub0, ub1 = kTMax;
-                if (ITEMS == 2) {
-                    const float4 s1 = __ldg(g.ref_geom + ref + 1);     // (one past a list's end is the next list's first entry, or the slack element)
+                float4 sg[ITEMS];
+#pragma unroll
+                for (int j = 0; j < ITEMS; j++) sg[j] = __ldg(g.ref_geom + ref + j);   // (past a list's end: the next list, or the slack elements)
+                float ub = kTMax;
+#pragma unroll
+                for (int j = 0; j < ITEMS; j++) {
+                    float ubj;
                     RT_COUNT(sphere_tests);
-                    pass1 = maybe_hit_ub(s1, oo, dd, ro.w, rd.w, mt.bound, ub1) && (int)ref + 1 < mt.kend;
-                    if (!pass1) ub1 = kTMax;
+                    const bool pj = maybe_hit_ub(sg[j], oo, dd, ro.w, rd.w, mt.bound, ubj) && (j == 0 || (int)ref + j < mt.kend);
+                    if (pj) { pass |= 1u << j; ub = fminf(ub, ubj); }
                 }
-                RT_COUNT(sphere_tests);
-                pass0 = maybe_hit_ub(s0, oo, dd, ro.w, rd.w, mt.bound, ub0);
                 // a certain hit lowers the owner's pruning bound at once (native shared-memory atomic on the float's bits: roots
                 // are positive); its exact evaluation waits in the ring until 32 candidates are queued
-                const float ub = fminf(ub0, ub1);
                 if (ub < mt.bound) atomicMin(reinterpret_cast<uint32_t *>(&ws.meta[owner].bound), __float_as_uint(ub));
             }
             __syncwarp();                       // slot[] is rewritten by the next chunk
-            push2(ws, sc, tv, lane, pass0, pass1, owner, ref, count);
+            push_n<ITEMS>(ws, sc, tv, lane, pass, owner, ref, count);
         }
         __syncwarp();
         best_t = ws.meta[lane].bound;           // no exact evaluation at the end of a round: the certain-hit bounds steer the walk

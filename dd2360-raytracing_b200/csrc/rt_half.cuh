@@ -425,7 +425,8 @@ struct CoopSmem {
     uint32_t ring[512];       // scan-order keys of candidates with a positive discriminant (0: the ground sphere)
     uint32_t cells[16][32];   // [word][lane]: 512-bit mask of the level-3 cells lane's ray passes (walk_cells_h)
     uint32_t tail;            // ring write position (shared atomic: the order of the keys in the ring does not matter)
-    uint32_t pad_[3];
+    uint32_t pairs_lo, pairs_hi;   // RT_COUNTERS builds: sphere pairs scanned by this warp (work counter of the roofline)
+    uint32_t pad_;
 };
 
 __device__ __forceinline__ void coop_eval_h(const PairView pv, const uint2 *geom_h, const uint32_t key, const vec3h o, const vec3h d, const hf a,
@@ -465,6 +466,13 @@ __device__ __forceinline__ void coop_filter_h(CoopSmem &sm, const PairView pv, c
     const __half2 dx = __half2half2(vx(d)), dy = __half2half2(vy(d)), dz = __half2half2(d.z);
     const __half2 a2 = __half2half2(a), zero2 = __float2half2_rn(0.0f);
     uint4 g[4];
+#ifdef RT_COUNTERS
+    if (lane == 0) {
+        const uint32_t before = sm.pairs_lo;
+        sm.pairs_lo = before + (pe - pb);
+        if (sm.pairs_lo < before) sm.pairs_hi++;
+    }
+#endif
     if (pb < pe) {
 #pragma unroll
         for (int i = 0; i < 4; i++) g[i] = __ldg(pv.geom + pb + lane + 32 * i);

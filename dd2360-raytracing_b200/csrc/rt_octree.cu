@@ -484,7 +484,7 @@ cudaError_t OctreeBuilder::build(cudaStream_t st, const float4 *geom, const int 
         RT_CUDA(cudaMemsetAsync(d.vox_count, 0, ((size_t)V + 2) * 4, st));
         k_vox_pass<true><<<(n + tb - 1) / tb, tb, 0, st>>>(geom, d.sph_flag, n, grid, d.vox_count, d.vox_start, d.vox_refs);
         k_vox_finish<<<(V + tb - 1) / tb, tb, 0, st>>>(d.vox_start, V, d.vox_refs, d.vox);
-        RT_CUDA(ensure(d.ref_geom, cap.ref_geom, (size_t)total_refs + 1));
+        RT_CUDA(ensure(d.ref_geom, cap.ref_geom, (size_t)total_refs + 4));   // (the cooperative kernel loads up to 3 entries past a list)
         if (total_refs) k_gather_geom<<<(unsigned)(((size_t)total_refs + tb - 1) / tb), tb, 0, st>>>(geom, d.vox_refs, total_refs, d.ref_geom);
     }
     if (!d.prolog_geom) RT_CUDA(cudaMalloc(&d.prolog_geom, (kMaxBig + 1) * sizeof(float4)));

@@ -478,6 +478,8 @@ cudaError_t launch_render(const RenderLaunch &p, bool octree, int sm_count, size
             case 42: return coop::launch_coop<4, 2>(p, sm_count, st, blocks_out);
             case 43: return coop::launch_coop<8, 2>(p, sm_count, st, blocks_out);
             case 44: return coop::launch_coop<6, 1>(p, sm_count, st, blocks_out);     // one candidate per lane and chunk step
+            case 45: return coop::launch_coop<6, 4>(p, sm_count, st, blocks_out);     // four
+            case 46: return coop::launch_coop<5, 4>(p, sm_count, st, blocks_out);
             default: break;
         }
         // automatic choice by scene size (measured on B200, profiles/README.md r02f): the pixel-per-lane walk for small scenes
@@ -485,6 +487,8 @@ cudaError_t launch_render(const RenderLaunch &p, bool octree, int sm_count, size
         // (C3 +8 %, C5 +19 % over the pooled kernel, which stays available as variants 10-15); variant 1 forces the per-lane walk
         if (p.variant != 1 && p.scene.n >= kCoopMinSpheres) {
             which = kKernelCoop;
+            // four candidates per lane once voxel lists are long (C5: 71 references per voxel, +4 %; C3: 13 per voxel, -6 %)
+            if (p.coop_items == 4) return coop::launch_coop<6, 4>(p, sm_count, st, blocks_out);
             return coop::launch_coop<6, 2>(p, sm_count, st, blocks_out);
         }
         which = kKernelLane;

@@ -32,6 +32,7 @@ struct RenderLaunch {
     uint32_t max_rounds;     // pool kernel watchdog: scheduling rounds per warp before it gives up (host reports an error)
     int tune_sticky, tune_sticky_min;   // pool kernel: TEST chunks per scheduling round, and the lane count that keeps it going
     int tune_test_min;       // pool kernel: TEST is only scheduled ahead of fuller-enough other states once this many contexts wait in it
+    int coop_items;          // cooperative kernel: candidates per lane and chunk step (2, or 4 for scenes with long voxel lists); 0 = 2
     int variant;             // kernel variant for A/B measurements (rt_render_args.reserved[1]); 0 = default
     int finalize;            // 1: write sqrt(sum/ns) (main.cu:111-115); 0: write the linear sum
     float *out;              // nx*ny*3 floats

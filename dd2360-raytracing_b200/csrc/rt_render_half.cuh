@@ -169,7 +169,10 @@ k_render_h(const __grid_constant__ RenderLaunch p, const uint2 *__restrict__ geo
         cam.lens_radius = cam_h[21];
     }
     const unsigned lane = threadIdx.x & 31u;
-    if (COOP2 && lane == 0) coop_sm[threadIdx.x >> 5].tail = 0u;
+    if (COOP2 && lane == 0) {
+        coop_sm[threadIdx.x >> 5].tail = 0u;
+        coop_sm[threadIdx.x >> 5].pairs_lo = coop_sm[threadIdx.x >> 5].pairs_hi = 0u;
+    }
     __syncwarp();
     const uint32_t gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     int pix = -1, pi = 0, pj = 0, s = 0, depth = 0;
@@ -265,6 +268,12 @@ k_render_h(const __grid_constant__ RenderLaunch p, const uint2 *__restrict__ geo
     if (lane == 0) {
         atomicAdd(p.counters + 0, r64);
         atomicAdd(p.counters + 1, p64);
+#ifdef RT_COUNTERS
+        if (COOP2) {     // two spheres per pair (NaN padding pairs included: they are scanned too)
+            const CoopSmem &cs = coop_sm[threadIdx.x >> 5];
+            atomicAdd(p.counters + 2, 2ull * ((unsigned long long)cs.pairs_hi << 32 | cs.pairs_lo));
+        }
+#endif
     }
 }
 

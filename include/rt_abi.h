@@ -222,6 +222,7 @@ int rt_broadcast(rt_context *ctx, void *dev, size_t bytes, int root);
 
 /* ---- measurement: dense FP32 FFMA rate of this GPU (2 flop per FFMA), the denominator of the FP32 roofline -------- */
 int rt_ffma_peak(rt_context *ctx, float *tflops, float *kernel_ms);
+int rt_hfma2_peak(rt_context *ctx, float *tflops, float *kernel_ms);    /* packed half: 4 flop per HFMA2 (USE_FP16 roofline) */
 
 /* ---- device memory helpers for hosts without a CUDA runtime binding ---------------------------------------- */
 int rt_malloc(rt_context *ctx, size_t bytes, void **dev_ptr);

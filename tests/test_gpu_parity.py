@@ -537,3 +537,63 @@ def test_config3_full_size_frame_is_the_reference_cuda_frame(rt, pkg, O, golden_
     i0, i1, j = 2064, 2077, 687
     ref, _, _ = O.render(sph, O.camera(nx, ny, O.ARITH_DEVICE), O.make_params(nx, ny, ns, True, spl, O.ARITH_DEVICE, window=(i0, i1, j, j + 1)), blob)
     assert np.array_equal(frame[j, i0:i1].view(np.uint32), ref[j, i0:i1].view(np.uint32))
+
+
+def test_config4_full_size_4spp_frame_is_the_reference_fp16_frame(rt, pkg, golden_dir):
+    """BASELINE config 4 (USE_FP16) at full frame size, 4 spp — the sample count at which the reference's FP16 CUDA build was run on a
+    B200 (3.4 s there; tests/golden/gen_ref_cuda_full.sh): sha256 of the half framebuffer and of the integer PPM values, plus the
+    committed 1/16 x 1/16 subsample pixel by pixel."""
+    import sys
+    import torch
+    sys.path.insert(0, golden_dir)
+    from digest_frame import digest, subsample16
+    man = json.load(open(os.path.join(golden_dir, "ref_cuda", "manifest_full.json")))["frames"]["C4_3840x2160x4"]
+    nx, ny, ns, n, spl = 3840, 2160, 4, 100000, 300
+    try:
+        rt.create_world(n, 0.1, pkg.PREC_FP16)
+        rt.build_octree(spl, pkg.PREC_FP16)
+        fb = torch.empty((ny, nx, 3), dtype=torch.float32, device="cuda")
+        st = rt.render_device(rt.args(nx, ny, ns, True, precision=pkg.PREC_FP16), fb.data_ptr())
+        frame = fb.cpu().numpy().astype(np.float16)              # the frame holds half values widened to float: exact
+        assert st["paths"] == nx * ny * ns and np.array_equal(frame.astype(np.float32), fb.cpu().numpy())
+        gsub = np.load(os.path.join(golden_dir, "ref_cuda", man["subsample"]))
+        assert np.array_equal(subsample16(frame).view(np.uint16), gsub.view(np.uint16))
+        d = digest(frame)
+        assert d["sha256_raw"] == man["sha256_raw"], d
+        assert d["sha256_i32_ppm_order"] == man["sha256_i32_ppm_order"]
+    finally:
+        rt.create_world(488, 0.1)                                 # leave the shared context in FP32
+        rt.build_octree(30)
+
+
+def test_one_million_spheres_default_kernel_matches_oracle(rt, pkg, O):
+    """BASELINE config 5's scene (1 M spheres, SPHERES_PER_LEAF 3000) through the AUTOMATIC kernel choice (the warp-cooperative
+    kernel, four candidates per lane at this list length): a small frame and a window of the 8K frame against the oracle, and
+    individual closest hits (sphere index and t) for random rays."""
+    n, spl = 1000000, 3000
+    rt.create_world(n, 0.1)
+    rt.build_octree(spl)
+    sph, _ = O.create_world(n)
+    blob, _ = O.build_octree(sph, spl)
+    fb, s = rt.render(96, 54, 2, use_octree=True)
+    assert s["kernel"].startswith("k_render_coop")
+    ref, _, ctr = O.render(sph, O.camera(96, 54, O.ARITH_DEVICE), O.make_params(96, 54, 2, True, spl, O.ARITH_DEVICE), blob)
+    assert _frac_identical(fb, ref) >= 1 - POWF_ALLOWANCE and abs(int(s["rays"]) - ctr["rays"]) <= 2
+    # a window of the full 7680x4320 frame (camera rays of the real configuration: a finer pixel grid over the same carpet)
+    import torch
+    nx, ny, ns = 7680, 4320, 1
+    big = torch.empty((ny, nx, 3), dtype=torch.float32, device="cuda")
+    rt.render_device(rt.args(nx, ny, ns, True), big.data_ptr())
+    i0, i1, j0, j1 = 3800, 3864, 1500, 1508
+    ref, _, _ = O.render(sph, O.camera(nx, ny, O.ARITH_DEVICE), O.make_params(nx, ny, ns, True, spl, O.ARITH_DEVICE, window=(i0, i1, j0, j1)), blob)
+    got = big[j0:j1, i0:i1].cpu().numpy()
+    assert _frac_identical(got, ref[j0:j1, i0:i1]) >= 1 - 2.0 / got[..., 0].size
+    # per-ray closest hits
+    rr = np.random.default_rng(5)
+    R = 600
+    org = np.stack([rr.uniform(-12, 13, R), rr.uniform(0.02, 2.5, R), rr.uniform(-12, 12, R)], 1).astype(np.float32)
+    dirs = rr.normal(size=(R, 3)).astype(np.float32)
+    gi, gt = rt.trace_rays(org, dirs, True)
+    for k in range(R):
+        oi, ot = O.closest_hit(sph, org[k], dirs[k], blob, spl, True)
+        assert oi == gi[k] and (oi < 0 or np.float32(ot) == gt[k]), (k, oi, ot, gi[k], gt[k])
