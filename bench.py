@@ -196,14 +196,17 @@ def measure_e2e(pkg, mg, rt, torch, dist, dev, rank, world, mode, prec, n, spl, 
             host = mg.SharedHostFrame(name, nx * ny * 12, False, torch)
         frame.attach_host(host)
     rays, secs = 0.0, 0.0
+    phases = [0.0, 0.0, 0.0]           # rank 0's host clock: scene upload, octree build, render + exchange + copy-out
     for k in range(steps + 1):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         rt.upload_world(spheres)
+        ta = time.perf_counter()
         if octree:
             rt.build_octree(spl, prec)
+        tb = time.perf_counter()
         if world == 1:
             a = rt.args(nx, ny, ns, octree, precision=prec)
             stt = pkg.RenderStats()
@@ -213,9 +216,12 @@ def measure_e2e(pkg, mg, rt, torch, dist, dev, rank, world, mode, prec, n, spl, 
             st = mg.render_sharded(rt, frame, ns, bool(octree), mode, dist, want_stats=True, to_host=True)
             r = float(st["rays"])
         torch.cuda.synchronize()
+        tc = time.perf_counter()
         if world > 1:
             dist.barrier()
         dt = time.perf_counter() - t0
+        if k > 0:
+            phases[0] += ta - t0; phases[1] += tb - ta; phases[2] += tc - tb
         if world > 1:
             t = torch.tensor([r], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.SUM)
@@ -245,6 +251,8 @@ def measure_e2e(pkg, mg, rt, torch, dist, dev, rank, world, mode, prec, n, spl, 
         host.close()
     return {"value": rays / secs / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": int(n * 36) * world,
             "d2h_bytes_per_step": int(nx * ny * 12 + 40), "ms_per_step": 1e3 * secs / steps, "frame_check": check,
+            "phases_ms_rank0": {"scene_upload": 1e3 * phases[0] / steps, "octree_build": 1e3 * phases[1] / steps,
+                                "render_exchange_copy": 1e3 * phases[2] / steps},
             "includes": "per rank: scene upload + GPU octree build + render of its shard; one reduce-scatter; /ns + sqrt and the copy of every "
                         "rank's slice into one pinned host frame"}
 

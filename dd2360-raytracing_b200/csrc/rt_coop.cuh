@@ -279,9 +279,12 @@ __device__ __forceinline__ Hit coop_trace_tree(WarpShared &ws, const SceneView &
     return h;
 }
 
-template <int MINB, int ITEMS>
+// PARK: the pixel state a lane does not need while its warp traces (RNG stream, attenuation, colour sum, pixel bookkeeping:
+// 16 words) waits in shared memory during coop_trace instead of being spilled to local memory by the register allocator.
+template <int MINB, int ITEMS, bool PARK>
 __global__ void __launch_bounds__(kRenderThreads, MINB) k_render_coop(const __grid_constant__ RenderLaunch p) {
     __shared__ WarpShared wsh[kRenderThreads / 32];
+    __shared__ uint32_t park[PARK ? 16 : 1][kRenderThreads];
     WarpShared &ws = wsh[threadIdx.x >> 5];
     const SceneView sc = p.scene;
     const unsigned lane = threadIdx.x & 31u;
@@ -332,8 +335,22 @@ __global__ void __launch_bounds__(kRenderThreads, MINB) k_render_coop(const __gr
             npaths++;
         }
         if (has) nrays++;
+        if (PARK) {
+            const unsigned t = threadIdx.x;
+            park[0][t] = rng.d; park[1][t] = rng.v0; park[2][t] = rng.v1; park[3][t] = rng.v2; park[4][t] = rng.v3; park[5][t] = rng.v4;
+            park[6][t] = __float_as_uint(att.x); park[7][t] = __float_as_uint(att.y); park[8][t] = __float_as_uint(att.z);
+            park[9][t] = __float_as_uint(col.x); park[10][t] = __float_as_uint(col.y); park[11][t] = __float_as_uint(col.z);
+            park[12][t] = (uint32_t)pi; park[13][t] = (uint32_t)pj; park[14][t] = (uint32_t)s; park[15][t] = (uint32_t)depth;
+        }
         __syncwarp();
         const Hit h = coop_trace_tree<ITEMS>(ws, sc, p.tree, &p.tree.planes[0][0], lane, has, o, d, tc);
+        if (PARK) {
+            const unsigned t = threadIdx.x;
+            rng.d = park[0][t]; rng.v0 = park[1][t]; rng.v1 = park[2][t]; rng.v2 = park[3][t]; rng.v3 = park[4][t]; rng.v4 = park[5][t];
+            att = mk(__uint_as_float(park[6][t]), __uint_as_float(park[7][t]), __uint_as_float(park[8][t]));
+            col = mk(__uint_as_float(park[9][t]), __uint_as_float(park[10][t]), __uint_as_float(park[11][t]));
+            pi = (int)park[12][t]; pj = (int)park[13][t]; s = (int)park[14][t]; depth = (int)park[15][t];
+        }
         if (has) {   // ---- one iteration of color()'s loop (main.cu:47-73) ----
             bool sample_done = false;
             vec3f contrib = mk(0, 0, 0);
@@ -413,9 +430,9 @@ __global__ void __launch_bounds__(kRenderThreads) k_trace_rays_coop(const __grid
     if (has) { out_idx[i] = h.idx; out_t[i] = h.t; }
 }
 
-template <int MINB, int ITEMS>
+template <int MINB, int ITEMS, bool PARK = false>
 static cudaError_t launch_coop(const RenderLaunch &p, int sm_count, cudaStream_t st, int *blocks_out) {
-    auto kern = k_render_coop<MINB, ITEMS>;
+    auto kern = k_render_coop<MINB, ITEMS, PARK>;
     int per_sm = 0;
     cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kRenderThreads, 0);
     if (e != cudaSuccess) return e;

@@ -18,6 +18,10 @@
 #include <cub/cub.cuh>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
+
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <limits.h>
 #include <stdio.h>
 #include <string.h>
@@ -390,8 +394,21 @@ OctreeBuilder::~OctreeBuilder() {
     for (void *p : ptrs) if (p) cudaFree(p);
 }
 
+// RT_BUILD_TRACE=1: host wall clock at the build's synchronisation points (diagnostic, stderr)
+struct BuildTrace {
+    bool on;
+    std::chrono::steady_clock::time_point t0;
+    BuildTrace() : on(getenv("RT_BUILD_TRACE") != nullptr), t0(std::chrono::steady_clock::now()) {}
+    void mark(const char *what) {
+        if (!on) return;
+        const double us = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count();
+        fprintf(stderr, "[build] %-28s %9.1f us\n", what, us);
+    }
+};
+
 cudaError_t OctreeBuilder::build(cudaStream_t st, const float4 *geom, const int *tag, int n, int spl_, float density, bool fp16_,
                                  bool all_spheres_) {
+    BuildTrace trace;
     spl = spl_;
     fp16 = fp16_;
     all_spheres = all_spheres_;
@@ -423,7 +440,9 @@ cudaError_t OctreeBuilder::build(cudaStream_t st, const float4 *geom, const int 
     cub::DeviceScan::ExclusiveSum(d.cub_tmp, tmp, d.ent_count, d.ent_off, n + 1, st);
     uint32_t E_h = 0;
     RT_CUDA(cudaMemcpyAsync(&E_h, d.ent_off + n, 4, cudaMemcpyDeviceToHost, st));
+    trace.mark("classify+scan issued");
     RT_CUDA(cudaStreamSynchronize(st));
+    trace.mark("sync 1 (entry count)");
     E = E_h;
     RT_CUDA(ensure(d.keys, cap.keys, (size_t)E + 1));
     RT_CUDA(ensure(d.vals, cap.vals, (size_t)E + 1));
@@ -454,7 +473,9 @@ cudaError_t OctreeBuilder::build(cudaStream_t st, const float4 *geom, const int 
     RT_CUDA(cudaMemcpyAsync(&prep, d.prep, sizeof prep, cudaMemcpyDeviceToHost, st));
     RT_CUDA(cudaMemcpyAsync(&counts, d.counts, sizeof counts, cudaMemcpyDeviceToHost, st));
     RT_CUDA(cudaMemcpyAsync(stats_h, d.stats, 4 * 8, cudaMemcpyDeviceToHost, st));
+    trace.mark("sort..grid_prep issued");
     RT_CUDA(cudaStreamSynchronize(st));
+    trace.mark("sync 2 (counts, grid box)");
     nbig = (int)(prep.nbig < (uint32_t)kMaxBig ? prep.nbig : (uint32_t)kMaxBig);
     std::sort(prep.big, prep.big + nbig);       // ascending: deterministic traversal order
     prolog_h[0] = 0;
@@ -478,7 +499,9 @@ cudaError_t OctreeBuilder::build(cudaStream_t st, const float4 *geom, const int 
         cub::DeviceScan::ExclusiveSum(d.cub_tmp, tmp, d.vox_count, d.vox_start, (int)V + 1, st);
         uint32_t R_h = 0;
         RT_CUDA(cudaMemcpyAsync(&R_h, d.vox_start + V, 4, cudaMemcpyDeviceToHost, st));
+        trace.mark("vox count pass issued");
         RT_CUDA(cudaStreamSynchronize(st));
+        trace.mark("sync 3 (reference count)");
         total_refs = R_h;
         RT_CUDA(ensure(d.vox_refs, cap.vox_refs, (size_t)total_refs + 1));
         RT_CUDA(cudaMemsetAsync(d.vox_count, 0, ((size_t)V + 2) * 4, st));
@@ -495,6 +518,7 @@ cudaError_t OctreeBuilder::build(cudaStream_t st, const float4 *geom, const int 
     grid.ref_geom = d.ref_geom;
     built = true;
     n_spheres = n;
+    trace.mark("fill passes issued (async)");
     return cudaSuccess;
 }
 

@@ -315,11 +315,16 @@ cudaError_t launch_render_half(const RenderLaunch &p, bool octree, const uint2 *
 cudaError_t build_half_pairs(HalfPairs &hp, const uint2 *geom_h, const int *tag, int n, bool octree, const TreeView &tv, cudaStream_t st) {
     const int lists = octree ? kCells : 1;
     cudaError_t e;
-    if (!hp.count) {
-        if ((e = cudaMalloc(&hp.count, (kCells + 1) * 4)) != cudaSuccess) return e;
-        if ((e = cudaMalloc(&hp.start, (kCells + 2) * 4)) != cudaSuccess) return e;
-        if ((e = cudaMalloc(&hp.nodes, (8 + 64 + 512) * sizeof(uint2))) != cudaSuccess) return e;
-        if ((e = cudaMalloc(&hp.node_count, (4 + 64 + 8) * 4)) != cudaSuccess) return e;
+    if (!hp.count || !hp.start || !hp.nodes || !hp.node_count) {      // all four or none: a partial failure is rolled back
+        cudaFree(hp.count); cudaFree(hp.start); cudaFree(hp.nodes); cudaFree(hp.node_count);
+        hp.count = hp.start = nullptr; hp.nodes = nullptr; hp.node_count = nullptr;
+        if ((e = cudaMalloc(&hp.count, (kCells + 1) * 4)) != cudaSuccess || (e = cudaMalloc(&hp.start, (kCells + 2) * 4)) != cudaSuccess ||
+            (e = cudaMalloc(&hp.nodes, (8 + 64 + 512) * sizeof(uint2))) != cudaSuccess ||
+            (e = cudaMalloc(&hp.node_count, (4 + 64 + 8) * 4)) != cudaSuccess) {
+            cudaFree(hp.count); cudaFree(hp.start); cudaFree(hp.nodes); cudaFree(hp.node_count);
+            hp.count = hp.start = nullptr; hp.nodes = nullptr; hp.node_count = nullptr;
+            return e;
+        }
     }
     if (octree) h16::k_fp16_nodes<<<1, 1, 0, st>>>(tv.cell_start, hp.nodes, hp.node_count);
     h16::k_pairs_count<<<(lists + 127) / 128, 128, 0, st>>>(tag, n, lists, tv.cell_start, tv.cell_list, tv.cell_cap, hp.count);
@@ -327,18 +332,24 @@ cudaError_t build_half_pairs(HalfPairs &hp, const uint2 *geom_h, const int *tag,
     uint32_t total = 0;
     if ((e = cudaMemcpyAsync(&total, hp.start + lists, 4, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return e;
     if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return e;
+    hp.valid = false;                           // until the lists are rebuilt: a failure below must not leave stale lists marked usable
     if (total + 1 > hp.cap) {
         cudaFree(hp.geom); cudaFree(hp.idx);
         hp.geom = nullptr; hp.idx = nullptr; hp.cap = 0;
         if ((e = cudaMalloc(&hp.geom, ((size_t)total + 1) * sizeof(uint4))) != cudaSuccess) return e;
-        if ((e = cudaMalloc(&hp.idx, ((size_t)total + 1) * sizeof(int2))) != cudaSuccess) return e;
+        if ((e = cudaMalloc(&hp.idx, ((size_t)total + 1) * sizeof(int2))) != cudaSuccess) {
+            cudaFree(hp.geom);
+            hp.geom = nullptr;
+            return e;
+        }
         hp.cap = (size_t)total + 1;
     }
     h16::k_pairs_fill<<<(lists + 127) / 128, 128, 0, st>>>(geom_h, tag, n, lists, tv.cell_start, tv.cell_list, tv.cell_cap, hp.start, hp.geom, hp.idx);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
     hp.pairs = total;
     hp.octree = octree;
     hp.valid = true;
-    return cudaGetLastError();
+    return cudaSuccess;
 }
 
 // Closest hit for caller-supplied rays (test hook: per-ray parity against the oracle's hitTree / hitable_list::hit)
@@ -480,6 +491,11 @@ cudaError_t launch_render(const RenderLaunch &p, bool octree, int sm_count, size
             case 44: return coop::launch_coop<6, 1>(p, sm_count, st, blocks_out);     // one candidate per lane and chunk step
             case 45: return coop::launch_coop<6, 4>(p, sm_count, st, blocks_out);     // four
             case 46: return coop::launch_coop<5, 4>(p, sm_count, st, blocks_out);
+            case 47: return coop::launch_coop<6, 2, true>(p, sm_count, st, blocks_out);      // A/B: idle pixel state parked in shared memory
+            case 48: return coop::launch_coop<7, 2, true>(p, sm_count, st, blocks_out);
+            case 49: return coop::launch_coop<8, 2, true>(p, sm_count, st, blocks_out);
+            case 50: return coop::launch_coop<6, 4, true>(p, sm_count, st, blocks_out);
+            case 51: return coop::launch_coop<7, 4, true>(p, sm_count, st, blocks_out);
             default: break;
         }
         // automatic choice by scene size (measured on B200, profiles/README.md r02f): the pixel-per-lane walk for small scenes
@@ -488,8 +504,9 @@ cudaError_t launch_render(const RenderLaunch &p, bool octree, int sm_count, size
         if (p.variant != 1 && p.scene.n >= kCoopMinSpheres) {
             which = kKernelCoop;
             // four candidates per lane once voxel lists are long (C5: 71 references per voxel, +4 %; C3: 13 per voxel, -6 %)
-            if (p.coop_items == 4) return coop::launch_coop<6, 4>(p, sm_count, st, blocks_out);
-            return coop::launch_coop<6, 2>(p, sm_count, st, blocks_out);
+            // (7 blocks per SM with the idle pixel state parked in shared memory: -6 % over 6 blocks without, profiles r02r)
+            if (p.coop_items == 4) return coop::launch_coop<7, 4, true>(p, sm_count, st, blocks_out);
+            return coop::launch_coop<7, 2, true>(p, sm_count, st, blocks_out);
         }
         which = kKernelLane;
         return launch_variant<true, false>(p, 0, sm_count, st, blocks_out);
