@@ -284,7 +284,7 @@ __device__ __forceinline__ Hit coop_trace_tree(WarpShared &ws, const SceneView &
 template <int MINB, int ITEMS, bool PARK>
 __global__ void __launch_bounds__(kRenderThreads, MINB) k_render_coop(const __grid_constant__ RenderLaunch p) {
     __shared__ WarpShared wsh[kRenderThreads / 32];
-    __shared__ uint32_t park[PARK ? 16 : 1][kRenderThreads];
+    __shared__ uint32_t park[PARK ? 21 : 1][kRenderThreads];
     WarpShared &ws = wsh[threadIdx.x >> 5];
     const SceneView sc = p.scene;
     const unsigned lane = threadIdx.x & 31u;
@@ -341,6 +341,7 @@ __global__ void __launch_bounds__(kRenderThreads, MINB) k_render_coop(const __gr
             park[6][t] = __float_as_uint(att.x); park[7][t] = __float_as_uint(att.y); park[8][t] = __float_as_uint(att.z);
             park[9][t] = __float_as_uint(col.x); park[10][t] = __float_as_uint(col.y); park[11][t] = __float_as_uint(col.z);
             park[12][t] = (uint32_t)pi; park[13][t] = (uint32_t)pj; park[14][t] = (uint32_t)s; park[15][t] = (uint32_t)depth;
+            park[16][t] = (uint32_t)pix; park[17][t] = nrays; park[18][t] = npaths; park[19][t] = stock_next; park[20][t] = stock_end;
         }
         __syncwarp();
         const Hit h = coop_trace_tree<ITEMS>(ws, sc, p.tree, &p.tree.planes[0][0], lane, has, o, d, tc);
@@ -350,8 +351,11 @@ __global__ void __launch_bounds__(kRenderThreads, MINB) k_render_coop(const __gr
             att = mk(__uint_as_float(park[6][t]), __uint_as_float(park[7][t]), __uint_as_float(park[8][t]));
             col = mk(__uint_as_float(park[9][t]), __uint_as_float(park[10][t]), __uint_as_float(park[11][t]));
             pi = (int)park[12][t]; pj = (int)park[13][t]; s = (int)park[14][t]; depth = (int)park[15][t];
+            pix = (int)park[16][t]; nrays = park[17][t]; npaths = park[18][t]; stock_next = park[19][t]; stock_end = park[20][t];
+            const float4 ro = ws.ro[lane], rd = ws.rd[lane];          // the ray itself is still where coop_trace published it
+            o = mk(ro.x, ro.y, ro.z); d = mk(rd.x, rd.y, rd.z);
         }
-        if (has) {   // ---- one iteration of color()'s loop (main.cu:47-73) ----
+        if (pix >= 0) {   // ---- one iteration of color()'s loop (main.cu:47-73) ----
             bool sample_done = false;
             vec3f contrib = mk(0, 0, 0);
             if (h.idx >= 0) {

@@ -496,6 +496,7 @@ cudaError_t launch_render(const RenderLaunch &p, bool octree, int sm_count, size
             case 49: return coop::launch_coop<8, 2, true>(p, sm_count, st, blocks_out);
             case 50: return coop::launch_coop<6, 4, true>(p, sm_count, st, blocks_out);
             case 51: return coop::launch_coop<7, 4, true>(p, sm_count, st, blocks_out);
+            case 52: return coop::launch_coop<8, 4, true>(p, sm_count, st, blocks_out);
             default: break;
         }
         // automatic choice by scene size (measured on B200, profiles/README.md r02f): the pixel-per-lane walk for small scenes
@@ -504,9 +505,9 @@ cudaError_t launch_render(const RenderLaunch &p, bool octree, int sm_count, size
         if (p.variant != 1 && p.scene.n >= kCoopMinSpheres) {
             which = kKernelCoop;
             // four candidates per lane once voxel lists are long (C5: 71 references per voxel, +4 %; C3: 13 per voxel, -6 %)
-            // (7 blocks per SM with the idle pixel state parked in shared memory: -6 % over 6 blocks without, profiles r02r)
-            if (p.coop_items == 4) return coop::launch_coop<7, 4, true>(p, sm_count, st, blocks_out);
-            return coop::launch_coop<7, 2, true>(p, sm_count, st, blocks_out);
+            // (8 / 7 blocks per SM with the idle pixel state parked in shared memory: -9 % over 6 blocks without, profiles r02r-r02t)
+            if (p.coop_items == 4) return coop::launch_coop<8, 4, true>(p, sm_count, st, blocks_out);
+            return coop::launch_coop<8, 2, true>(p, sm_count, st, blocks_out);
         }
         which = kKernelLane;
         return launch_variant<true, false>(p, 0, sm_count, st, blocks_out);
