@@ -29,6 +29,33 @@ WORKER = textwrap.dedent("""
     mg.reduce_frame(part, dist)
     if rank == 0:
         assert np.array_equal(part.numpy().view(np.uint32), full.view(np.uint32)), "tile shards do not sum to the frame"
+    # the path's one collective as bench.py runs it: reduce-scatter of the padded linear buffer, every rank finalises its own
+    # slice and writes it into ONE host frame shared by the ranks (POSIX shared memory); 3 ranks' worth of padding is exercised
+    # by a frame whose element count is odd
+    total = nx * ny * 3
+    S = mg.slice_elems(total, world)
+    padded = torch.zeros(S * world, dtype=torch.float32)
+    padded[:total] = torch.from_numpy(np.where((owner == rank)[..., None], full, 0.0).astype(np.float32)).reshape(-1)
+    mine = torch.empty(S, dtype=torch.float32)
+    mg.reduce_scatter_frame(padded, mine, dist)
+    b, e = mg.slice_range(total, rank, world)
+    assert (b, e) == (rank * S, min((rank + 1) * S, total))
+    assert np.array_equal(mine.numpy()[: e - b].view(np.uint32), full.reshape(-1)[b:e].view(np.uint32)), "reduce-scatter slice differs"
+    name = "rt_b200_test_%(port)d"
+    if rank == 0:
+        host = mg.SharedHostFrame(name, total * 4, True, torch)
+    dist.barrier()
+    if rank != 0:
+        host = mg.SharedHostFrame(name, total * 4, False, torch)
+    fin = np.sqrt(mine.numpy()[: e - b] * np.float32(1.0 / ns)).astype(np.float32)       # /ns and sqrt of the slice (main.cu:111-114)
+    host.tensor[b:e].copy_(torch.from_numpy(fin))
+    dist.barrier()
+    if rank == 0:
+        want = np.sqrt(full.reshape(-1) * np.float32(1.0 / ns)).astype(np.float32)
+        assert np.array_equal(host.array.view(np.uint32), want.view(np.uint32)), "the shared host frame is not the finalised frame"
+    dist.barrier()
+    host.close()
+    assert mg.slice_elems(7, 3) == 3 and mg.slice_range(7, 2, 3) == (6, 7) and mg.slice_range(7, 1, 3) == (3, 6)
     # spp shares add up and differ by at most one
     shares = [mg.spp_share(7, r, world) for r in range(world)]
     assert sum(shares) == 7 and max(shares) - min(shares) <= 1
