@@ -134,12 +134,14 @@ def ref_cuda_leg(cfg: str, rays_at_live_spp: float, rays_full: float, budget_s: 
         out["live"] = {"error": "binary not built (make -C oracle ref_cuda needs /root/reference)"}
         return out
     if budget_s < 150:
-        out["live"] = {"skipped": f"only {budget_s:.0f} s of the bench's time budget left; the run needs ~130 s"}
+        out["live"] = {"skipped": f"only {budget_s:.0f} s of the bench's time budget left; the run needs ~125 s (create_world alone ~115 s)"}
         return out
     sampler = ClockSampler(int(os.environ.get("LOCAL_RANK", "0")))
     sampler.start()
     try:
-        r = subprocess.run([exe, str(nx), str(ny), str(REF_CUDA_LIVE_SPP)], capture_output=True, text=True, timeout=min(budget_s, 240))
+        # (--reps 1 --no-free: the reference's free_world deletes 100 k materials from one device thread, another ~90 s)
+        r = subprocess.run([exe, str(nx), str(ny), str(REF_CUDA_LIVE_SPP), "--reps", "1", "--no-free"], capture_output=True, text=True,
+                           timeout=min(budget_s, 170))
         rec = json.loads(r.stdout.strip().splitlines()[-1])
         out["live"] = {"spp": REF_CUDA_LIVE_SPP, "render_ms": rec["render_ms"], "create_world_ms": rec["create_world_ms"],
                        "mrays_s": rays_at_live_spp / rec["render_ms"] / 1e3 if rays_at_live_spp else None,

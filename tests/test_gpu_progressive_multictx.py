@@ -289,3 +289,22 @@ def test_dropin_octree_hit_scatter_and_get_ray_members(rt, pkg, O, tmp_path):
         f = out[1 + Q + k].split()
         assert [np.float32(float.fromhex(x)) for x in f[0:3]] == list(co[k]) and [np.float32(float.fromhex(x)) for x in f[3:6]] == list(cd[k])
         assert np.linalg.norm(co[k] - np.array([13, 2, 3], np.float32)) <= 0.05 + 1e-5       # inside the lens disk
+
+
+@pytest.mark.skipif(_multi_gpu_count() < 2, reason="needs two GPUs (gpurun --gpus 2)")
+def test_torch_distributed_nccl_frame_equals_the_one_gpu_frame():
+    """multigpu.render_sharded over torch.distributed / NCCL, two ranks (what `bench.py --gpus 2` runs): render on torch's current
+    stream, reduce-scatter, per-rank finalise, slices copied into the shared pinned host frame — all without host synchronisation in
+    between (round 1 raced here).  With tile shards the assembled frame must be the 1-GPU frame bit for bit; bench.py checks it."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port", "29577",
+           os.path.join(root, "bench.py"), "--gpus", "2", "--steps", "2", "--warmup", "3", "--config", "C2", "--shard", "tiles", "--no-cpu-baseline"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
+    chk = line["e2e"]["frame_check"]
+    assert line["n_gpus"] == 2 and chk["sharding"] == "tiles" and chk["identical_to_1gpu_frame"] is True, chk
