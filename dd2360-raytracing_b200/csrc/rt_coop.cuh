@@ -11,7 +11,7 @@
 // candidate tests of the warp's 32 rays are pooled:
 //   round   : every walking lane publishes the reference range of its CURRENT voxel; an inclusive warp scan lays the
 //             ranges end to end (a flat list of `total` (ray, reference) items);
-//   chunks  : 32 items at a time, item -> owner lane by a REDUX.OR of the segment starts + one CLZ; the lane reads the
+//   chunks  : 32 items at a time, item -> owner lane by a REDUX.OR of the segment ends + one POPC into a table of the lanes that have items; the lane reads the
 //             owner's ray from shared memory, one float4 of list-order geometry from L1/L2 and runs the conservative root
 //             pre-filter (maybe_hit) against the owner's current closest hit.  Trip count is warp-uniform: total / 32;
 //   ring    : candidates that pass (1.3 per ray at config 3) are appended to a per-warp ring in shared memory by
@@ -48,7 +48,7 @@ struct __align__(16) WarpShared {
     uint32_t best_t[32];             // closest hit so far: float bits of t (positive floats order like their bits) ...
     uint32_t best_i[32];             // ... and its sphere index (0xffffffff: none); provisional among equal t (the smallest seen)
     uint32_t tie[32];                // 1: two DIFFERENT spheres share best_t — finish_hit ranks them in the reference's order
-    uint32_t slot[32];               // chunk position of a segment start -> owner lane
+    uint32_t slot[32];               // the lanes that have items this round, in lane order (item -> owner lookup)
     uint2 ring[kRing];               // {owner lane, reference}
 };
 
@@ -98,14 +98,19 @@ __device__ __forceinline__ float drain(WarpShared &ws, const SceneView &sc, cons
 template <int N>
 __device__ __forceinline__ void push_n(WarpShared &ws, const SceneView &sc, const TreeView &tv, const unsigned lane, const uint32_t pass,
                                        const uint32_t owner, const uint32_t ref, int &count) {
-    if (!__any_sync(kFull, pass != 0u)) return;
+    unsigned m[N];
+    unsigned any = 0u;
+#pragma unroll
+    for (int j = 0; j < N; j++) {
+        m[j] = __ballot_sync(kFull, (pass >> j) & 1u);
+        any |= m[j];
+    }
+    if (!any) return;
     const unsigned lt = (1u << lane) - 1u;
 #pragma unroll
     for (int j = 0; j < N; j++) {
-        const bool pj = (pass >> j) & 1u;
-        const unsigned m = __ballot_sync(kFull, pj);
-        if (pj) ws.ring[count + __popc(m & lt)] = make_uint2(owner, ref + (uint32_t)j);
-        count += __popc(m);
+        if ((pass >> j) & 1u) ws.ring[count + __popc(m[j] & lt)] = make_uint2(owner, ref + (uint32_t)j);
+        count += __popc(m[j]);
     }
     __syncwarp();
     while (count >= 32) {
@@ -128,6 +133,7 @@ __device__ __forceinline__ Hit coop_trace(WarpShared &ws, const SceneView &sc, c
     __syncwarp();
     ws.ro[lane] = make_float4(o.x, o.y, o.z, a);
     ws.rd[lane] = make_float4(d.x, d.y, d.z, ia);
+    ws.slot[lane] = lane;                   // (entries past this round's owners are read by lanes without an item: keep them lane ids)
     float best_t = kTMax;
     {   // ground sphere first, unconditionally (acceleration_structure.h:322-332)
         uint32_t idx = 0xffffffffu;
@@ -216,19 +222,22 @@ __device__ __forceinline__ Hit coop_trace(WarpShared &ws, const SceneView &sc, c
         const uint32_t excl = incl - mine;
         ws.meta[lane].koff = (int)k - ITEMS * (int)excl;
         ws.meta[lane].kend = (int)(k + cnt);
+        // the lanes that have items, in lane order (= item order): slot[j] is the j-th of them
+        const unsigned lt = (1u << lane) - 1u;
+        const unsigned nz = __ballot_sync(kFull, mine > 0u);
+        if (mine > 0u) ws.slot[__popc(nz & lt)] = lane;
         __syncwarp();
 
+        uint32_t r0 = 0u;                       // rank in slot[] of the owner of item `base`
         for (uint32_t base = 0; base < total; base += 32u) {
-            // segment starts inside this chunk: a lane owns items [max(excl, base), min(incl, base + 32))
-            const uint32_t s_pos = excl > base ? excl : base;
-            const uint32_t e_pos = incl < base + 32u ? incl : base + 32u;
-            const bool owns = s_pos < e_pos;
-            if (owns) ws.slot[s_pos - base] = lane;
-            const unsigned starts = __reduce_or_sync(kFull, owns ? 1u << (s_pos - base) : 0u);
-            __syncwarp();
+            // a lane's last item is incl - 1: the segment ENDS inside this chunk are OR-reduced into one mask (REDUX); the owner of
+            // item base + i is r0 + (ends before position i) lanes down the table; r0 moves on by the ends of the chunk
+            const bool ends_here = mine > 0u && incl > base && incl <= base + 32u;
+            const unsigned ends = __reduce_or_sync(kFull, ends_here ? 1u << (incl - 1u - base) : 0u);
             const uint32_t item = base + lane;
             const bool valid = item < total;
-            const uint32_t owner = ws.slot[31 - __clz(starts & (0xffffffffu >> (31u - lane)))];   // bit 0 is always a start
+            const uint32_t owner = ws.slot[(r0 + (uint32_t)__popc(ends & lt)) & 31u];
+            r0 += (uint32_t)__popc(ends);
             const float4 ro = ws.ro[owner], rd = ws.rd[owner];
             const RayMeta mt = ws.meta[owner];
             const uint32_t ref = (uint32_t)(mt.koff + ITEMS * (int)item);
@@ -250,7 +259,6 @@ __device__ __forceinline__ Hit coop_trace(WarpShared &ws, const SceneView &sc, c
                 // are positive); its exact evaluation waits in the ring until 32 candidates are queued
                 if (ub < mt.bound) atomicMin(reinterpret_cast<uint32_t *>(&ws.meta[owner].bound), __float_as_uint(ub));
             }
-            __syncwarp();                       // slot[] is rewritten by the next chunk
             push_n<ITEMS>(ws, sc, tv, lane, pass, owner, ref, count);
         }
         __syncwarp();
