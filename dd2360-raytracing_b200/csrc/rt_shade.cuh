@@ -77,18 +77,20 @@ RT_HD float schlick(const float cosine, const float ref_idx) {
 // Returns false when the ray is absorbed (metal only).
 RT_HD bool scatter(const int tag, const float4 m, const vec3f d_in, const vec3f p, const vec3f n, vec3f &atten,
                    vec3f &d_out, xorwow &rng) {
-    if (tag == 0) {  // lambertian: target = p + normal + r; direction = target - p (not simplified)
+    if (tag <= 1) {
+        // lambertian and metal both begin their draws with random_in_unit_sphere (metal's reflect() draws nothing), so ONE
+        // rejection loop serves the lanes of both materials: as separate branches the warp ran the loop twice, each time until
+        // its slowest lane was done (~5 rounds of 3 draws for a dozen lanes)
         const vec3f r = random_in_unit_sphere(rng);
-        const vec3f target = mk(add_(add_(p.x, n.x), r.x), add_(add_(p.y, n.y), r.y), add_(add_(p.z, n.z), r.z));
-        d_out = mk(sub_(target.x, p.x), sub_(target.y, p.y), sub_(target.z, p.z));
         atten = mk(m.x, m.y, m.z);
-        return true;
-    }
-    if (tag == 1) {  // metal: draws even when fuzz == 0
+        if (tag == 0) {  // lambertian: target = p + normal + r; direction = target - p (not simplified)
+            const vec3f target = mk(add_(add_(p.x, n.x), r.x), add_(add_(p.y, n.y), r.y), add_(add_(p.z, n.z), r.z));
+            d_out = mk(sub_(target.x, p.x), sub_(target.y, p.y), sub_(target.z, p.z));
+            return true;
+        }
+        // metal: draws even when fuzz == 0
         const vec3f refl = reflect(unit_vector(d_in), n);
-        const vec3f r = random_in_unit_sphere(rng);
         d_out = mk(fma_(m.w, r.x, refl.x), fma_(m.w, r.y, refl.y), fma_(m.w, r.z, refl.z));
-        atten = mk(m.x, m.y, m.z);
         return dot3(d_out, n) > 0.0f;
     }
     // dielectric
