@@ -1,0 +1,6 @@
+# r02y: final evidence at HEAD: smoke(), ncu launch list of the bench command, --set full at the bench configuration, the default bench line
+timeout 300 python -c "import __graft_entry__ as e; e.smoke()" > gpurun_out/r02y_smoke.log 2>&1; tail -4 gpurun_out/r02y_smoke.log | cut -c1-250
+CMD="python bench.py --steps 2 --warmup 3 --no-ref-cuda --no-cpu-baseline"
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r02y_launches_bench_c3.csv $CMD > gpurun_out/r02y_ncu_launches.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_render_coop -s 1 -c 1 -o gpurun_out/r02y_coop_c3_64spp -f python profiles/profile_render.py C3 64 2 > gpurun_out/r02y_ncu_full.log 2>&1; tail -1 gpurun_out/r02y_ncu_full.log
+timeout 900 python bench.py > gpurun_out/r02y_bench_c3.json 2> gpurun_out/r02y_bench_c3.err; cut -c1-200 gpurun_out/r02y_bench_c3.json; tail -2 gpurun_out/r02y_bench_c3.err
