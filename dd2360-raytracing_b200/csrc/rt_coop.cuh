@@ -10,15 +10,19 @@
 // Here the lanes still own one pixel chain each (ray, RNG and pixel state in registers, shading as in k_render), but the
 // candidate tests of the warp's 32 rays are pooled:
 //   round   : every walking lane publishes the reference range of its CURRENT voxel; an inclusive warp scan lays the
-//             ranges end to end (a flat list of `total` (ray, reference) items);
-//   chunks  : 32 items at a time, item -> owner lane by a REDUX.OR of the segment ends + one POPC into a table of the lanes that have items; the lane reads the
-//             owner's ray from shared memory, one float4 of list-order geometry from L1/L2 and runs the conservative root
-//             pre-filter (maybe_hit) against the owner's current closest hit.  Trip count is warp-uniform: total / 32;
-//   ring    : candidates that pass (1.3 per ray at config 3) are appended to a per-warp ring in shared memory by
-//             ballot/popc (no atomics: the warp is converged); whenever 32 are queued — and at the end of a round — the
-//             lanes evaluate the EXACT reference test (sphere.h:17-46, IEEE) on one entry each and fold the result into the
-//             owner's (t, sphere index) key with a 64-bit shared-memory atomicMin;
-//   advance : owners re-read their closest hit and step the 3D-DDA to their next non-empty voxel (or stop).
+//             ranges end to end (a flat list of `total` items of ITEMS consecutive references of one ray);
+//   chunks  : 32 items at a time; item -> owner lane by a REDUX.OR of the segment ends + one POPC into a table of the lanes
+//             that have items; the lane reads the owner's ray and pruning bound from shared memory, ITEMS float4 of list-order
+//             geometry from L1/L2 and runs the conservative root pre-filter (maybe_hit_ub) on them.  The trip count is
+//             warp-uniform (total / 32): no lane idles because its own ray had a short list;
+//   bounds  : when the pre-filter makes a hit CERTAIN it also bounds the accepted root from above; a native shared-memory
+//             atomicMin on the float's bits lowers the owner's pruning bound at once, so the walk and the later pre-filters
+//             prune as sharply as with exact values while the exact evaluation waits;
+//   ring    : candidates that pass (1.3 per ray at config 3) are appended to a per-warp ring in shared memory by ballot/popc
+//             (no atomics: the warp is converged); whenever 32 are queued — and at the end of the trace — the lanes evaluate
+//             the EXACT reference test (sphere.h:17-46, IEEE) on one entry each and fold (t, sphere index) into the owner's
+//             record with two native 32-bit shared-memory atomics;
+//   advance : owners re-read their bound and step the 3D-DDA to their next non-empty voxel (or stop).
 // The closest hit of hitable_list::hit / hitTree is a strict-'<' minimum over a candidate set, so it does not depend on the
 // order of evaluation; a candidate's accepted root does not depend on closest_so_far either:
 //   sphere::hit(t_max) accepts root1 if t_min < root1 < t_max, else root2 if t_min < root2 < t_max; root2 >= root1 (the

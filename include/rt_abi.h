@@ -77,7 +77,8 @@ typedef struct rt_render_args {
     int32_t precision;       /* RT_PREC_* (USE_FP16, precision_types.h:8); FP16 renders whole frames only (RT_SHARD_NONE) */
     int32_t tune[6];         /* kernel A/B and tuning knobs for measurements; 0 = defaults; they never change the image
                               * (one documented exception, variant 21).  [1] kernel variant: 1 pixel-per-lane kernel, 10-15 pooled
-                              * kernel shapes, 20 flat list as an N-test sweep, 21 visibility rule off (MEASUREMENT ONLY: same image
+                              * kernel shapes, 40-52 warp-cooperative kernel shapes (blocks per SM, candidates per lane, parked pixel
+                              * state), 20 flat list as an N-test sweep, 21 visibility rule off (MEASUREMENT ONLY: same image
                               * only when the build dropped nothing), 30 first cooperative USE_FP16 form, 31 / 32 single-pixel /
                               * tile queue, 33 per-lane USE_FP16 node walk; [2] pooled-kernel watchdog (scheduling rounds);
                               * [3], [4] TEST chunks per round and the lane count that keeps a round going; [5] TEST hold-back
