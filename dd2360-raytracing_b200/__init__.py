@@ -39,7 +39,7 @@ ABI_SYMBOLS = [
     "rt_abi_version", "rt_create", "rt_destroy", "rt_last_error", "rt_set_stream", "rt_device_info",
     "rt_scene_generate", "rt_scene_generate_ex", "rt_scene_upload", "rt_scene_download", "rt_scene_size", "rt_camera_set", "rt_camera_get", "rt_camera_get_half",
     "rt_octree_build", "rt_octree_build_ex", "rt_octree_reference_bytes", "rt_octree_export_reference", "rt_octree_debug_read", "rt_xorwow_state", "rt_debug_counters", "rt_trace_rays", "rt_camera_get_rays", "rt_scatter_rays",
-    "rt_render_accumulate", "rt_render_progressive", "rt_finalize", "rt_finalize_n", "rt_render", "rt_render_to_host", "rt_format_ppm",
+    "rt_render_accumulate", "rt_last_render_stats", "rt_render_progressive", "rt_finalize", "rt_finalize_n", "rt_render", "rt_render_to_host", "rt_format_ppm",
     "rt_ppm_format", "rt_ppm_read", "rt_render_to_ppm",
     "rt_ffma_peak", "rt_hfma2_peak", "rt_malloc", "rt_free", "rt_memcpy_to_host", "rt_synchronize", "rt_kernel_name",
     "rt_comm_get_unique_id", "rt_comm_init_rank", "rt_comm_init_all", "rt_comm_attach", "rt_comm_destroy", "rt_comm_rank", "rt_comm_size",
@@ -122,6 +122,7 @@ def load_library(path: str | None = None) -> C.CDLL:
         "rt_camera_get_rays": (i32, [vp, i32, vp, vp, vp, vp, vp]),
         "rt_scatter_rays": (i32, [vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
         "rt_render_accumulate": (i32, [vp, C.POINTER(RenderArgs), vp, C.POINTER(RenderStats)]),
+        "rt_last_render_stats": (i32, [vp, C.POINTER(RenderStats)]),
         "rt_render_progressive": (i32, [vp, C.POINTER(RenderArgs), vp, vp, i32, C.POINTER(RenderStats)]),
         "rt_finalize": (i32, [vp, vp, vp, i32, i32, i32]),
         "rt_finalize_n": (i32, [vp, vp, vp, sz, i32]),
@@ -378,6 +379,12 @@ class RayTracer:
         self._ck(self.L.rt_render_progressive(self._ctx, C.byref(args), C.c_void_p(accum_dev_ptr), C.c_void_p(state_dev_ptr), int(first),
                                               C.byref(st) if want_stats else None), "rt_render_progressive")
         return st.as_dict() if want_stats else None
+
+    def last_render_stats(self) -> dict:
+        """Statistics of the last render call made with want_stats=False (waits for the stream)."""
+        st = RenderStats()
+        self._ck(self.L.rt_last_render_stats(self._ctx, C.byref(st)), "rt_last_render_stats")
+        return st.as_dict()
 
     def finalize(self, accum_dev_ptr: int, fb_dev_ptr: int, nx, ny, ns):
         self._ck(self.L.rt_finalize(self._ctx, C.c_void_p(accum_dev_ptr), C.c_void_p(fb_dev_ptr), nx, ny, ns), "rt_finalize")

@@ -637,6 +637,26 @@ extern "C" int rt_xorwow_state(unsigned long long seed, unsigned long long subse
     return RT_OK;
 }
 
+// Statistics of the LAST render call, for callers that passed stats = NULL to keep the call asynchronous (e.g. to queue the
+// multi-GPU exchange behind the render without a host round trip in between): waits for the context's stream, then reads the
+// counters and the render's CUDA events.
+extern "C" int rt_last_render_stats(rt_context *ctx, rt_render_stats *stats) {
+    if (!ctx || !stats) return fail(ctx, RT_ERR_INVALID, "rt_last_render_stats: null argument");
+    CK(cudaSetDevice(ctx->device));
+    unsigned long long c[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    CK(cudaMemcpyAsync(c, ctx->counters, sizeof c, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    memset(stats, 0, sizeof *stats);
+    stats->rays = c[0]; stats->paths = c[1];
+    stats->sphere_tests = c[2]; stats->node_tests = c[3];
+    stats->kernel_id = ctx->last_kernel;
+    stats->launches = 1;
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) == cudaSuccess) stats->kernel_ms = ms;
+    if (c[7]) return fail(ctx, RT_ERR_STATE, "render: scheduler watchdog tripped in %llu warps", c[7]);
+    return RT_OK;
+}
+
 // test hook: the raw device counters of the last render (instrumented builds fill [8..27] with per-state scheduling data)
 extern "C" int rt_debug_counters(rt_context *ctx, uint64_t out[32]) {
     if (!ctx || !out) return fail(ctx, RT_ERR_INVALID, "rt_debug_counters: null argument");

@@ -131,11 +131,16 @@ def render_sharded(rt: RayTracer, frame: ShardedFrame, ns: int, use_octree: bool
     synchronises.  Returns the per-rank render stats (None without want_stats)."""
     world, rank = frame.world, frame.rank
     args = rt.args(frame.nx, frame.ny, ns, use_octree, shard_mode=mode if world > 1 else SHARD_NONE, shard_rank=rank, shard_count=world)
-    st = rt.render_accumulate(args, frame.accum.data_ptr(), want_stats=want_stats)
+    # the render is queued WITHOUT waiting for its statistics, so that the collective, the finalise kernel and the copy are
+    # queued right behind it (no host round trip in the middle of the frame); the statistics are read at the end
+    world_sharded = world > 1
+    st = rt.render_accumulate(args, frame.accum.data_ptr(), want_stats=want_stats and not world_sharded)
     reduce_scatter_frame(frame.accum, frame.slice, dist)
     rt.finalize_n(frame.slice.data_ptr(), frame.slice.data_ptr(), frame.S, ns)
     if to_host and frame.host is not None and frame.end > frame.begin:
         frame.host.tensor[frame.begin:frame.end].copy_(frame.slice[: frame.end - frame.begin], non_blocking=True)
+    if want_stats and world_sharded:
+        st = rt.last_render_stats()
     return st
 
 

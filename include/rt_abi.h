@@ -175,6 +175,9 @@ int rt_render_accumulate(rt_context *ctx, const rt_render_args *args, float *acc
  * (args->seed_mode) and overwrites accum_dev.  Dump a frame at any point with rt_finalize(.., samples so far).  FP32 only. */
 int rt_render_progressive(rt_context *ctx, const rt_render_args *args, float *accum_dev, uint32_t *rng_state_dev, int first,
                           rt_render_stats *stats);
+/* statistics of the last rt_render* call made with stats == NULL (the call then returns without waiting for the kernel, so a
+ * collective or a copy can be queued right behind it); waits for the context's stream */
+int rt_last_render_stats(rt_context *ctx, rt_render_stats *stats);
 /* fb = sqrt(accum * (1/ns)) per channel (main.cu:111-114); in place allowed */
 int rt_finalize(rt_context *ctx, const float *accum_dev, float *fb_dev, int nx, int ny, int ns);
 /* the same on `count` consecutive floats: a rank's slice of the frame after rt_reduce_scatter */
