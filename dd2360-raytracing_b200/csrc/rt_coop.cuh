@@ -156,6 +156,12 @@ __device__ __forceinline__ Hit coop_trace(WarpShared &ws, const SceneView &sc, c
     for (int k = 1; k < tv.nprolog; k++) {   // big spheres: one pre-filter per lane, exact tests through the ring
         const float4 s = __ldg(tv.prolog_geom + k);
         if (has) RT_COUNT(sphere_tests);
+        // most warps look nowhere near a given big sphere: the discriminant alone (the exact test's own float operations, so its
+        // sign is the exact test's) settles that for the whole warp in a dozen instructions
+        const vec3f oc = mk(sub_(o.x, s.x), sub_(o.y, s.y), sub_(o.z, s.z));
+        const float bq = dot3(oc, d);
+        const float disc = fma_(bq, bq, -mul_(a, fma_(-s.w, s.w, dot3(oc, oc))));
+        if (!__any_sync(kFull, has && disc > 0.0f)) continue;
         float ub;
         const bool pass = has && maybe_hit_ub(s, o, d, a, ia, ws.meta[lane].bound, ub);
         if (pass && ub < ws.meta[lane].bound) ws.meta[lane].bound = ub;        // (the lane's own record: no other lane touches it here)
