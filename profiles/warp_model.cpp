@@ -114,6 +114,8 @@ struct Acc {
     double b_rounds = 0, b_chunks = 0, b_lanes_round = 0;
     // design B2: rounds advance to the next NON-EMPTY voxel (empties skipped inside the advance)
     double b2_rounds = 0, b2_chunks = 0, b2_max_adv = 0;
+    // what k_render_coop does: B2 with ITEMS = 2 / 4 consecutive references per lane and chunk step
+    double c2_chunks = 0, c2_slots_used = 0, c4_chunks = 0, c4_slots_used = 0;
     // histograms
     double hist_vox[65] = {0}, hist_cands[257] = {0}, hist_trips[129] = {0};
     double shade_hit = 0, shade_sky = 0;
@@ -243,10 +245,15 @@ extern "C" int wm_run(const hs_sphere *sph, int n, const float *camera22, const 
                     }
                     a.b2_rounds += rmax;
                     for (size_t t = 0; t < rmax; t++) {
-                        int tot = 0, madv = 0;
-                        for (int l = 0; l < 32; l++) if (t < ne[l].size()) { tot += ne[l][t].first; madv = std::max(madv, ne[l][t].second + 1); }
+                        int tot = 0, madv = 0, p2 = 0, p4 = 0;
+                        for (int l = 0; l < 32; l++) if (t < ne[l].size()) {
+                            tot += ne[l][t].first; madv = std::max(madv, ne[l][t].second + 1);
+                            p2 += (ne[l][t].first + 1) / 2; p4 += (ne[l][t].first + 3) / 4;
+                        }
                         a.b2_chunks += (tot + 31) / 32;
                         a.b2_max_adv += madv;
+                        a.c2_chunks += (p2 + 31) / 32; a.c2_slots_used += tot;
+                        a.c4_chunks += (p4 + 31) / 32; a.c4_slots_used += tot;
                     }
                 }
                 // ---- shade, exactly as k_render ----
