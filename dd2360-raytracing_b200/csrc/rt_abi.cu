@@ -122,6 +122,12 @@ extern "C" int rt_create(int device, rt_context **out) {
     ctx->list_accel = new OctreeBuilder();
     const char *dens = getenv("RT_GRID_DENSITY");
     if (dens && atof(dens) > 0) ctx->grid_density = (float)atof(dens);
+    float flat = 0, wide = 0;
+    const char *shape = getenv("RT_GRID_SHAPE");        // "flat:wide", e.g. "1:1" for cubes everywhere
+    if (shape && sscanf(shape, "%f:%f", &flat, &wide) == 2 && flat > 0 && wide > 0) {
+        ctx->octree->grid_flat = ctx->list_accel->grid_flat = flat;
+        ctx->octree->grid_wide = ctx->list_accel->grid_wide = wide;
+    }
     const char *var = getenv("RT_RENDER_VARIANT");
     if (var) ctx->default_variant = atoi(var);
     *out = ctx;

@@ -1,5 +1,5 @@
 """Host model of k_render's lane occupancy (analysis tool; see warp_model.cpp).
-    python profiles/warp_model.py [n=100000] [spl=300] [nx=3840] [ny=2160] [ns=8] [warps=256] [tiles_per_warp=3] [per_trip=2]
+    python profiles/warp_model.py [n=100000] [spl=300] [nx=3840] [ny=2160] [ns=8] [warps=256] [tiles_per_warp=3] [per_trip=2] [density=4] [flat=1.5] [wide=0.75]
 """
 import ctypes as C
 import os
@@ -18,8 +18,10 @@ FIELDS = ("rays paths vox_visits vox_nonempty cands positives filter_pass exact_
 
 
 def main():
-    a = [int(x) for x in sys.argv[1:]]
-    n, spl, nx, ny, ns, warps, tpw, per_trip = (a + [100000, 300, 3840, 2160, 8, 256, 3, 2][len(a):])[:8]
+    a = [float(x) for x in sys.argv[1:]]
+    vals = (a + [100000, 300, 3840, 2160, 8, 256, 3, 2, 4.0, 1.5, 0.75][len(a):])[:11]
+    n, spl, nx, ny, ns, warps, tpw, per_trip = [int(v) for v in vals[:8]]
+    density, flat, wide = float(vals[8]), float(vals[9]), float(vals[10])
     here = os.path.dirname(os.path.abspath(__file__))
     so = os.path.join(ROOT, "gpurun_out", "libwarp_model.so")
     os.makedirs(os.path.dirname(so), exist_ok=True)
@@ -34,7 +36,8 @@ def main():
     step = max(tpw, tiles // warps)
     out = np.zeros(1024, dtype=np.float64)
     lib.wm_run.restype = C.c_int
-    nd = lib.wm_run(C.c_void_p(sph.ctypes.data), len(sph), C.c_void_p(cam.ctypes.data), C.c_void_p(blob.ctypes.data), spl, C.c_float(4.0), nx, ny, ns,
+    lib.hs_set_grid_shape(C.c_float(flat), C.c_float(wide))
+    nd = lib.wm_run(C.c_void_p(sph.ctypes.data), len(sph), C.c_void_p(cam.ctypes.data), C.c_void_p(blob.ctypes.data), spl, C.c_float(density), nx, ny, ns,
                     50, 0, step, warps, tpw, per_trip, C.c_void_p(out.ctypes.data), len(out))
     assert nd > 0, nd
     r = dict(zip(FIELDS, out))

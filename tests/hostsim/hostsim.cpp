@@ -45,6 +45,9 @@ static void make_planes(float P[3][kPlanes]) {
     }
 }
 
+// voxel shape of slab-shaped scenes: the product's defaults; profiles/warp_model.py moves them (hs_set_grid_shape)
+static float g_grid_flat = kGridFlat, g_grid_wide = kGridWide;
+
 // Rebuild the traversal structure on the host from a reference-layout Octree blob: the per-sphere lists of cells that
 // STORE the sphere come straight from the reference's leaf buckets.
 static void build_host_tree(const std::vector<float4> &geom, const std::vector<int> &tag, const int32_t *blob, int spl,
@@ -104,7 +107,7 @@ static void build_host_tree(const std::vector<float4> &geom, const std::vector<i
         lo[2] = fminf(lo[2], s.z - r); hi[2] = fmaxf(hi[2], s.z + r);
     }
     memset(&T.grid, 0, sizeof T.grid);
-    const uint32_t voxels = choose_grid(lo, hi, (uint32_t)small.size(), density, T.grid);
+    const uint32_t voxels = choose_grid(lo, hi, (uint32_t)small.size(), density, T.grid, g_grid_flat, g_grid_wide);
     if (voxels) {
         std::vector<std::vector<uint32_t>> lists(voxels);
         for (uint32_t idx : small) {
@@ -145,6 +148,8 @@ static void view_of(HostTree &T, TreeView &tv) {
 }
 
 extern "C" {
+
+void hs_set_grid_shape(float flat, float wide) { g_grid_flat = flat; g_grid_wide = wide; }
 
 // camera22: origin, llc, horizontal, vertical, u, v, w, lens_radius (taken from the oracle so that only the
 // hot path is under test here)
