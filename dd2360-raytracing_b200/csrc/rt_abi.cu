@@ -15,6 +15,7 @@
 
 #include "../../include/rt_abi.h"
 #include "rt_math.cuh"
+#include "rt_build.cuh"
 #include "rt_octree.h"
 #include "rt_render.h"
 #include "rt_xorwow_skip.h"
@@ -123,10 +124,12 @@ extern "C" int rt_create(int device, rt_context **out) {
     const char *dens = getenv("RT_GRID_DENSITY");
     if (dens && atof(dens) > 0) ctx->grid_density = (float)atof(dens);
     float flat = 0, wide = 0;
-    const char *shape = getenv("RT_GRID_SHAPE");        // "flat:wide", e.g. "1:1" for cubes everywhere
-    if (shape && sscanf(shape, "%f:%f", &flat, &wide) == 2 && flat > 0 && wide > 0) {
+    unsigned flat_min = kFlatVoxelMinSpheres;
+    const char *shape = getenv("RT_GRID_SHAPE");        // "flat:wide[:from how many spheres]", e.g. "1:1" for cubes everywhere
+    if (shape && sscanf(shape, "%f:%f:%u", &flat, &wide, &flat_min) >= 2 && flat > 0 && wide > 0) {
         ctx->octree->grid_flat = ctx->list_accel->grid_flat = flat;
         ctx->octree->grid_wide = ctx->list_accel->grid_wide = wide;
+        ctx->octree->grid_flat_min = ctx->list_accel->grid_flat_min = flat_min;
     }
     const char *var = getenv("RT_RENDER_VARIANT");
     if (var) ctx->default_variant = atoi(var);

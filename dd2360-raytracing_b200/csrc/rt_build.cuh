@@ -68,9 +68,9 @@ RT_HD AxisRange axis_range(const float *P, float c, float r, bool open_low /* x 
 // c = dot(oc,oc) - r*r is about 3 ulp(|oc|^2), and the miss distance that produces is that error over 2r.
 // kSceneReach bounds |oc| (camera at |(13,2,3)|, spheres within |x|,|z| <= 11.1).
 constexpr float kSceneReach = 40.0f;
-RT_HD float sphere_pad(float r) {
+RT_HD float sphere_pad(float r, float reach = kSceneReach) {
     const float rr = fmaxf(r, 1e-3f);
-    return fmaxf(2e-4f, 4e-7f * kSceneReach * kSceneReach / rr);
+    return fmaxf(2e-4f, 4e-7f * reach * reach / rr);
 }
 
 // Does the surface of sphere (c, r), thickened by pad, cross the box [lo, hi]?
@@ -101,7 +101,7 @@ RT_HD bool shell_hits_box(const float4 s, const float pad, const float *lo, cons
 constexpr float kGridFlat = 1.5f, kGridWide = 0.75f;
 constexpr uint32_t kFlatVoxelMinSpheres = 40000;
 inline uint32_t choose_grid(const float *lo, const float *hi, uint32_t live, float density, GridView &g, float flat = kGridFlat,
-                            float wide = kGridWide) {
+                            float wide = kGridWide, uint32_t flat_min = kFlatVoxelMinSpheres) {
     g.nx = g.ny = g.nz = 0;
     if (live == 0) return 0;
     float sz[3];
@@ -113,7 +113,7 @@ inline uint32_t choose_grid(const float *lo, const float *hi, uint32_t live, flo
     int thin = 0;                               // the axis across the slab, if the box is one
     for (int k = 1; k < 3; k++)
         if (sz[k] < sz[thin]) thin = k;
-    bool slab = live >= kFlatVoxelMinSpheres;
+    bool slab = live >= flat_min;
     for (int k = 0; k < 3; k++)
         if (k != thin && sz[thin] * 4.0f > sz[k]) slab = false;
     const float vol = sz[0] * sz[1] * sz[2];

@@ -385,7 +385,7 @@ static cudaError_t ensure(T *&ptr, size_t &cap, size_t need) {
     return e;
 }
 
-OctreeBuilder::OctreeBuilder() : grid_flat(kGridFlat), grid_wide(kGridWide) {
+OctreeBuilder::OctreeBuilder() : grid_flat(kGridFlat), grid_wide(kGridWide), grid_flat_min(kFlatVoxelMinSpheres) {
     memset(&d, 0, sizeof d); memset(&cap, 0, sizeof cap); memset(&grid, 0, sizeof grid); make_planes(planes);
 }
 
@@ -486,7 +486,7 @@ cudaError_t OctreeBuilder::build(cudaStream_t st, const float4 *geom, const int 
     float lo[3], hi[3];
     for (int k = 0; k < 3; k++) { lo[k] = ord2f(prep.lo[k]); hi[k] = ord2f(prep.hi[k]); }
     memset(&grid, 0, sizeof grid);
-    const uint32_t V = choose_grid(lo, hi, prep.live, density, grid, grid_flat, grid_wide);
+    const uint32_t V = choose_grid(lo, hi, prep.live, density, grid, grid_flat, grid_wide, grid_flat_min);
     total_voxels = V;
     total_refs = 0;
     RT_CUDA(ensure(d.vox_count, cap.vox_count, (size_t)V + 2));

@@ -43,7 +43,8 @@ public:
     size_t debug_read(cudaStream_t st, int which, void *host, size_t cap) const;
 
     bool built = false, blob_valid = false, fp16 = false, all_spheres = false;
-    float grid_flat, grid_wide;       // voxel shape in slab-shaped scenes (choose_grid; tuning knob RT_GRID_SHAPE="flat:wide")
+    float grid_flat, grid_wide;       // voxel shape in slab-shaped scenes (choose_grid; tuning knob RT_GRID_SHAPE="flat:wide[:min spheres]")
+    uint32_t grid_flat_min;
     int spl = 0, n_spheres = 0, leaf_count_h = 0;
     int nbig = 0;
     uint32_t prolog_h[kMaxBig + 1];   // staging for the async upload (must outlive build())

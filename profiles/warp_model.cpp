@@ -16,11 +16,53 @@ struct RayScript {
     int positives = 0;       // candidates with disc > 0
     int filter_pass = 0;     // candidates the pre-filter lets through (exact test needed)
     int exact_accept = 0;    // exact tests that improved the closest hit
+    int cands_lvl = 0;       // candidates a distance-levelled list would offer (see level_of_ref)
     int nprolog = 0;
     bool grid_missed = false;
     // per loop trip of the present flat loop: bit0 = advance executed, bits1-2 = candidates tested (0..2), bits3-4 = exact tests run
     std::vector<uint8_t> trips;
 };
+
+// How far from the sphere's surface do the hits lie that the FLOAT test reports?  (what rt_build.cuh's sphere_pad must cover)
+struct HitError {
+    double max_e = 0, max_rel = 0, max_e_m = 0;   // distance from the surface; the same in units of 2^-24 |oc|^2 / r; |oc| of the worst
+    double n = 0;
+    double hist[40] = {0};                        // bin k: 2^(k-34) <= e < 2^(k-33)
+    double bm_max[8] = {0}, bm_n[8] = {0}, bm_p999[8][40] = {{0}};   // by |oc| bucket: [0,1) [1,2) [2,4) [4,8) [8,16) [16,32) [32,64) 64+
+    void add(const float4 s, const vec3f o, const vec3f d, const float t) {
+        const double px = (double)o.x + (double)t * d.x - s.x, py = (double)o.y + (double)t * d.y - s.y, pz = (double)o.z + (double)t * d.z - s.z;
+        const double e = fabs(sqrt(px * px + py * py + pz * pz) - (double)s.w);
+        const double ox = (double)o.x - s.x, oy = (double)o.y - s.y, oz = (double)o.z - s.z;
+        const double m2 = ox * ox + oy * oy + oz * oz;
+        const double rel = e * s.w / m2 * 16777216.0;
+        if (e > max_e) { max_e = e; max_e_m = sqrt(m2); }
+        if (rel > max_rel) max_rel = rel;
+        int k = e > 0 ? (int)floor(log2(e)) + 34 : 0;
+        k = k < 0 ? 0 : (k > 39 ? 39 : k);
+        hist[k]++;
+        n++;
+        const double m = sqrt(m2);
+        const int b = m < 1 ? 0 : (m < 2 ? 1 : (m < 4 ? 2 : (m < 8 ? 3 : (m < 16 ? 4 : (m < 32 ? 5 : (m < 64 ? 6 : 7))))));
+        bm_n[b]++; bm_p999[b][k]++;
+        if (e > bm_max[b]) bm_max[b] = e;
+    }
+};
+static thread_local HitError t_err;
+static HitError g_err;
+
+// distance levels of a voxel list: reference k of a voxel is needed only by rays that have travelled far enough for the float error of
+// the hit test (~ K |oc|^2 / r) to reach across the gap between the sphere's surface and the voxel
+static const float kLvlDist[4] = {8.0f, 16.0f, 28.0f, 64.0f};
+static float g_lvl_k = getenv("WM_LVL_K") ? (float)atof(getenv("WM_LVL_K")) : 1e-6f;
+static int level_of_ref(const GridView &g, const float4 s, int ix, int iy, int iz) {
+    float lo[3], hi[3];
+    voxel_box(g, ix, iy, iz, lo, hi);
+    for (int l = 0; l < 3; l++) {
+        const float m = kLvlDist[l] + s.w;
+        if (shell_hits_box(s, 2e-4f + g_lvl_k * m * m / fmaxf(s.w, 1e-3f), lo, hi)) return l;
+    }
+    return 3;
+}
 
 // trace_walk<false> (rt_trace.cuh) with recording; `two` = candidates per trip
 static Hit walk_record(const SceneView &sc, const TreeView &tv, const vec3f o, const vec3f d, RayScript &rs, const int per_trip) {
@@ -76,12 +118,19 @@ static Hit walk_record(const SceneView &sc, const TreeView &tv, const vec3f o, c
         if (walking && k < e) {
             int ntest = 0, nexact = 0;
             const float bound = h.t;
+            const float l_out = fminf(tmx, fminf(tmy, tmz)) * sqrtf(r.a) * 1.001f;
+            const int ray_lvl = (l_out > kLvlDist[0]) + (l_out > kLvlDist[1]) + (l_out > kLvlDist[2]);
             for (int q = 0; q < per_trip && k < e; q++, k++) {
                 const float4 s = sc.geom[g.refs[k]];
                 ntest++;
+                if (level_of_ref(g, s, ix, iy, iz) <= ray_lvl) rs.cands_lvl++;
                 const vec3f oc = mk(sub_(o.x, s.x), sub_(o.y, s.y), sub_(o.z, s.z));
                 const float b = dot3(oc, d), c = fma_(-s.w, s.w, dot3(oc, oc)), disc = fma_(b, b, -mul_(r.a, c));
-                if (disc > 0.0f) rs.positives++;
+                if (disc > 0.0f) {
+                    rs.positives++;
+                    float ta;
+                    if (s.w < 0.5f && sphere_test(s, o, d, r.a, kTMax, ta)) t_err.add(s, o, d, ta);     // (small spheres: the gridded ones)
+                }
                 if (maybe_hit(s, o, d, r.a, ia, bound)) {
                     rs.filter_pass++;
                     nexact++;
@@ -105,7 +154,7 @@ struct Lane {
 struct Acc {
     // per-ray totals
     double rays = 0, paths = 0, vox_visits = 0, vox_nonempty = 0, cands = 0, positives = 0, filter_pass = 0, exact_accept = 0, grid_missed = 0;
-    double trips = 0;
+    double trips = 0, cands_lvl = 0;
     // present loop, lock-step
     double outer = 0, active_lane_outer = 0;         // outer iterations (one closest-hit query per active lane), lanes with a pixel
     double loop_trips = 0;                           // warp loop trips (max over lanes)
@@ -202,6 +251,7 @@ extern "C" int wm_run(const hs_sphere *sph, int n, const float *camera22, const 
                     int c = 0;
                     for (uint16_t vc : r.vox_counts) { a.vox_nonempty += vc > 0; c += vc; }
                     a.cands += c; a.positives += r.positives; a.filter_pass += r.filter_pass; a.exact_accept += r.exact_accept;
+                    a.cands_lvl += r.cands_lvl;
                     a.grid_missed += r.grid_missed;
                     a.trips += r.trips.size();
                     a.hist_vox[std::min<size_t>(r.vox_counts.size(), 64)]++;
@@ -278,10 +328,32 @@ extern "C" int wm_run(const hs_sphere *sph, int n, const float *camera22, const 
         }
 #pragma omp critical
         {
+            g_err.n += t_err.n;
+            if (t_err.max_e > g_err.max_e) { g_err.max_e = t_err.max_e; g_err.max_e_m = t_err.max_e_m; }
+            g_err.max_rel = std::max(g_err.max_rel, t_err.max_rel);
+            for (int k = 0; k < 40; k++) g_err.hist[k] += t_err.hist[k];
+            for (int b = 0; b < 8; b++) {
+                g_err.bm_n[b] += t_err.bm_n[b];
+                g_err.bm_max[b] = std::max(g_err.bm_max[b], t_err.bm_max[b]);
+                for (int k = 0; k < 40; k++) g_err.bm_p999[b][k] += t_err.bm_p999[b][k];
+            }
+            t_err = HitError();
             double *dst = reinterpret_cast<double *>(&A), *src = reinterpret_cast<double *>(&a);
             for (size_t i = 0; i < sizeof(Acc) / sizeof(double); i++) dst[i] += src[i];
         }
     }
+    fprintf(stderr, "float-accepted hits on gridded spheres: %.0f; distance from the surface: max %.3g (|oc| %.1f), max in units of 2^-24 |oc|^2 / r: %.2f\n",
+            g_err.n, g_err.max_e, g_err.max_e_m, g_err.max_rel);
+    fprintf(stderr, "  log2(distance) histogram:");
+    for (int k = 0; k < 40; k++) if (g_err.hist[k] > 0) fprintf(stderr, " [%d] %.0f", k - 34, g_err.hist[k]);
+    fprintf(stderr, "\n");
+    for (int b = 0; b < 8; b++) {
+        if (g_err.bm_n[b] == 0) continue;
+        double cum = 0; int k999 = 0;
+        for (int k = 0; k < 40; k++) { cum += g_err.bm_p999[b][k]; if (cum >= 0.999 * g_err.bm_n[b]) { k999 = k; break; } }
+        fprintf(stderr, "  |oc| bucket %d: hits %.0f, max distance %.3g, 99.9 %% below 2^%d\n", b, g_err.bm_n[b], g_err.bm_max[b], k999 - 33);
+    }
+    g_err = HitError();
     const size_t nd = sizeof(Acc) / sizeof(double);
     if ((size_t)out_len < nd) return -(int)nd;
     memcpy(out, &A, sizeof A);

@@ -1,5 +1,5 @@
 """Host model of k_render's lane occupancy (analysis tool; see warp_model.cpp).
-    python profiles/warp_model.py [n=100000] [spl=300] [nx=3840] [ny=2160] [ns=8] [warps=256] [tiles_per_warp=3] [per_trip=2] [density=4] [flat=1.5] [wide=0.75]
+    python profiles/warp_model.py [n=100000] [spl=300] [nx=3840] [ny=2160] [ns=8] [warps=256] [tiles_per_warp=3] [per_trip=2] [density=4] [flat=1.5] [wide=0.75] [pad_reach=40]
 """
 import ctypes as C
 import os
@@ -12,16 +12,16 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import __graft_entry__ as entry  # noqa: E402
 
-FIELDS = ("rays paths vox_visits vox_nonempty cands positives filter_pass exact_accept grid_missed trips outer active_lane_outer loop_trips "
+FIELDS = ("rays paths vox_visits vox_nonempty cands positives filter_pass exact_accept grid_missed trips cands_lvl outer active_lane_outer loop_trips "
           "trips_with_adv lanes_adv trips_with_test lanes_test trips_with_exact lanes_exact b_rounds b_chunks b_lanes_round b2_rounds b2_chunks "
           "b2_max_adv c2_chunks c2_slots_used c4_chunks c4_slots_used").split()
 
 
 def main():
     a = [float(x) for x in sys.argv[1:]]
-    vals = (a + [100000, 300, 3840, 2160, 8, 256, 3, 2, 4.0, 1.5, 0.75][len(a):])[:11]
+    vals = (a + [100000, 300, 3840, 2160, 8, 256, 3, 2, 4.0, 1.5, 0.75, 40.0][len(a):])[:12]
     n, spl, nx, ny, ns, warps, tpw, per_trip = [int(v) for v in vals[:8]]
-    density, flat, wide = float(vals[8]), float(vals[9]), float(vals[10])
+    density, flat, wide, reach = float(vals[8]), float(vals[9]), float(vals[10]), float(vals[11])
     here = os.path.dirname(os.path.abspath(__file__))
     so = os.path.join(ROOT, "gpurun_out", "libwarp_model.so")
     os.makedirs(os.path.dirname(so), exist_ok=True)
@@ -37,13 +37,14 @@ def main():
     out = np.zeros(1024, dtype=np.float64)
     lib.wm_run.restype = C.c_int
     lib.hs_set_grid_shape(C.c_float(flat), C.c_float(wide))
+    lib.hs_set_pad_reach(C.c_float(reach))
     nd = lib.wm_run(C.c_void_p(sph.ctypes.data), len(sph), C.c_void_p(cam.ctypes.data), C.c_void_p(blob.ctypes.data), spl, C.c_float(density), nx, ny, ns,
                     50, 0, step, warps, tpw, per_trip, C.c_void_p(out.ctypes.data), len(out))
     assert nd > 0, nd
     r = dict(zip(FIELDS, out))
     rays = r["rays"]
     print(f"rays {rays:.0f} paths {r['paths']:.0f} rays/path {rays / r['paths']:.3f}")
-    for k in ("vox_visits", "vox_nonempty", "cands", "positives", "filter_pass", "exact_accept", "grid_missed", "trips"):
+    for k in ("vox_visits", "vox_nonempty", "cands", "positives", "filter_pass", "exact_accept", "grid_missed", "trips", "cands_lvl"):
         print(f"  per ray: {k:13s} {r[k] / rays:8.3f}")
     print(f"outer iterations {r['outer']:.0f}, lanes with a ray {r['active_lane_outer'] / r['outer']:.2f}")
     lt = r["loop_trips"]

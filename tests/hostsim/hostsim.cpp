@@ -46,7 +46,7 @@ static void make_planes(float P[3][kPlanes]) {
 }
 
 // voxel shape of slab-shaped scenes: the product's defaults; profiles/warp_model.py moves them (hs_set_grid_shape)
-static float g_grid_flat = kGridFlat, g_grid_wide = kGridWide;
+static float g_grid_flat = kGridFlat, g_grid_wide = kGridWide, g_pad_reach = kSceneReach;
 
 // Rebuild the traversal structure on the host from a reference-layout Octree blob: the per-sphere lists of cells that
 // STORE the sphere come straight from the reference's leaf buckets.
@@ -101,7 +101,7 @@ static void build_host_tree(const std::vector<float4> &geom, const std::vector<i
         const float4 s = geom[(size_t)i];
         if (s.w > big_r && (int)T.big_refs.size() < kMaxBig) { T.big_refs.push_back((uint32_t)i); continue; }
         small.push_back((uint32_t)i);
-        const float r = s.w + sphere_pad(s.w);
+        const float r = s.w + sphere_pad(s.w, g_pad_reach);
         lo[0] = fminf(lo[0], s.x - r); hi[0] = fmaxf(hi[0], s.x + r);
         lo[1] = fminf(lo[1], s.y - r); hi[1] = fmaxf(hi[1], s.y + r);
         lo[2] = fminf(lo[2], s.z - r); hi[2] = fmaxf(hi[2], s.z + r);
@@ -112,7 +112,7 @@ static void build_host_tree(const std::vector<float4> &geom, const std::vector<i
         std::vector<std::vector<uint32_t>> lists(voxels);
         for (uint32_t idx : small) {
             const float4 s = geom[idx];
-            const float pad = sphere_pad(s.w);
+            const float pad = sphere_pad(s.w, g_pad_reach);
             int v0[3], v1[3];
             voxel_range(T.grid, s, pad, v0, v1);
             for (int z = v0[2]; z <= v1[2]; z++)
@@ -150,6 +150,15 @@ static void view_of(HostTree &T, TreeView &tv) {
 extern "C" {
 
 void hs_set_grid_shape(float flat, float wide) { g_grid_flat = flat; g_grid_wide = wide; }
+void hs_set_pad_reach(float reach) { g_pad_reach = reach; }
+// choose_grid as the build calls it (the product's default voxel shape): dims[3]; returns the voxel count
+unsigned hs_choose_grid(const float *lo, const float *hi, unsigned live, float density, int *dims) {
+    GridView g;
+    memset(&g, 0, sizeof g);
+    const uint32_t v = choose_grid(lo, hi, live, density, g);
+    dims[0] = g.nx; dims[1] = g.ny; dims[2] = g.nz;
+    return v;
+}
 
 // camera22: origin, llc, horizontal, vertical, u, v, w, lens_radius (taken from the oracle so that only the
 // hot path is under test here)

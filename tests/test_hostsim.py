@@ -41,6 +41,41 @@ def test_grid_resolution_does_not_change_the_image(hostsim, O, density):
     assert np.array_equal(fb.view(np.uint32), ref.view(np.uint32))
 
 
+@pytest.mark.parametrize("flat,wide", [(1.0, 1.0), (2.5, 0.5)])
+def test_voxel_shape_does_not_change_the_image(hostsim, O, flat, wide):
+    """Flat voxels in slab-shaped scenes (choose_grid, from 40 k spheres) are a speed knob: cubes and very flat voxels give the
+    frame of the default shape, which test_device_code_matches_oracle holds to the oracle at the same size."""
+    hostsim.hs_set_grid_shape(C.c_float(flat), C.c_float(wide))
+    try:
+        fb, ref, c, ctr = _run(hostsim, O, 100000, 300, True, 96, 54, 1)
+    finally:
+        hostsim.hs_set_grid_shape(C.c_float(1.5), C.c_float(0.75))
+    assert c.rays == ctr["rays"]
+    assert np.array_equal(fb.view(np.uint32), ref.view(np.uint32))
+
+
+def test_choose_grid_shape_rule(hostsim):
+    """Cubic voxels, except slab-shaped boxes from 40 k spheres: 1.5x the layers across the slab, 0.75x the columns along it."""
+    def grid(lo, hi, live):
+        dims = (C.c_int * 3)()
+        hostsim.hs_choose_grid.restype = C.c_uint
+        v = hostsim.hs_choose_grid((C.c_float * 3)(*lo), (C.c_float * 3)(*hi), C.c_uint(live), C.c_float(4.0), dims)
+        assert v == dims[0] * dims[1] * dims[2]
+        return tuple(dims)
+    slab_lo, slab_hi = (-11.0, 0.0, -11.0), (11.0, 0.2, 11.0)
+    small = grid(slab_lo, slab_hi, 8000)                 # below the threshold: cubes
+    edge = [(slab_hi[k] - slab_lo[k]) / small[k] for k in range(3)]
+    assert max(edge) / min(edge) < 1.6
+    cubic_edge = (22.0 * 0.2 * 22.0 / 400000.0) ** (1.0 / 3.0)
+    big = grid(slab_lo, slab_hi, 100000)
+    assert big[1] == int(np.ceil(np.ceil(0.2 / cubic_edge) * 1.5))
+    assert big[0] == big[2] == int(np.ceil(np.ceil(22.0 / cubic_edge) * 0.75))
+    cube = grid((-5.0, -5.0, -5.0), (5.0, 5.0, 5.0), 100000)      # not a slab: cubes at any size
+    assert cube[0] == cube[1] == cube[2]
+    thin_z = grid((-11.0, -11.0, 0.0), (11.0, 11.0, 0.2), 100000)   # the thin axis is found, not assumed to be y
+    assert thin_z == (big[0], big[2], big[1])
+
+
 def test_irregular_scene(hostsim, O):
     """Radii from 0.02 to 1.5, spheres poking out of the root box and fully outside it (dropped by the reference)."""
     rng = np.random.default_rng(11)
