@@ -17,6 +17,7 @@ struct RayScript {
     int filter_pass = 0;     // candidates the pre-filter lets through (exact test needed)
     int exact_accept = 0;    // exact tests that improved the closest hit
     int cands_lvl = 0;       // candidates a distance-levelled list would offer (see level_of_ref)
+    int cands_front = 0;     // candidates left when primary rays skip the spheres whose surface inside the voxel faces away from the camera
     int nprolog = 0;
     bool grid_missed = false;
     // per loop trip of the present flat loop: bit0 = advance executed, bits1-2 = candidates tested (0..2), bits3-4 = exact tests run
@@ -62,6 +63,26 @@ static int level_of_ref(const GridView &g, const float4 s, int ix, int iy, int i
         if (shell_hits_box(s, 2e-4f + g_lvl_k * m * m / fmaxf(s.w, 1e-3f), lo, hi)) return l;
     }
     return 3;
+}
+
+// Thales: p on sphere (c, r) faces the eye e, (p - e).(p - c) <= 0, iff p lies inside the sphere on the diameter e-c.  A voxel can
+// hold a front-facing point of the surface only if it reaches into that sphere (margin: lens radius + list padding).
+static bool g_primary = false;
+#pragma omp threadprivate(g_primary)
+static float g_eye[3] = {0, 0, 0}, g_eye_margin = 0.06f;
+static bool faces_eye(const GridView &g, const float4 s, int ix, int iy, int iz) {
+    float lo[3], hi[3];
+    voxel_box(g, ix, iy, iz, lo, hi);
+    const float m[3] = {0.5f * (g_eye[0] + s.x), 0.5f * (g_eye[1] + s.y), 0.5f * (g_eye[2] + s.z)};
+    const float ex = g_eye[0] - s.x, ey = g_eye[1] - s.y, ez = g_eye[2] - s.z;
+    const float R2 = 0.25f * (ex * ex + ey * ey + ez * ez) + (s.w + sphere_pad(s.w)) * g_eye_margin;   // (p - e).(p - c) <= |p - c| * margin
+    float d2 = 0;
+    for (int k = 0; k < 3; k++) {
+        const float a = lo[k] - m[k], b = hi[k] - m[k];
+        const float nearest = a > 0.f ? a : (b < 0.f ? b : 0.f);
+        d2 += nearest * nearest;
+    }
+    return d2 <= R2;
 }
 
 // trace_walk<false> (rt_trace.cuh) with recording; `two` = candidates per trip
@@ -124,6 +145,7 @@ static Hit walk_record(const SceneView &sc, const TreeView &tv, const vec3f o, c
                 const float4 s = sc.geom[g.refs[k]];
                 ntest++;
                 if (level_of_ref(g, s, ix, iy, iz) <= ray_lvl) rs.cands_lvl++;
+                if (!g_primary || faces_eye(g, s, ix, iy, iz)) rs.cands_front++;
                 const vec3f oc = mk(sub_(o.x, s.x), sub_(o.y, s.y), sub_(o.z, s.z));
                 const float b = dot3(oc, d), c = fma_(-s.w, s.w, dot3(oc, oc)), disc = fma_(b, b, -mul_(r.a, c));
                 if (disc > 0.0f) {
@@ -154,7 +176,7 @@ struct Lane {
 struct Acc {
     // per-ray totals
     double rays = 0, paths = 0, vox_visits = 0, vox_nonempty = 0, cands = 0, positives = 0, filter_pass = 0, exact_accept = 0, grid_missed = 0;
-    double trips = 0, cands_lvl = 0;
+    double trips = 0, cands_lvl = 0, cands_front = 0;
     // present loop, lock-step
     double outer = 0, active_lane_outer = 0;         // outer iterations (one closest-hit query per active lane), lanes with a pixel
     double loop_trips = 0;                           // warp loop trips (max over lanes)
@@ -193,6 +215,8 @@ extern "C" int wm_run(const hs_sphere *sph, int n, const float *camera22, const 
     CameraData cam;
     memcpy(&cam, camera22, sizeof cam);
     const int tiles_x = (nx + 7) / 8, tiles_y = (ny + 3) / 4;
+    for (int k = 0; k < 3; k++) g_eye[k] = cam.origin[k];
+    g_eye_margin = cam.lens_radius + 0.01f;
     Acc A;
 #pragma omp parallel
     {
@@ -244,6 +268,7 @@ extern "C" int wm_run(const hs_sphere *sph, int n, const float *camera22, const 
                     a.rays++;
                     TraceCounters tcn{};
                     hs[l] = trace_tree(sc, tv, &tv.planes[0][0], q.o, q.d, tcn);
+                    g_primary = q.depth == 0;
                     const Hit h2 = walk_record(sc, tv, q.o, q.d, rs[l], per_trip);
                     if (h2.idx != hs[l].idx || h2.t != hs[l].t) { /* checked re-walk case: rare; keep trace_tree's answer */ }
                     const RayScript &r = rs[l];
@@ -251,7 +276,7 @@ extern "C" int wm_run(const hs_sphere *sph, int n, const float *camera22, const 
                     int c = 0;
                     for (uint16_t vc : r.vox_counts) { a.vox_nonempty += vc > 0; c += vc; }
                     a.cands += c; a.positives += r.positives; a.filter_pass += r.filter_pass; a.exact_accept += r.exact_accept;
-                    a.cands_lvl += r.cands_lvl;
+                    a.cands_lvl += r.cands_lvl; a.cands_front += r.cands_front;
                     a.grid_missed += r.grid_missed;
                     a.trips += r.trips.size();
                     a.hist_vox[std::min<size_t>(r.vox_counts.size(), 64)]++;
