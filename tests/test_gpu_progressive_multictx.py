@@ -106,6 +106,33 @@ def test_cooperative_and_per_lane_kernels_agree(rt):
         assert same >= 1 - 1e-5 and abs(out[0][1] - out[1][1]) <= 4, (n, same, out[0][1], out[1][1])
 
 
+def test_voxel_shape_is_only_a_speed_knob(pkg, monkeypatch):
+    """choose_grid's flat voxels (slab-shaped scenes from 40 k spheres; RT_GRID_SHAPE is read when a context is created): cubes, the
+    default and very flat voxels render the same frame, through the cooperative and the per-lane kernel."""
+    import torch
+    nx, ny, ns = 192, 108, 2
+    frames, grids = [], []
+    for shape in ("1:1", None, "3:0.5"):
+        if shape is None:
+            monkeypatch.delenv("RT_GRID_SHAPE", raising=False)
+        else:
+            monkeypatch.setenv("RT_GRID_SHAPE", shape)
+        r = pkg.RayTracer(0)
+        try:
+            r.create_world(100000, 0.1)
+            st = r.build_octree(300)
+            grids.append((st["fine_voxels"], st["fine_refs"]))
+            for variant in (0, 1):
+                fb = torch.empty((ny, nx, 3), dtype=torch.float32, device="cuda")
+                r.render_device(r.args(nx, ny, ns, True, variant=variant), fb.data_ptr())
+                frames.append(fb.cpu().numpy())
+        finally:
+            r.close()
+    assert len(set(grids)) == 3, grids                       # the knob did change the grid
+    for f in frames[1:]:
+        assert np.array_equal(f.view(np.uint32), frames[0].view(np.uint32))
+
+
 def _multi_gpu_count():
     try:
         import torch
