@@ -29,7 +29,7 @@ struct rt_context {
     std::string err;
     // scene
     int n = 0;
-    std::vector<rt_sphere_desc> host_scene;
+    bool slot0_defined = true;
     float4 *geom = nullptr, *matl = nullptr;
     int *tag = nullptr;
     size_t scene_cap = 0;
@@ -251,7 +251,10 @@ __global__ void k_split_scene(const rt_sphere_desc *__restrict__ d, int n, float
     tag[i] = s.mat;
 }
 
-static int upload_scene(rt_context *ctx) {
+// The 36-byte descriptors cross PCIe once, from page-locked staging memory, and are split into the SoA arrays on the device
+// (three pageable copies of host-built arrays took 1.0 ms at 100 k spheres: as much as the whole octree build).  The staging
+// buffer is also the context's host copy of the scene (rt_scene_download): `src` is copied ONCE, straight into it.
+static int upload_scene(rt_context *ctx, const rt_sphere_desc *src, bool clamp_fuzz) {
     const int n = ctx->n;
     if ((size_t)n > ctx->scene_cap) {
         cudaFree(ctx->geom); cudaFree(ctx->matl); cudaFree(ctx->tag);
@@ -261,9 +264,8 @@ static int upload_scene(rt_context *ctx) {
         CK(cudaMalloc(&ctx->tag, (size_t)n * sizeof(int)));
         ctx->scene_cap = (size_t)n;
     }
-    // the 36-byte descriptors cross PCIe once, from page-locked staging memory, and are split into the SoA arrays on the device
-    // (three pageable copies of host-built arrays took 1.0 ms at 100 k spheres: as much as the whole octree build)
     const size_t bytes = (size_t)n * sizeof(rt_sphere_desc);
+    CK(cudaStreamSynchronize(ctx->stream));                      // (an earlier upload may still be reading the staging buffer)
     if (bytes > ctx->pinned_bytes) {
         if (ctx->pinned) cudaFreeHost(ctx->pinned);
         ctx->pinned = nullptr; ctx->pinned_bytes = 0;
@@ -273,8 +275,12 @@ static int upload_scene(rt_context *ctx) {
         ctx->pinned_bytes = bytes + bytes / 4;
         CK(cudaMalloc(&ctx->desc_dev, bytes + bytes / 4));
     }
-    CK(cudaStreamSynchronize(ctx->stream));                      // (an earlier upload may still be reading the staging buffer)
-    memcpy(ctx->pinned, ctx->host_scene.data(), bytes);
+    rt_sphere_desc *host = reinterpret_cast<rt_sphere_desc *>(ctx->pinned);
+    memcpy(host, src, bytes);
+    if (clamp_fuzz)
+        for (int i = 0; i < n; i++)
+            if (host[i].mat == RT_MAT_METAL && !(host[i].param < 1.0f)) host[i].param = 1.0f;   // metal::metal clamps fuzz (material.h:67)
+    ctx->slot0_defined = host[0].mat != RT_MAT_NONE;
     CK(cudaMemcpyAsync(ctx->desc_dev, ctx->pinned, bytes, cudaMemcpyHostToDevice, ctx->stream));
     k_split_scene<<<(n + 255) / 256, 256, 0, ctx->stream>>>(static_cast<const rt_sphere_desc *>(ctx->desc_dev), n, ctx->geom, ctx->matl, ctx->tag);
     CK(cudaGetLastError());
@@ -291,8 +297,9 @@ extern "C" int rt_scene_generate_ex(rt_context *ctx, int n, float radius, int pr
     ctx->n = n;
     ctx->half_valid = false;          // the half copy of the scene (USE_FP16 path) is derived on demand
     ctx->list_accel_valid = false;
-    generate_world(n, radius, precision == RT_PREC_FP16, ctx->host_scene);
-    return upload_scene(ctx);
+    std::vector<rt_sphere_desc> world;
+    generate_world(n, radius, precision == RT_PREC_FP16, world);
+    return upload_scene(ctx, world.data(), false);
 }
 
 extern "C" int rt_scene_upload(rt_context *ctx, const rt_sphere_desc *spheres, int n) {
@@ -301,15 +308,12 @@ extern "C" int rt_scene_upload(rt_context *ctx, const rt_sphere_desc *spheres, i
     ctx->n = n;
     ctx->half_valid = false;          // the half copy of the scene (USE_FP16 path) is derived on demand
     ctx->list_accel_valid = false;
-    ctx->host_scene.assign(spheres, spheres + n);
-    for (auto &s : ctx->host_scene)
-        if (s.mat == RT_MAT_METAL && !(s.param < 1.0f)) s.param = 1.0f;   // metal::metal clamps fuzz (material.h:67)
-    return upload_scene(ctx);
+    return upload_scene(ctx, spheres, true);
 }
 
 extern "C" int rt_scene_download(rt_context *ctx, rt_sphere_desc *out, int n) {
     if (!ctx || !out || n != ctx->n) return fail(ctx, RT_ERR_INVALID, "rt_scene_download: n does not match the scene");
-    memcpy(out, ctx->host_scene.data(), (size_t)n * sizeof(rt_sphere_desc));
+    memcpy(out, ctx->pinned, (size_t)n * sizeof(rt_sphere_desc));      // the staging buffer of the last upload
     return RT_OK;
 }
 
@@ -502,7 +506,7 @@ static int do_render(rt_context *ctx, const rt_render_args *a, float *out_dev, b
     // with a few dozen tests instead of N (the result is the same minimum; variant 20 forces the N-test sweep)
     bool list_grid = false;
     if (!a->use_octree && a->precision == RT_PREC_FP32 && ctx->n >= kListGridMinSpheres && a->tune[1] != 20 &&
-        ctx->host_scene[0].mat != RT_MAT_NONE) {      // (the prolog tests sphere 0 unconditionally; an undefined slot 0 must stay unhittable)
+        ctx->slot0_defined) {      // (the prolog tests sphere 0 unconditionally; an undefined slot 0 must stay unhittable)
         if (!ctx->list_accel_valid) {
             CK(ctx->list_accel->build(ctx->stream, ctx->geom, ctx->tag, ctx->n, 30, ctx->grid_density, false, true));
             ctx->list_accel_valid = true;
