@@ -187,6 +187,9 @@ struct Acc {
     double b2_rounds = 0, b2_chunks = 0, b2_max_adv = 0;
     // what k_render_coop does: B2 with ITEMS = 2 / 4 consecutive references per lane and chunk step
     double c2_chunks = 0, c2_slots_used = 0, c4_chunks = 0, c4_slots_used = 0;
+    // variant "deferred tails": a round runs only its FULL chunks; the items left over stay with their (trailing) lanes and are
+    // republished next round next to the other lanes' new voxels (a partial chunk runs only when there is no full one)
+    double d2_chunks = 0, d2_rounds = 0, d4_chunks = 0, d4_rounds = 0;
     // histograms
     double hist_vox[65] = {0}, hist_cands[257] = {0}, hist_trips[129] = {0};
     double shade_hit = 0, shade_sky = 0;
@@ -330,6 +333,31 @@ extern "C" int wm_run(const hs_sphere *sph, int n, const float *camera22, const 
                         a.c2_chunks += (p2 + 31) / 32; a.c2_slots_used += tot;
                         a.c4_chunks += (p4 + 31) / 32; a.c4_slots_used += tot;
                     }
+                }
+                // ---- deferred tails ----
+                for (int items_per = 2; items_per <= 4; items_per += 2) {
+                    std::vector<std::vector<int>> seq(32);
+                    for (int l = 0; l < 32; l++)
+                        for (uint16_t vc : rs[l].vox_counts) if (vc) seq[l].push_back((vc + items_per - 1) / items_per);
+                    size_t pos[32] = {0};
+                    int rem[32];
+                    for (int l = 0; l < 32; l++) rem[l] = seq[l].empty() ? 0 : seq[l][0];
+                    double chunks = 0, rounds = 0;
+                    while (true) {
+                        int total = 0;
+                        for (int l = 0; l < 32; l++) total += rem[l];
+                        if (!total) break;
+                        rounds++;
+                        int run = total >= 32 ? (total / 32) * 32 : total;
+                        chunks += (run + 31) / 32;
+                        for (int l = 0; l < 32 && run > 0; l++) {
+                            const int take = std::min(run, rem[l]);
+                            rem[l] -= take; run -= take;
+                        }
+                        for (int l = 0; l < 32; l++)
+                            if (rem[l] == 0 && pos[l] < seq[l].size()) { pos[l]++; rem[l] = pos[l] < seq[l].size() ? seq[l][pos[l]] : 0; }
+                    }
+                    if (items_per == 2) { a.d2_chunks += chunks; a.d2_rounds += rounds; } else { a.d4_chunks += chunks; a.d4_rounds += rounds; }
                 }
                 // ---- shade, exactly as k_render ----
                 for (int l = 0; l < 32; l++) {

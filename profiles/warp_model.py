@@ -14,7 +14,7 @@ import __graft_entry__ as entry  # noqa: E402
 
 FIELDS = ("rays paths vox_visits vox_nonempty cands positives filter_pass exact_accept grid_missed trips cands_lvl cands_front outer active_lane_outer loop_trips "
           "trips_with_adv lanes_adv trips_with_test lanes_test trips_with_exact lanes_exact b_rounds b_chunks b_lanes_round b2_rounds b2_chunks "
-          "b2_max_adv c2_chunks c2_slots_used c4_chunks c4_slots_used").split()
+          "b2_max_adv c2_chunks c2_slots_used c4_chunks c4_slots_used d2_chunks d2_rounds d4_chunks d4_rounds").split()
 
 
 def main():
@@ -58,6 +58,8 @@ def main():
           f"fill {r['cands'] / (32 * r['b2_chunks']):.3f}, advance steps per round (max over lanes) {r['b2_max_adv'] / r['b2_rounds']:.2f}")
     print(f"k_render_coop: chunk steps per outer with 2 references per lane {r['c2_chunks'] / r['outer']:.2f} (candidate slots filled "
           f"{r['c2_slots_used'] / (64 * r['c2_chunks']):.3f}), with 4 per lane {r['c4_chunks'] / r['outer']:.2f} (filled {r['c4_slots_used'] / (128 * r['c4_chunks']):.3f})")
+    print(f"deferred tails: 2 per lane: chunk steps per outer {r['d2_chunks'] / r['outer']:.2f}, rounds {r['d2_rounds'] / r['outer']:.2f}; "
+          f"4 per lane: {r['d4_chunks'] / r['outer']:.2f}, rounds {r['d4_rounds'] / r['outer']:.2f}")
     base = len(FIELDS)
     hv, hc, ht = out[base:base + 65], out[base + 65:base + 65 + 257], out[base + 65 + 257:base + 65 + 257 + 129]
     def pct(h, name):
