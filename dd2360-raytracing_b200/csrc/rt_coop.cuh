@@ -35,14 +35,17 @@ namespace coop {
 
 constexpr unsigned kFull = 0xffffffffu;
 constexpr uint32_t kPrologFlag = 0x80000000u;    // ring reference: index into the prolog list instead of the voxel lists
-constexpr int kRing = 160;                       // >= 31 (left over) + 128 (one chunk's pushes at four candidates per lane)
+constexpr int kRing = 160;
+constexpr float kVoxelExitSlackRel = 1e-4f, kVoxelExitSlackAbs = 1e-4f;   // covers the DDA's accumulated rounding (<= ~700 additions per axis)                       // >= 31 (left over) + 128 (one chunk's pushes at four candidates per lane)
 
 struct __align__(16) RayMeta {
     int koff;        // first reference of the lane's current voxel - ITEMS * its offset in the flat item list
     int kend;        // one past the last reference of that voxel
     float bound;     // what the pre-filter and the walk prune against: an upper bound of the ray's closest hit — the exact t of
                      // best_t, or less: the certain-hit bound of a candidate still waiting in the ring (maybe_hit_ub)
-    int pad;
+    float t_out;     // where the ray leaves its current voxel (+ slack): a root beyond it belongs to a later voxel, which lists the
+                     // sphere too (the lists cover the padded surface) and offers it when the walk gets there — so a sphere that spans
+                     // several voxels of the ray is queued for its exact test once, not once per voxel
 };
 
 struct __align__(16) WarpShared {
@@ -232,6 +235,7 @@ __device__ __forceinline__ Hit coop_trace(WarpShared &ws, const SceneView &sc, c
         const uint32_t excl = incl - mine;
         ws.meta[lane].koff = (int)k - ITEMS * (int)excl;
         ws.meta[lane].kend = (int)(k + cnt);
+        ws.meta[lane].t_out = fminf(tmx, fminf(tmy, tmz)) * (1.0f + kVoxelExitSlackRel) + kVoxelExitSlackAbs;
         // the lanes that have items, in lane order (= item order): slot[j] is the j-th of them
         const unsigned lt = (1u << lane) - 1u;
         const unsigned nz = __ballot_sync(kFull, mine > 0u);
@@ -258,11 +262,12 @@ __device__ __forceinline__ Hit coop_trace(WarpShared &ws, const SceneView &sc, c
 #pragma unroll
                 for (int j = 0; j < ITEMS; j++) sg[j] = __ldg(g.ref_geom + ref + j);   // (past a list's end: the next list, or the slack elements)
                 float ub = kTMax;
+                const float t_far = fminf(mt.bound, mt.t_out);
 #pragma unroll
                 for (int j = 0; j < ITEMS; j++) {
                     float ubj;
                     RT_COUNT(sphere_tests);
-                    const bool pj = maybe_hit_ub(sg[j], oo, dd, ro.w, rd.w, mt.bound, ubj) && (j == 0 || (int)ref + j < mt.kend);
+                    const bool pj = maybe_hit_ub(sg[j], oo, dd, ro.w, rd.w, t_far, ubj) && (j == 0 || (int)ref + j < mt.kend);
                     if (pj) { pass |= 1u << j; ub = fminf(ub, ubj); }
                 }
                 // a certain hit lowers the owner's pruning bound at once (native shared-memory atomic on the float's bits: roots

@@ -17,6 +17,7 @@ struct RayScript {
     int filter_pass = 0;     // candidates the pre-filter lets through (exact test needed)
     int exact_accept = 0;    // exact tests that improved the closest hit
     int cands_lvl = 0;       // candidates a distance-levelled list would offer (see level_of_ref)
+    int pass_cap_hi = 0, pass_cap_both = 0;   // pre-filter passes when roots beyond the voxel's exit (and certain hits before its entry) are left to the other voxels
     int cands_front = 0;     // candidates left when primary rays skip the spheres whose surface inside the voxel faces away from the camera
     int nprolog = 0;
     bool grid_missed = false;
@@ -118,6 +119,7 @@ static Hit walk_record(const SceneView &sc, const TreeView &tv, const vec3f o, c
     float tmz = fabsf(d.z) > 0.0f ? (g.org[2] + (float)(iz + (sz > 0)) * g.vs[2] - o.z) * r.inv.z : kTMax;
     const float dtx = fabsf(g.vs[0] * r.inv.x), dty = fabsf(g.vs[1] * r.inv.y), dtz = fabsf(g.vs[2] * r.inv.z);
     uint32_t k, e;
+    float t_vox_in = te;
     { const uint2 v = g.vox[((size_t)(iz * g.ny + iy) * g.nx + ix)]; k = v.x; e = v.x + v.y; rs.vox_counts.push_back((uint16_t)v.y); }
     int budget = g.nx + g.ny + g.nz + 4;
     bool walking = true;
@@ -134,6 +136,7 @@ static Hit walk_record(const SceneView &sc, const TreeView &tv, const vec3f o, c
                 const uint2 v = g.vox[((size_t)(iz * g.ny + iy) * g.nx + ix)];
                 k = v.x; e = v.x + v.y;
                 rs.vox_counts.push_back((uint16_t)v.y);
+                t_vox_in = t_in;
             }
         }
         if (walking && k < e) {
@@ -152,6 +155,17 @@ static Hit walk_record(const SceneView &sc, const TreeView &tv, const vec3f o, c
                     rs.positives++;
                     float ta;
                     if (s.w < 0.5f && sphere_test(s, o, d, r.a, kTMax, ta)) t_err.add(s, o, d, ta);     // (small spheres: the gridded ones)
+                }
+                {
+                    const float t_out_v = fminf(tmx, fminf(tmy, tmz));
+                    const float cap = fminf(bound, t_out_v * (1.0f + 1e-4f) + 1e-4f);
+                    float ubx;
+                    if (maybe_hit_ub(s, o, d, r.a, ia, cap, ubx)) {
+                        rs.pass_cap_hi++;
+                        // certain hit that lies before this voxel: the voxel holding it has offered it already
+                        const float sa = sqrtf(fmaxf(disc, 0.0f)), t1 = (-b - sa) * ia, eps = (fabsf(b) + sa) * ia * 1e-5f;
+                        if (!(t1 - eps > kTMin && t1 + eps < t_vox_in * (1.0f - 1e-4f) - 1e-4f)) rs.pass_cap_both++;
+                    }
                 }
                 if (maybe_hit(s, o, d, r.a, ia, bound)) {
                     rs.filter_pass++;
@@ -176,7 +190,7 @@ struct Lane {
 struct Acc {
     // per-ray totals
     double rays = 0, paths = 0, vox_visits = 0, vox_nonempty = 0, cands = 0, positives = 0, filter_pass = 0, exact_accept = 0, grid_missed = 0;
-    double trips = 0, cands_lvl = 0, cands_front = 0;
+    double trips = 0, cands_lvl = 0, cands_front = 0, pass_cap_hi = 0, pass_cap_both = 0;
     // present loop, lock-step
     double outer = 0, active_lane_outer = 0;         // outer iterations (one closest-hit query per active lane), lanes with a pixel
     double loop_trips = 0;                           // warp loop trips (max over lanes)
@@ -279,7 +293,7 @@ extern "C" int wm_run(const hs_sphere *sph, int n, const float *camera22, const 
                     int c = 0;
                     for (uint16_t vc : r.vox_counts) { a.vox_nonempty += vc > 0; c += vc; }
                     a.cands += c; a.positives += r.positives; a.filter_pass += r.filter_pass; a.exact_accept += r.exact_accept;
-                    a.cands_lvl += r.cands_lvl; a.cands_front += r.cands_front;
+                    a.cands_lvl += r.cands_lvl; a.cands_front += r.cands_front; a.pass_cap_hi += r.pass_cap_hi; a.pass_cap_both += r.pass_cap_both;
                     a.grid_missed += r.grid_missed;
                     a.trips += r.trips.size();
                     a.hist_vox[std::min<size_t>(r.vox_counts.size(), 64)]++;

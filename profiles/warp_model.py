@@ -12,7 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import __graft_entry__ as entry  # noqa: E402
 
-FIELDS = ("rays paths vox_visits vox_nonempty cands positives filter_pass exact_accept grid_missed trips cands_lvl cands_front outer active_lane_outer loop_trips "
+FIELDS = ("rays paths vox_visits vox_nonempty cands positives filter_pass exact_accept grid_missed trips cands_lvl cands_front pass_cap_hi pass_cap_both outer active_lane_outer loop_trips "
           "trips_with_adv lanes_adv trips_with_test lanes_test trips_with_exact lanes_exact b_rounds b_chunks b_lanes_round b2_rounds b2_chunks "
           "b2_max_adv c2_chunks c2_slots_used c4_chunks c4_slots_used d2_chunks d2_rounds d4_chunks d4_rounds").split()
 
@@ -44,7 +44,7 @@ def main():
     r = dict(zip(FIELDS, out))
     rays = r["rays"]
     print(f"rays {rays:.0f} paths {r['paths']:.0f} rays/path {rays / r['paths']:.3f}")
-    for k in ("vox_visits", "vox_nonempty", "cands", "positives", "filter_pass", "exact_accept", "grid_missed", "trips", "cands_lvl", "cands_front"):
+    for k in ("vox_visits", "vox_nonempty", "cands", "positives", "filter_pass", "exact_accept", "grid_missed", "trips", "cands_lvl", "cands_front", "pass_cap_hi", "pass_cap_both"):
         print(f"  per ray: {k:13s} {r[k] / rays:8.3f}")
     print(f"outer iterations {r['outer']:.0f}, lanes with a ray {r['active_lane_outer'] / r['outer']:.2f}")
     lt = r["loop_trips"]
