@@ -147,10 +147,90 @@ static void view_of(HostTree &T, TreeView &tv) {
     for (int a = 0; a < 3; a++) tv.cell_inv[a] = 8.0f / (T.planes[a][kPlanes - 1] - T.planes[a][0]);
 }
 
+// ---- host emulation of k_render_coop's candidate rule (rt_coop.cuh coop_trace), one ray at a time -------------------------
+// What the cooperative kernel does differently from trace_walk: candidates only pass the conservative pre-filter
+// (maybe_hit_ub) against  min(pruning bound, exit of the ray's current voxel + slack)  — a root beyond the voxel is left to the
+// voxel that holds it — certain hits lower the pruning bound before they are evaluated, and the exact tests run later, in any
+// order.  `eager`: the queued candidates are evaluated after every voxel (the bound follows the exact values at once);
+// otherwise only at the end of the trace (the walk is steered by the certain-hit bounds alone).  Both extremes — and every
+// schedule between them, which is what the warp's ring does — must return trace_walk's minimum.
+static const float kCoopExitSlackRel = 1e-4f, kCoopExitSlackAbs = 1e-4f;      // rt_coop.cuh kVoxelExitSlack*
+struct CoopHit { float t; int idx; bool tie; };
+static CoopHit coop_walk_host(const SceneView &sc, const TreeView &tv, const vec3f o, const vec3f d, const bool eager) {
+    const float a = dot3(d, d), ia = rcp_trav(a);
+    CoopHit h;
+    h.t = kTMax; h.idx = -1; h.tie = false;
+    float bound = kTMax;
+    std::vector<int> ring;
+    auto drain = [&]() {
+        for (int idx : ring) {
+            float t;
+            if (sphere_test(sc.geom[idx], o, d, a, kTMax, t)) {
+                if (t < h.t) { h.t = t; h.idx = idx; h.tie = false; }
+                else if (t == h.t && idx != h.idx) h.tie = true;
+            }
+        }
+        ring.clear();
+        bound = fminf(bound, h.t);
+    };
+    { float t; if (sphere_test(sc.geom[0], o, d, a, kTMax, t)) { h.t = t; h.idx = 0; bound = t; } }
+    for (int k = 1; k < tv.nprolog; k++) {
+        const int idx = (int)tv.prolog[k];
+        float ub;
+        if (maybe_hit_ub(sc.geom[idx], o, d, a, ia, bound, ub)) { if (ub < bound) bound = ub; ring.push_back(idx); }
+    }
+    const GridView &g = tv.grid;
+    RayPre r;
+    r.o = o; r.d = d; r.a = a;
+    r.inv = mk(rcp_trav(d.x), rcp_trav(d.y), rcp_trav(d.z));
+    float te, t_exit;
+    if (g.nx != 0 && ray_box(r, g.org, g.hi, bound * (1.0f + kTSlackRel) + kTSlackAbs, te, t_exit)) {
+        int ix = (int)floorf((o.x + d.x * te - g.org[0]) * g.inv_vs[0]);
+        int iy = (int)floorf((o.y + d.y * te - g.org[1]) * g.inv_vs[1]);
+        int iz = (int)floorf((o.z + d.z * te - g.org[2]) * g.inv_vs[2]);
+        ix = imin(imax(ix, 0), g.nx - 1); iy = imin(imax(iy, 0), g.ny - 1); iz = imin(imax(iz, 0), g.nz - 1);
+        const int sx = d.x >= 0.0f ? 1 : -1, sy = d.y >= 0.0f ? 1 : -1, sz = d.z >= 0.0f ? 1 : -1;
+        float tmx = fabsf(d.x) > 0.0f ? (g.org[0] + (float)(ix + (sx > 0)) * g.vs[0] - o.x) * r.inv.x : kTMax;
+        float tmy = fabsf(d.y) > 0.0f ? (g.org[1] + (float)(iy + (sy > 0)) * g.vs[1] - o.y) * r.inv.y : kTMax;
+        float tmz = fabsf(d.z) > 0.0f ? (g.org[2] + (float)(iz + (sz > 0)) * g.vs[2] - o.z) * r.inv.z : kTMax;
+        const float dtx = fabsf(g.vs[0] * r.inv.x), dty = fabsf(g.vs[1] * r.inv.y), dtz = fabsf(g.vs[2] * r.inv.z);
+        int budget = g.nx + g.ny + g.nz + 4;
+        bool walking = true;
+        while (walking) {
+            const uint2 v = g.vox[((size_t)(iz * g.ny + iy) * g.nx + ix)];
+            if (v.y) {
+                const float t_out = fminf(tmx, fminf(tmy, tmz)) * (1.0f + kCoopExitSlackRel) + kCoopExitSlackAbs;
+                const float round_bound = bound;          // the chunks of one round may all see the bound the round began with
+                for (uint32_t k = v.x; k < v.x + v.y; k++) {
+                    const int idx = (int)g.refs[k];
+                    float ub;
+                    if (maybe_hit_ub(sc.geom[idx], o, d, a, ia, fminf(eager ? bound : round_bound, t_out), ub)) {
+                        if (ub < bound) bound = ub;
+                        ring.push_back(idx);
+                    }
+                }
+                if (eager) drain();
+            }
+            float t_in;
+            if (tmx <= tmy && tmx <= tmz) { t_in = tmx; ix += sx; tmx += dtx; walking = (unsigned)ix < (unsigned)g.nx; }
+            else if (tmy <= tmz)          { t_in = tmy; iy += sy; tmy += dty; walking = (unsigned)iy < (unsigned)g.ny; }
+            else                          { t_in = tmz; iz += sz; tmz += dtz; walking = (unsigned)iz < (unsigned)g.nz; }
+            if (t_in > bound * (1.0f + kTSlackRel) + kTSlackAbs || t_in > t_exit * (1.0f + 1e-5f) + 1e-6f || --budget < 0) walking = false;
+        }
+    }
+    drain();
+    return h;
+}
+static bool g_coop_check = false;
+static unsigned long long g_coop_rays = 0, g_coop_bad = 0;
+
 extern "C" {
 
 void hs_set_grid_shape(float flat, float wide) { g_grid_flat = flat; g_grid_wide = wide; }
 void hs_set_pad_reach(float reach) { g_pad_reach = reach; }
+// every octree ray of the following renders is also traced by coop_walk_host (both schedules) and compared with trace_walk's minimum
+void hs_coop_check(int on) { g_coop_check = on != 0; g_coop_rays = g_coop_bad = 0; }
+void hs_coop_check_result(unsigned long long *rays, unsigned long long *mismatches) { *rays = g_coop_rays; *mismatches = g_coop_bad; }
 // choose_grid as the build calls it (the product's default voxel shape): dims[3]; returns the voxel count
 unsigned hs_choose_grid(const float *lo, const float *hi, unsigned live, float density, int *dims) {
     GridView g;
@@ -215,6 +295,19 @@ static int render_core(const hs_sphere *sph, int n, const float *camera22, const
                         TraceCounters tcn{};
                         Hit h = p->use_octree ? trace_tree(sc, tv, &tv.planes[0][0], o, d, tcn)
                                               : trace_list(sc.geom, sc.tag, sc.n, o, d, tcn);
+                        if (g_coop_check && p->use_octree) {
+                            bool tie = false;
+                            const Hit m = trace_walk<kWalkMin>(sc, tv, &tv.planes[0][0], o, d, tcn, 0.0f, &tie);
+                            unsigned long long bad = 0;
+                            for (int eager = 0; eager < 2; eager++) {
+                                const CoopHit c2 = coop_walk_host(sc, tv, o, d, eager != 0);
+                                bad += !(c2.t == m.t && c2.tie == tie && (tie || c2.idx == m.idx));
+                            }
+#pragma omp atomic
+                            g_coop_rays += 1;
+#pragma omp atomic
+                            g_coop_bad += bad;
+                        }
                         if (h.idx >= 0) {
                             vec3f hp, hn, a, dn;
                             hit_point(geom[(size_t)h.idx], o, d, h.t, hp, hn);

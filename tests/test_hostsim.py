@@ -54,6 +54,23 @@ def test_voxel_shape_does_not_change_the_image(hostsim, O, flat, wide):
     assert np.array_equal(fb.view(np.uint32), ref.view(np.uint32))
 
 
+@pytest.mark.parametrize("n,spl,nx,ny,ns", [(488, 30, 120, 80, 3), (8000, 30, 96, 64, 2), (100000, 300, 160, 90, 2)])
+def test_cooperative_candidate_rule_returns_the_same_minimum(hostsim, O, n, spl, nx, ny, ns):
+    """k_render_coop offers a candidate only in the voxel that holds its root (exit cap), prunes by certain-hit bounds and evaluates
+    exactly later, in any order.  A host emulation of that rule, under the two extreme schedules, returns trace_walk's minimum
+    (and its tie flag) for every ray of these frames."""
+    hostsim.hs_coop_check(1)
+    try:
+        fb, ref, c, ctr = _run(hostsim, O, n, spl, True, nx, ny, ns)
+        rays, bad = C.c_ulonglong(0), C.c_ulonglong(0)
+        hostsim.hs_coop_check_result(C.byref(rays), C.byref(bad))
+    finally:
+        hostsim.hs_coop_check(0)
+    assert rays.value == c.rays and rays.value > 10000
+    assert bad.value == 0
+    assert np.array_equal(fb.view(np.uint32), ref.view(np.uint32))
+
+
 def test_choose_grid_shape_rule(hostsim):
     """Cubic voxels, except slab-shaped boxes from 40 k spheres: 1.5x the layers across the slab, 0.75x the columns along it."""
     def grid(lo, hi, live):
